@@ -1,0 +1,189 @@
+/*
+ * pbx.h -- C ABI of poissbox-b200: the B200 (sm_100a) implementation of the compact-scheme
+ * gradient / divergence / Laplacian hot path of 3decomp/poissbox, its batched tridiagonal solves,
+ * and the conjugate-gradient loop that drives the Laplacian.
+ *
+ * This is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (file:line relative to the reference tree); INTEGRATION.md shows the ISO_C_BINDING module and
+ * the PETSc MATSHELL glue a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - All arrays are IEEE fp64 in Fortran column-major order: f(i,j,k) <-> f[i + nx*(j + ny*k)],
+ *     df(i,j,k,c) adds c*nx*ny*nz (src/compact_schemes.f90:19-23,46).
+ *   - Every function returns 0 on success or a PBX_ERR_* code; PBX_ERR_SIZE is 7 on purpose: it
+ *     is what the reference reports with `stop 7` (src/compact_schemes.f90:177-180, 292-295).
+ *   - Caller owns every array; outputs are fully overwritten.  Scratch and coefficient tables
+ *     belong to a handle (pbx_create) -- there is no hidden global state except the per-thread
+ *     handle cache behind the *_host convenience calls.
+ *   - `*_device` calls take device pointers and are asynchronous on the handle's CUDA stream.
+ *     `*_host` calls take host pointers, stage H2D/D2H themselves and return when the result is
+ *     in the caller's buffer.
+ *   - There is no CPU fallback: without a CUDA device every compute call returns PBX_ERR_CUDA.
+ *   - One handle per rank/GPU; calls on one handle must not be issued concurrently.
+ */
+#ifndef PBX_H
+#define PBX_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBX_VERSION 100
+
+#define PBX_OK 0
+#define PBX_ERR_ARG 1         /* bad argument (null pointer, n too small, unknown enum) */
+#define PBX_ERR_CUDA 2        /* CUDA runtime error or no device; see pbx_last_error() */
+#define PBX_ERR_NCCL 3        /* NCCL error */
+#define PBX_ERR_UNSUPPORTED 4 /* valid request this build cannot serve */
+#define PBX_ERR_NOMEM 5
+#define PBX_ERR_SIZE 7        /* array-length mismatch: the reference's `stop 7` */
+
+/* Laplacian schedules.  Both compute src/compact_schemes.f90:17-37 (lapl = div(grad)).
+ *   REFERENCE  the reference's own order of operations (16 line-operator sweeps, sequential
+ *              Thomas + Sherman-Morrison per line, true division, no FMA contraction):
+ *              bit-identical to the CPU oracle.
+ *   FAST       one sweep per axis (the 1-D operators of different axes commute), each sweep a
+ *              chunked constant-coefficient recursion held in registers; agrees with REFERENCE to
+ *              a few 1e-16 of max|result| (not bit-identical; tests/test_parity_gpu.py). */
+#define PBX_MODE_FAST 0
+#define PBX_MODE_REFERENCE 1
+
+/* stagger argument of the 1-D/3-D operators, as in the reference's opt_stagger:
+ * -1 = cell -> vertex (default of grad_1d / interp_1d), +1 = vertex -> cell (div_1d, *_div). */
+#define PBX_STAGGER_BACKWARD (-1)
+#define PBX_STAGGER_FORWARD (+1)
+
+/* KSPConvergedReason values used by pbx_cg_solve (PETSc numbering) */
+#define PBX_CONVERGED_RTOL 2
+#define PBX_CONVERGED_ATOL 3
+#define PBX_DIVERGED_ITS (-3)
+#define PBX_DIVERGED_DTOL (-4)
+#define PBX_DIVERGED_INDEFINITE_MAT (-10)
+#define PBX_DIVERGED_NANORINF (-9)
+
+typedef struct pbx_handle_s *pbx_handle;
+
+int pbx_version(void);
+const char *pbx_error_string(int code);
+/* text of the last failure on the calling thread ("" if none) */
+const char *pbx_last_error(void);
+/* number of CUDA devices visible (0 when there is none or the driver is missing) */
+int pbx_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Lifecycle.  A handle binds a local brick nx x ny x nz_local, the grid spacings, a device, a
+ * stream and (optionally) an NCCL communicator for the z-slab decomposition.
+ * Replaces: the per-call allocate/deallocate of the reference (src/compact_schemes.f90:30,59,69,
+ * 183-185,225,235) and the shell-matrix context `mat_ctx` (src/poissbox.f90:17-20).
+ *   nccl_comm  NULL for a single GPU; otherwise an ncclComm_t whose rank r owns global planes
+ *              [r*nz, (r+1)*nz) of a periodic box of nz*nranks planes.
+ * ------------------------------------------------------------------------------------------- */
+int pbx_create(int nx, int ny, int nz, const double dx[3], int device, void *nccl_comm,
+               pbx_handle *h);
+int pbx_destroy(pbx_handle h);
+int pbx_set_mode(pbx_handle h, int mode);
+int pbx_get_mode(pbx_handle h, int *mode);
+/* cudaStream_t; NULL selects the legacy default stream */
+int pbx_set_stream(pbx_handle h, void *stream);
+int pbx_synchronize(pbx_handle h);
+/* sizes the handle was created with */
+int pbx_get_dims(pbx_handle h, int *nx, int *ny, int *nz);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+long long pbx_launch_count(pbx_handle h);
+
+/* NCCL bootstrap helpers so that a host language without NCCL bindings can build the
+ * communicator: rank 0 fills `id` (128 bytes), ships it to the other ranks by any means, and
+ * every rank calls pbx_comm_init_rank.  The returned pointer is an ncclComm_t. */
+int pbx_comm_unique_id(void *id128);
+int pbx_comm_init_rank(const void *id128, int nranks, int rank, int device, void **comm);
+int pbx_comm_destroy(void *comm);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3-D compact operators on device-resident fields (asynchronous on the handle's stream).
+ * ------------------------------------------------------------------------------------------- */
+/* compact_schemes::lapl  src/compact_schemes.f90:17-37;  also the body of the MATSHELL MatMult
+ * callback `mfmult` src/poissbox.f90:300-322 once it is re-pointed at the compact operator. */
+int pbx_lapl_device(pbx_handle h, const double *f, double *d2f);
+/* as above, and additionally *dot_dev (device double) <- sum f * d2f (the CG p.Ap, fused) */
+int pbx_lapl_dot_device(pbx_handle h, const double *f, double *d2f, double *dot_dev);
+/* compact_schemes::grad  src/compact_schemes.f90:42-88;  df has 3 components */
+int pbx_grad_device(pbx_handle h, const double *f, double *df);
+/* compact_schemes::div   src/compact_schemes.f90:207-257;  f has 3 components */
+int pbx_div_device(pbx_handle h, const double *f, double *df);
+/* compact_schemes::interp / interp_div  src/compact_schemes.f90:93-152 */
+int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched 1-D compact operators: one call applies grad_1d / interp_1d to `nlines` periodic lines
+ * of n points.  Point i of line l lives at base[l*line_stride + i*elem_stride] (in doubles), for
+ * both input and output, which must not overlap.
+ * Replaces: grad_1d :155-204, div_1d :260-268, interp_1d :271-319, interp_1d_div :322-329 and
+ * eval_1d_rhs :332-372 of src/compact_schemes.f90, looped over lines at :60-86 and :226-253.
+ * ------------------------------------------------------------------------------------------- */
+int pbx_grad_1d_batch_device(int n, long long nlines, long long elem_stride, long long line_stride,
+                             const double *f, double dx, double *df, int stagger, void *stream);
+int pbx_interp_1d_batch_device(int n, long long nlines, long long elem_stride,
+                               long long line_stride, const double *f, double *fi, int stagger,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched general-coefficient tridiagonal solves (module tridsol, src/tridsol.f90:16-18).
+ * a = sub-diagonal, b = DIAGONAL, c = super-diagonal, d = rhs/solution -- the reference's dummy
+ * names (its in-file comments swap b and c; tests/tridiag/test_tdma.f90:42-44 has it right).
+ * All four arrays share the layout base[l*line_stride + i*elem_stride].
+ *   tdma           :22-32   non-periodic; b is overwritten with the pivots exactly as :92 does
+ *   tdma_periodic  :34-74   Sherman-Morrison closure; b is left untouched
+ *   fwd_sweep      :76-96   b and d overwritten
+ *   bwd_sweep      :98-115  d overwritten
+ * ------------------------------------------------------------------------------------------- */
+int pbx_tdma_batch_device(int n, long long nlines, long long elem_stride, long long line_stride,
+                          const double *a, double *b, const double *c, double *d, void *stream);
+int pbx_tdma_periodic_batch_device(int n, long long nlines, long long elem_stride,
+                                   long long line_stride, const double *a, const double *b,
+                                   const double *c, double *d, void *stream);
+int pbx_fwd_sweep_batch_device(int n, long long nlines, long long elem_stride,
+                               long long line_stride, const double *a, double *b, const double *c,
+                               double *d, void *stream);
+int pbx_bwd_sweep_batch_device(int n, long long nlines, long long elem_stride,
+                               long long line_stride, const double *b, const double *c, double *d,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conjugate gradients on the compact Laplacian, entirely on the device, with the semantics of
+ * PETSc's `-ksp_type cg -pc_type none` as the reference's solve() sets it up
+ * (src/poissbox.f90:269-298: constant MatNullSpace on A, KSPSetFromOptions, KSPSolve):
+ * x0 = 0, z = r - mean(r), preconditioned norm ||z||_2, converged when
+ * ||z|| <= max(rtol*||z_0||, abstol), diverged at 1e4*||z_0|| or max_it.
+ *   hist  may be NULL; else receives ||z|| for iterations 0..its (at most nhist values).
+ * ------------------------------------------------------------------------------------------- */
+int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, double abstol,
+                        int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-pointer convenience variants (what the Fortran module bodies call).
+ * They use a cached handle for (nx,ny,nz,dx) on the current device, copy in, run, copy out.
+ * ------------------------------------------------------------------------------------------- */
+int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], double *d2f,
+                  int mode);
+int pbx_grad_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df);
+int pbx_div_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df);
+int pbx_interp_host(int nx, int ny, int nz, const double *f, double *fi, int stagger);
+/* single-line forms with the reference's size check (nf != ndf -> PBX_ERR_SIZE) */
+int pbx_grad_1d_host(int nf, const double *f, double dx, int ndf, double *df, int stagger);
+int pbx_interp_1d_host(int nf, const double *f, int nfi, double *fi, int stagger);
+int pbx_tdma_host(int n, const double *a, double *b, const double *c, double *d);
+int pbx_tdma_periodic_host(int n, const double *a, const double *b, const double *c, double *d);
+int pbx_fwd_sweep_host(int n, const double *a, double *b, const double *c, double *d);
+int pbx_bwd_sweep_host(int n, const double *b, const double *c, double *d);
+int pbx_cg_solve_host(int nx, int ny, int nz, const double dx[3], const double *b, double *x,
+                      double rtol, double abstol, int maxit, int mode, int *its, double *rnorm,
+                      int *reason, double *hist, int nhist);
+/* drop the cached handles of the *_host calls (frees their device memory) */
+int pbx_host_cache_clear(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBX_H */

@@ -449,7 +449,7 @@ int orc_cg_solve(int nx, int ny, int nz, const double dx[3], const double *b, do
             dpi = vdot(N, p, w);
             betaold = beta;
             if (dpi == 0.0 || (i > 0 && ((dpi > 0) - (dpi < 0)) * ((dpiold > 0) - (dpiold < 0)) < 0)) {
-                why = -8;
+                why = -10; /* KSP_DIVERGED_INDEFINITE_MAT */
                 break;
             }
             {

@@ -60,7 +60,7 @@ int orc_get_threads(void);
 
 /* ---- CG with PETSc KSPCG semantics on the oracle Laplacian (PC none, constant null space) ----
  * x0 = 0.  Returns the iteration count; *reason > 0 converged (2 = rtol, 3 = atol),
- * < 0 diverged (-3 = max_it, -8 = indefinite operator).  hist (may be NULL) receives the
+ * < 0 diverged (-3 = max_it, -4 = dtol, -8 = indefinite PC, -9 = NaN, -10 = indefinite operator).  hist (may be NULL) receives the
  * residual norm at iterations 0..its, at most nhist entries. */
 int orc_cg_solve(int nx, int ny, int nz, const double dx[3], const double *b, double *x,
                  double rtol, double abstol, int maxit, double *rnorm, int *reason, double *hist,

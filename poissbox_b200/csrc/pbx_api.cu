@@ -1,0 +1,672 @@
+// pbx_api.cu -- the C ABI (include/pbx.h): handle lifecycle, operator drivers for both schedules,
+// host-pointer convenience variants.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "pbx_internal.h"
+
+namespace pbx {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e),
+             what, file, line);
+    g_last_error = buf;
+    return PBX_ERR_CUDA;
+}
+
+int ensure_scratch(pbx_handle_s *h, int count)
+{
+    const size_t bytes = sizeof(double) * (size_t)h->nx * h->ny * h->nz;
+    while (h->nscratch < count) {
+        if (h->nscratch >= 10) return PBX_ERR_NOMEM;
+        PBX_CUDA(cudaMalloc(&h->scratch[h->nscratch], bytes));
+        ++h->nscratch;
+    }
+    return PBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// REFERENCE schedule drivers: the reference's own stage order.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Lines {
+    int n;
+    long long nl1, nl2, es, ls1, ls2;
+};
+
+Lines lines_of(const pbx_handle_s *h, int dir)
+{
+    const long long nx = h->nx, ny = h->ny, nz = h->nz;
+    switch (dir) {
+    case 0: return {h->nx, ny, nz, 1, nx, nx * ny};        // x lines: (j,k)
+    case 1: return {h->ny, nx, nz, nx, 1, nx * ny};        // y lines: (i,k)
+    default: return {h->nz, nx, ny, nx * ny, 1, nx};       // z lines: (i,j)
+    }
+}
+
+int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in, double *out)
+{
+    Lines L = lines_of(h, dir);
+    return ref_line_op(h->stream, L.n, L.nl1, L.nl2, L.es, L.ls1, L.ls2, kind, stagger, h->dx[dir],
+                       h->ref[dir][kind], in, out, &h->launches);
+}
+
+}  // namespace
+
+// src/compact_schemes.f90:42-88 (Z -> Y -> X, backward stagger).  S = 5 scratch fields.
+static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2, double *o3)
+{
+    PBX_TRY(ensure_scratch(h, 5));
+    double **S = h->scratch;
+    const int B = PBX_STAGGER_BACKWARD;
+    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0]));      // dff1 (= dff2, :63)
+    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1]));       // dff3
+    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[0], S[2]));   // dfe1
+    PBX_TRY(line_op(h, 1, OP_DERIV, B, S[0], S[3]));    // dfe2
+    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[1], S[4]));   // dfe3
+    PBX_TRY(line_op(h, 0, OP_DERIV, B, S[2], o1));      // df1
+    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[3], o2));     // df2
+    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[4], o3));     // df3
+    return PBX_OK;
+}
+
+// src/compact_schemes.f90:207-257 (X -> Y -> Z, forward stagger).  i1..i3 may be scratch 0..2.
+static int div_stages(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
+                      double *out)
+{
+    PBX_TRY(ensure_scratch(h, 5));
+    double **S = h->scratch;
+    const int F = PBX_STAGGER_FORWARD;
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    // order chosen so that an input living in S[0..2] is consumed before its slot is reused
+    PBX_TRY(line_op(h, 0, OP_DERIV, F, i1, S[3]));      // dfe1
+    PBX_TRY(line_op(h, 0, OP_INTERP, F, i2, S[4]));     // dfe2
+    double *e3 = S[0];                                  // i1 (possibly S[0]) is consumed by now
+    PBX_TRY(line_op(h, 0, OP_INTERP, F, i3, e3));       // dfe3
+    PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1]));   // dff1
+    PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2]));    // dff2
+    PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3]));     // dff3
+    PBX_TRY(ref_add(h->stream, N, S[1], S[2], S[4], &h->launches));   // :249
+    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0]));   // dfc
+    PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], out));     // df
+    PBX_TRY(ref_add(h->stream, N, out, S[0], out, &h->launches));     // :251
+    return PBX_OK;
+}
+
+int lapl_reference(pbx_handle_s *h, const double *f, double *out)
+{
+    PBX_TRY(ensure_scratch(h, 5));
+    double **S = h->scratch;
+    PBX_TRY(grad_stages(h, f, S[0], S[1], S[2]));
+    return div_stages(h, S[0], S[1], S[2], out);
+}
+
+int grad_reference(pbx_handle_s *h, const double *f, double *df)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    return grad_stages(h, f, df, df + N, df + 2 * N);
+}
+
+int div_reference(pbx_handle_s *h, const double *f, double *out)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    return div_stages(h, f, f + N, f + 2 * N, out);
+}
+
+// src/compact_schemes.f90:93-142
+int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger)
+{
+    PBX_TRY(ensure_scratch(h, 2));
+    double **S = h->scratch;
+    PBX_TRY(line_op(h, 2, OP_INTERP, stagger, f, S[0]));
+    PBX_TRY(line_op(h, 1, OP_INTERP, stagger, S[0], S[1]));
+    PBX_TRY(line_op(h, 0, OP_INTERP, stagger, S[1], fi));
+    return PBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST schedule driver
+// ------------------------------------------------------------------------------------------------
+int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)
+{
+    if (!h->fast_ok) {
+        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; ny, nz <= 512)");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) {
+        set_last_error("FAST schedule needs 16-byte aligned fields");
+        return PBX_ERR_ARG;
+    }
+    PBX_TRY(ensure_scratch(h, 2));
+    double **S = h->scratch;
+    Brick g{h->nx, h->ny, h->nz};
+    PBX_TRY(fast_xpass(h->stream, g, h->fc, f, S[0], S[1], &h->launches));
+    // the y pass runs in place: every CTA reads its whole tile before it writes it
+    PBX_TRY(fast_ypass(h->stream, g, h->fc, S[0], S[1], S[0], S[1], &h->launches));
+    PBX_TRY(fast_zpass(h->stream, g, h->fc, S[0], S[1], out, p, partials, nullptr, &h->launches));
+    return PBX_OK;
+}
+
+}  // namespace pbx
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace pbx;
+
+extern "C" {
+
+int pbx_version(void) { return PBX_VERSION; }
+
+const char *pbx_error_string(int code)
+{
+    switch (code) {
+    case PBX_OK: return "success";
+    case PBX_ERR_ARG: return "invalid argument";
+    case PBX_ERR_CUDA: return "CUDA error or no CUDA device";
+    case PBX_ERR_NCCL: return "NCCL error";
+    case PBX_ERR_UNSUPPORTED: return "unsupported configuration";
+    case PBX_ERR_NOMEM: return "out of memory";
+    case PBX_ERR_SIZE: return "array size mismatch";
+    default: return "unknown error";
+    }
+}
+
+const char *pbx_last_error(void) { return g_last_error.c_str(); }
+
+int pbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pbx_create(int nx, int ny, int nz, const double dx[3], int device, void *nccl_comm,
+               pbx_handle *out)
+{
+    if (!out || !dx) return PBX_ERR_ARG;
+    *out = nullptr;
+    if (nx < 3 || ny < 3 || nz < 3 || !(dx[0] > 0) || !(dx[1] > 0) || !(dx[2] > 0)) {
+        set_last_error("pbx_create: need nx, ny, nz >= 3 and positive spacings");
+        return PBX_ERR_ARG;
+    }
+    if (pbx_device_count() <= 0) {
+        set_last_error("pbx_create: no CUDA device (there is no CPU fallback)");
+        return PBX_ERR_CUDA;
+    }
+    PBX_CUDA(cudaSetDevice(device));
+    pbx_handle_s *h = new pbx_handle_s();
+    h->nx = nx;
+    h->ny = ny;
+    h->nz = nz;
+    for (int d = 0; d < 3; ++d) h->dx[d] = dx[d];
+    h->device = device;
+    h->comm = nccl_comm;
+    const int nn[3] = {nx, ny, nz};
+    for (int d = 0; d < 3; ++d) {
+        make_composite_coef(OP_DERIV, dx[d], &h->fc.D[d]);
+        for (int k = 0; k < 2; ++k) {
+            int rc = make_ref_tables(nn[d], scheme_alpha((OpKind)k), &h->ref[d][k]);
+            if (rc != PBX_OK) {
+                pbx_destroy(h);
+                return rc;
+            }
+        }
+    }
+    make_composite_coef(OP_INTERP, 1.0, &h->fc.M);
+    h->fast_ok = fast_supported(nx, ny, nz);
+    h->mode = h->fast_ok ? PBX_MODE_FAST : PBX_MODE_REFERENCE;
+    if (nccl_comm) {
+        int rc = dist_attach(h);
+        if (rc != PBX_OK) {
+            pbx_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return PBX_OK;
+}
+
+int pbx_destroy(pbx_handle h)
+{
+    if (!h) return PBX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int d = 0; d < 3; ++d)
+        for (int k = 0; k < 2; ++k) free_ref_tables(&h->ref[d][k]);
+    for (int i = 0; i < h->nscratch; ++i) cudaFree(h->scratch[i]);
+    cg_free(h);
+    dist_free(h);
+    delete h;
+    return PBX_OK;
+}
+
+int pbx_set_mode(pbx_handle h, int mode)
+{
+    if (!h || (mode != PBX_MODE_FAST && mode != PBX_MODE_REFERENCE)) return PBX_ERR_ARG;
+    if (mode == PBX_MODE_FAST && !h->fast_ok) {
+        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; ny, nz <= 512)");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    if (mode == PBX_MODE_REFERENCE && h->nranks > 1) {
+        set_last_error("REFERENCE schedule is single-rank (as the reference itself is)");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    h->mode = mode;
+    return PBX_OK;
+}
+
+int pbx_get_mode(pbx_handle h, int *mode)
+{
+    if (!h || !mode) return PBX_ERR_ARG;
+    *mode = h->mode;
+    return PBX_OK;
+}
+
+int pbx_set_stream(pbx_handle h, void *stream)
+{
+    if (!h) return PBX_ERR_ARG;
+    h->stream = (cudaStream_t)stream;
+    return PBX_OK;
+}
+
+int pbx_synchronize(pbx_handle h)
+{
+    if (!h) return PBX_ERR_ARG;
+    PBX_CUDA(cudaStreamSynchronize(h->stream));
+    return PBX_OK;
+}
+
+int pbx_get_dims(pbx_handle h, int *nx, int *ny, int *nz)
+{
+    if (!h) return PBX_ERR_ARG;
+    if (nx) *nx = h->nx;
+    if (ny) *ny = h->ny;
+    if (nz) *nz = h->nz;
+    return PBX_OK;
+}
+
+long long pbx_launch_count(pbx_handle h) { return h ? h->launches : 0; }
+
+// ---- 3-D operators -----------------------------------------------------------------------------
+int pbx_lapl_device(pbx_handle h, const double *f, double *d2f)
+{
+    if (!h || !f || !d2f || f == d2f) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    if (h->nranks > 1) return dist_lapl(h, f, d2f, nullptr, nullptr);
+    return h->mode == PBX_MODE_FAST ? lapl_fast(h, f, d2f, nullptr, nullptr)
+                                    : lapl_reference(h, f, d2f);
+}
+
+int pbx_lapl_dot_device(pbx_handle h, const double *f, double *d2f, double *dot_dev)
+{
+    if (!h || !f || !d2f || !dot_dev || f == d2f) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return cg_lapl_dot(h, f, d2f, dot_dev);
+}
+
+int pbx_grad_device(pbx_handle h, const double *f, double *df)
+{
+    if (!h || !f || !df) return PBX_ERR_ARG;
+    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return grad_reference(h, f, df);
+}
+
+int pbx_div_device(pbx_handle h, const double *f, double *df)
+{
+    if (!h || !f || !df) return PBX_ERR_ARG;
+    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return div_reference(h, f, df);
+}
+
+int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger)
+{
+    if (!h || !f || !fi || (stagger != -1 && stagger != 1)) return PBX_ERR_ARG;
+    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return interp_reference(h, f, fi, stagger);
+}
+
+// ---- batched 1-D operators ---------------------------------------------------------------------
+namespace {
+
+std::mutex g_tab_mutex;
+std::map<std::tuple<int, int, int>, RefLineTables> g_tabs;   // (device, n, kind)
+
+int cached_tables(int n, OpKind kind, const RefLineTables **out)
+{
+    int dev = 0;
+    PBX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mutex);
+    auto key = std::make_tuple(dev, n, (int)kind);
+    auto it = g_tabs.find(key);
+    if (it == g_tabs.end()) {
+        RefLineTables t;
+        PBX_TRY(make_ref_tables(n, scheme_alpha(kind), &t));
+        it = g_tabs.emplace(key, t).first;
+    }
+    *out = &it->second;
+    return PBX_OK;
+}
+
+int line_batch(int n, long long nl, long long es, long long ls, OpKind kind, const double *f,
+               double dx, double *o, int stagger, void *stream)
+{
+    if (!f || !o || nl < 0 || (stagger != -1 && stagger != 1)) return PBX_ERR_ARG;
+    if (n < 3) {
+        set_last_error("compact line operators need n >= 3");
+        return PBX_ERR_ARG;
+    }
+    if (pbx_device_count() <= 0) {
+        set_last_error("no CUDA device (there is no CPU fallback)");
+        return PBX_ERR_CUDA;
+    }
+    if (nl == 0) return PBX_OK;
+    const RefLineTables *t = nullptr;
+    PBX_TRY(cached_tables(n, kind, &t));
+    return ref_line_op((cudaStream_t)stream, n, nl, 1, es, ls, 0, kind, stagger, dx, *t, f, o,
+                       nullptr);
+}
+
+}  // namespace
+
+int pbx_grad_1d_batch_device(int n, long long nlines, long long es, long long ls, const double *f,
+                             double dx, double *df, int stagger, void *stream)
+{
+    if (!(dx > 0)) return PBX_ERR_ARG;
+    return line_batch(n, nlines, es, ls, OP_DERIV, f, dx, df, stagger, stream);
+}
+
+int pbx_interp_1d_batch_device(int n, long long nlines, long long es, long long ls,
+                               const double *f, double *fi, int stagger, void *stream)
+{
+    return line_batch(n, nlines, es, ls, OP_INTERP, f, 1.0, fi, stagger, stream);
+}
+
+// ---- batched tridiagonal solves ----------------------------------------------------------------
+#define PBX_NEED_DEVICE()                                                   \
+    do {                                                                    \
+        if (pbx_device_count() <= 0) {                                      \
+            set_last_error("no CUDA device (there is no CPU fallback)");    \
+            return PBX_ERR_CUDA;                                            \
+        }                                                                   \
+    } while (0)
+
+int pbx_tdma_batch_device(int n, long long nl, long long es, long long ls, const double *a,
+                          double *b, const double *c, double *d, void *stream)
+{
+    if (!a || !b || !c || !d) return PBX_ERR_ARG;
+    PBX_NEED_DEVICE();
+    PBX_TRY(tdma_fwd_batch((cudaStream_t)stream, n, nl, es, ls, a, b, c, d));
+    return tdma_bwd_batch((cudaStream_t)stream, n, nl, es, ls, b, c, d);
+}
+
+int pbx_tdma_periodic_batch_device(int n, long long nl, long long es, long long ls,
+                                   const double *a, const double *b, const double *c, double *d,
+                                   void *stream)
+{
+    if (!a || !b || !c || !d) return PBX_ERR_ARG;
+    PBX_NEED_DEVICE();
+    return tdma_periodic_batch((cudaStream_t)stream, n, nl, es, ls, a, b, c, d);
+}
+
+int pbx_fwd_sweep_batch_device(int n, long long nl, long long es, long long ls, const double *a,
+                               double *b, const double *c, double *d, void *stream)
+{
+    if (!a || !b || !c || !d) return PBX_ERR_ARG;
+    PBX_NEED_DEVICE();
+    return tdma_fwd_batch((cudaStream_t)stream, n, nl, es, ls, a, b, c, d);
+}
+
+int pbx_bwd_sweep_batch_device(int n, long long nl, long long es, long long ls, const double *b,
+                               const double *c, double *d, void *stream)
+{
+    if (!b || !c || !d) return PBX_ERR_ARG;
+    PBX_NEED_DEVICE();
+    return tdma_bwd_batch((cudaStream_t)stream, n, nl, es, ls, b, c, d);
+}
+
+// ---- CG ----------------------------------------------------------------------------------------
+int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, double abstol,
+                        int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist)
+{
+    if (!h || !b || !x || maxit < 0) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return cg_solve(h, b, x, rtol, abstol, maxit, its, rnorm, reason, hist, nhist);
+}
+
+}  // extern "C"
+
+// ---- host-pointer convenience variants ---------------------------------------------------------
+namespace {
+
+struct HostEntry {
+    pbx_handle h = nullptr;
+    double *din = nullptr, *dout = nullptr;   // 3 fields each
+    size_t N = 0;
+};
+std::mutex g_host_mutex;
+std::vector<HostEntry> g_host;
+
+int host_entry(int nx, int ny, int nz, const double dx[3], HostEntry **out)
+{
+    int dev = 0;
+    if (pbx_device_count() <= 0) {
+        set_last_error("no CUDA device (there is no CPU fallback)");
+        return PBX_ERR_CUDA;
+    }
+    PBX_CUDA(cudaGetDevice(&dev));
+    for (auto &e : g_host) {
+        pbx_handle_s *h = e.h;
+        if (h->nx == nx && h->ny == ny && h->nz == nz && h->device == dev && h->dx[0] == dx[0] &&
+            h->dx[1] == dx[1] && h->dx[2] == dx[2]) {
+            *out = &e;
+            return PBX_OK;
+        }
+    }
+    if (g_host.size() >= 4) {   // small LRU-less cache: drop the oldest
+        HostEntry &o = g_host.front();
+        cudaFree(o.din);
+        cudaFree(o.dout);
+        pbx_destroy(o.h);
+        g_host.erase(g_host.begin());
+    }
+    HostEntry e;
+    PBX_TRY(pbx_create(nx, ny, nz, dx, dev, nullptr, &e.h));
+    e.N = (size_t)nx * ny * nz;
+    if (cudaMalloc(&e.din, 3 * e.N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&e.dout, 3 * e.N * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(e.din);
+        pbx_destroy(e.h);
+        set_last_error("host staging allocation failed");
+        return PBX_ERR_NOMEM;
+    }
+    g_host.push_back(e);
+    *out = &g_host.back();
+    return PBX_OK;
+}
+
+template <class Fn>
+int host_run(int nx, int ny, int nz, const double dx[3], const double *in, int nin, double *out,
+             int nout, Fn fn)
+{
+    if (!in || !out || !dx) return PBX_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_host_mutex);
+    HostEntry *e = nullptr;
+    PBX_TRY(host_entry(nx, ny, nz, dx, &e));
+    cudaStream_t s = e->h->stream;
+    PBX_CUDA(cudaMemcpyAsync(e->din, in, nin * e->N * sizeof(double), cudaMemcpyHostToDevice, s));
+    PBX_TRY(fn(e));
+    PBX_CUDA(cudaMemcpyAsync(out, e->dout, nout * e->N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PBX_CUDA(cudaStreamSynchronize(s));
+    return PBX_OK;
+}
+
+// single-line / small-batch host staging
+struct DevBuf {
+    double *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n)
+    {
+        PBX_CUDA(cudaMalloc(&p, n * sizeof(double)));
+        return PBX_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], double *d2f,
+                  int mode)
+{
+    return host_run(nx, ny, nz, dx, f, 1, d2f, 1, [&](HostEntry *e) {
+        int m = mode;
+        if (m == PBX_MODE_FAST && !e->h->fast_ok) m = PBX_MODE_REFERENCE;
+        PBX_TRY(pbx_set_mode(e->h, m));
+        return pbx_lapl_device(e->h, e->din, e->dout);
+    });
+}
+
+int pbx_grad_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df)
+{
+    return host_run(nx, ny, nz, dx, f, 1, df, 3,
+                    [&](HostEntry *e) { return pbx_grad_device(e->h, e->din, e->dout); });
+}
+
+int pbx_div_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df)
+{
+    return host_run(nx, ny, nz, dx, f, 3, df, 1,
+                    [&](HostEntry *e) { return pbx_div_device(e->h, e->din, e->dout); });
+}
+
+int pbx_interp_host(int nx, int ny, int nz, const double *f, double *fi, int stagger)
+{
+    const double dx[3] = {1.0, 1.0, 1.0};
+    return host_run(nx, ny, nz, dx, f, 1, fi, 1, [&](HostEntry *e) {
+        return pbx_interp_device(e->h, e->din, e->dout, stagger);
+    });
+}
+
+static int line_host(int nf, const double *f, double dx, int nout, double *o, int stagger,
+                     bool deriv)
+{
+    if (!f || !o) return PBX_ERR_ARG;
+    if (nf != nout) {   // src/compact_schemes.f90:177-180, 292-295
+        set_last_error("ERROR: periodic gradient is same length as field!");
+        return PBX_ERR_SIZE;
+    }
+    PBX_NEED_DEVICE();
+    DevBuf in, out;
+    PBX_TRY(in.alloc(nf));
+    PBX_TRY(out.alloc(nf));
+    PBX_CUDA(cudaMemcpy(in.p, f, nf * sizeof(double), cudaMemcpyHostToDevice));
+    if (deriv)
+        PBX_TRY(pbx_grad_1d_batch_device(nf, 1, 1, nf, in.p, dx, out.p, stagger, nullptr));
+    else
+        PBX_TRY(pbx_interp_1d_batch_device(nf, 1, 1, nf, in.p, out.p, stagger, nullptr));
+    PBX_CUDA(cudaMemcpy(o, out.p, nf * sizeof(double), cudaMemcpyDeviceToHost));
+    return PBX_OK;
+}
+
+int pbx_grad_1d_host(int nf, const double *f, double dx, int ndf, double *df, int stagger)
+{
+    return line_host(nf, f, dx, ndf, df, stagger, true);
+}
+
+int pbx_interp_1d_host(int nf, const double *f, int nfi, double *fi, int stagger)
+{
+    return line_host(nf, f, 1.0, nfi, fi, stagger, false);
+}
+
+namespace {
+// which: 0 tdma, 1 periodic, 2 fwd, 3 bwd
+int tri_host(int which, int n, const double *a, double *b, const double *c, double *d)
+{
+    if (!b || !c || !d || (which != 3 && !a) || n < 1) return PBX_ERR_ARG;
+    PBX_NEED_DEVICE();
+    DevBuf buf;
+    PBX_TRY(buf.alloc(4 * (size_t)n));
+    double *da = buf.p, *db = da + n, *dc = db + n, *dd = dc + n;
+    const size_t by = n * sizeof(double);
+    if (a) PBX_CUDA(cudaMemcpy(da, a, by, cudaMemcpyHostToDevice));
+    PBX_CUDA(cudaMemcpy(db, b, by, cudaMemcpyHostToDevice));
+    PBX_CUDA(cudaMemcpy(dc, c, by, cudaMemcpyHostToDevice));
+    PBX_CUDA(cudaMemcpy(dd, d, by, cudaMemcpyHostToDevice));
+    int rc = PBX_OK;
+    switch (which) {
+    case 0: rc = pbx_tdma_batch_device(n, 1, 1, n, da, db, dc, dd, nullptr); break;
+    case 1: rc = pbx_tdma_periodic_batch_device(n, 1, 1, n, da, db, dc, dd, nullptr); break;
+    case 2: rc = pbx_fwd_sweep_batch_device(n, 1, 1, n, da, db, dc, dd, nullptr); break;
+    default: rc = pbx_bwd_sweep_batch_device(n, 1, 1, n, db, dc, dd, nullptr); break;
+    }
+    PBX_TRY(rc);
+    PBX_CUDA(cudaMemcpy(d, dd, by, cudaMemcpyDeviceToHost));
+    if (which == 0 || which == 2) PBX_CUDA(cudaMemcpy(b, db, by, cudaMemcpyDeviceToHost));
+    return PBX_OK;
+}
+}  // namespace
+
+int pbx_tdma_host(int n, const double *a, double *b, const double *c, double *d)
+{
+    return tri_host(0, n, a, b, c, d);
+}
+int pbx_tdma_periodic_host(int n, const double *a, const double *b, const double *c, double *d)
+{
+    return tri_host(1, n, a, const_cast<double *>(b), c, d);
+}
+int pbx_fwd_sweep_host(int n, const double *a, double *b, const double *c, double *d)
+{
+    return tri_host(2, n, a, b, c, d);
+}
+int pbx_bwd_sweep_host(int n, const double *b, const double *c, double *d)
+{
+    return tri_host(3, n, nullptr, const_cast<double *>(b), c, d);
+}
+
+int pbx_cg_solve_host(int nx, int ny, int nz, const double dx[3], const double *b, double *x,
+                      double rtol, double abstol, int maxit, int mode, int *its, double *rnorm,
+                      int *reason, double *hist, int nhist)
+{
+    return host_run(nx, ny, nz, dx, b, 1, x, 1, [&](HostEntry *e) {
+        int m = mode;
+        if (m == PBX_MODE_FAST && !e->h->fast_ok) m = PBX_MODE_REFERENCE;
+        PBX_TRY(pbx_set_mode(e->h, m));
+        return pbx_cg_solve_device(e->h, e->din, e->dout, rtol, abstol, maxit, its, rnorm, reason,
+                                   hist, nhist);
+    });
+}
+
+int pbx_host_cache_clear(void)
+{
+    std::lock_guard<std::mutex> lk(g_host_mutex);
+    for (auto &e : g_host) {
+        cudaFree(e.din);
+        cudaFree(e.dout);
+        pbx_destroy(e.h);
+    }
+    g_host.clear();
+    return PBX_OK;
+}
+
+}  // extern "C"

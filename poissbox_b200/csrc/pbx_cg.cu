@@ -1,0 +1,440 @@
+// pbx_cg.cu -- conjugate gradients on the compact Laplacian, resident on the device.
+//
+// Semantics: PETSc KSPCG as the reference's solve() configures it (src/poissbox.f90:269-298:
+// constant MatNullSpace attached to A, KSPSetFromOptions, KSPSolve) with `-ksp_type cg
+// -pc_type none`: zero initial guess, z = r - mean(r) (the "preconditioner apply" followed by
+// null-space removal), preconditioned norm ||z||_2, beta = z.r, default convergence test.
+// PETSc is third-party and not vendored by the reference; the loop below follows its published
+// algorithm; the test-side CPU restatement of the same loop lives under oracle/.
+//
+// Per iteration (PC none) the vector work is two fused kernels,
+//   update   x += a p ; r -= a w ; partial sums of (r - m0), (r - m0)^2        48 B/DoF
+//   pupdate  p = (r - m) + b p                                                 24 B/DoF
+// and p.w comes out of the Laplacian's z pass, so an iteration moves 80 + 72 = 152 B/DoF.
+// All scalars (a, b, mean, norms, status) stay in a device block; the host only reads back the
+// status word, one iteration late, so there is no host synchronisation on the critical path.
+// Reductions are two-stage with a fixed shape (per-CTA partials, then one CTA), so the iteration
+// count is reproducible run to run.
+//
+// Because mean(r) is invariant in exact arithmetic, the sums are taken about the mean of b (m0):
+//   mean = m0 + S1/N ,  ||z||^2 = S2 - S1^2/N   with S1 = sum(r - m0), S2 = sum (r - m0)^2,
+// which avoids the cancellation a raw sum(r^2) - N mean^2 would suffer when mean(b) != 0.
+#include <cmath>
+
+#include "pbx_internal.h"
+
+namespace pbx {
+
+namespace {
+
+enum {
+    SC_M0 = 0, SC_S1, SC_S2, SC_PW, SC_BETA, SC_BETAOLD, SC_A, SC_B, SC_DP, SC_DP0, SC_TTOL,
+    SC_PWOLD, SC_STATUS, SC_IT, SC_RTOL, SC_ABSTOL, SC_MEAN, SC_MAXIT, SC_NTOT, SC_COUNT
+};
+
+constexpr int VT = 256;
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    // fixed-shape: warp shuffle tree, then warp 0 over the warp sums (blockDim.x == VT)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < VT / 32 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    }
+    return s;   // valid in thread 0
+}
+
+// each CTA owns a contiguous slice so that the summation order is fixed
+__device__ __forceinline__ void slice(size_t N, size_t *lo, size_t *hi)
+{
+    size_t per = (N + gridDim.x - 1) / gridDim.x;
+    per = (per + 1) & ~(size_t)1;
+    *lo = per * blockIdx.x;
+    *hi = *lo + per < N ? *lo + per : N;
+    if (*lo > N) *lo = N;
+}
+
+__global__ void __launch_bounds__(VT) k_sum(size_t N, const double *__restrict__ b,
+                                            double *__restrict__ part)
+{
+    __shared__ double sh[VT / 32];
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += VT) s += b[i];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// r = b ; x = 0 ; p = b - m0 ; partial sums about m0
+__global__ void __launch_bounds__(VT)
+k_init(size_t N, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r,
+       double *__restrict__ p, const double *__restrict__ sc, double *__restrict__ part, int np)
+{
+    __shared__ double sh[VT / 32];
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    const double m0 = sc[SC_M0];
+    double s1 = 0.0, s2 = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += VT) {
+        double v = b[i];
+        double t = v - m0;
+        x[i] = 0.0;
+        r[i] = v;
+        p[i] = t;
+        s1 += t;
+        s2 = fma(t, t, s2);
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = s1;
+        part[np + blockIdx.x] = s2;
+    }
+}
+
+// x += a p ; r -= a w ; partial sums of r - m0
+__global__ void __launch_bounds__(VT)
+k_update(size_t N, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+         const double *__restrict__ w, const double *__restrict__ sc, double *__restrict__ part,
+         int np)
+{
+    __shared__ double sh[VT / 32];
+    if (sc[SC_STATUS] != 0.0) return;
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    const double a = sc[SC_A], m0 = sc[SC_M0];
+    double s1 = 0.0, s2 = 0.0;
+    // two elements per thread per trip: slices start at even indices and the fields are 16-byte
+    // aligned, so the double2 accesses are aligned
+    size_t i = lo + 2 * (size_t)threadIdx.x;
+    for (; i + 1 < hi; i += 2 * VT) {
+        double2 xv = *reinterpret_cast<const double2 *>(x + i);
+        double2 rv = *reinterpret_cast<const double2 *>(r + i);
+        double2 pv = *reinterpret_cast<const double2 *>(p + i);
+        double2 wv = *reinterpret_cast<const double2 *>(w + i);
+        xv.x = fma(a, pv.x, xv.x);
+        xv.y = fma(a, pv.y, xv.y);
+        rv.x = fma(-a, wv.x, rv.x);
+        rv.y = fma(-a, wv.y, rv.y);
+        *reinterpret_cast<double2 *>(x + i) = xv;
+        *reinterpret_cast<double2 *>(r + i) = rv;
+        double t0 = rv.x - m0, t1 = rv.y - m0;
+        s1 += t0 + t1;
+        s2 = fma(t0, t0, fma(t1, t1, s2));
+    }
+    if (i < hi) {
+        double xv = fma(a, p[i], x[i]);
+        double rv = fma(-a, w[i], r[i]);
+        x[i] = xv;
+        r[i] = rv;
+        double t = rv - m0;
+        s1 += t;
+        s2 = fma(t, t, s2);
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = s1;
+        part[np + blockIdx.x] = s2;
+    }
+}
+
+// p = (r - mean) + b p
+__global__ void __launch_bounds__(VT)
+k_pupdate(size_t N, const double *__restrict__ r, double *__restrict__ p,
+          const double *__restrict__ sc)
+{
+    if (sc[SC_STATUS] != 0.0) return;
+    const double m = sc[SC_MEAN], b = sc[SC_B];
+    size_t st = (size_t)gridDim.x * VT * 2;
+    size_t i = ((size_t)blockIdx.x * VT + threadIdx.x) * 2;
+    for (; i + 1 < N; i += st) {
+        double2 rv = *reinterpret_cast<const double2 *>(r + i);
+        double2 pv = *reinterpret_cast<const double2 *>(p + i);
+        pv.x = fma(b, pv.x, rv.x - m);
+        pv.y = fma(b, pv.y, rv.y - m);
+        *reinterpret_cast<double2 *>(p + i) = pv;
+    }
+    if (i < N) p[i] = fma(b, p[i], r[i] - m);
+}
+
+// sum `cnt` partials of each of `narr` arrays (`stride` apart) into dst[0..narr) (one CTA, fixed order)
+__global__ void __launch_bounds__(VT)
+k_reduce(const double *__restrict__ part, int cnt, int stride, int narr, double *__restrict__ dst,
+         const double *__restrict__ sc, int guarded)
+{
+    __shared__ double sh[VT / 32];
+    if (guarded && sc[SC_STATUS] != 0.0) return;
+    for (int a = 0; a < narr; ++a) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < cnt; i += VT) s += part[a * stride + i];
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) dst[a] = s;
+        __syncthreads();
+    }
+}
+
+// the scalar logic of the KSPCG loop; one thread
+//   phase 0: m0 = S1 / N                     (S1 = sum b)
+//   phase 1: initial residual norm / test    (S1, S2 about m0)
+//   phase 2: a = beta / (p.w), indefiniteness test
+//   phase 3: new residual norm, test, b = beta/beta_old
+__global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double N = sc[SC_NTOT];
+    if (phase == 0) {
+        sc[SC_M0] = sc[SC_S1] / N;
+        return;
+    }
+    if (sc[SC_STATUS] != 0.0) return;
+    if (phase == 2) {
+        const double dpi = sc[SC_PW], dpiold = sc[SC_PWOLD];
+        const int i = (int)sc[SC_IT];
+        const double beta = sc[SC_BETA];
+        if (beta == 0.0) {
+            sc[SC_IT] = i + 1;
+            sc[SC_STATUS] = PBX_CONVERGED_ATOL;
+            return;
+        }
+        if (dpi != dpi) {
+            sc[SC_IT] = i + 1;
+            sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
+            return;
+        }
+        const double sg = (dpi > 0) - (dpi < 0), sgo = (dpiold > 0) - (dpiold < 0);
+        if (dpi == 0.0 || (i > 0 && sg * sgo < 0.0)) {
+            sc[SC_IT] = i + 1;
+            sc[SC_STATUS] = PBX_DIVERGED_INDEFINITE_MAT;
+            return;
+        }
+        sc[SC_PWOLD] = dpi;
+        sc[SC_A] = beta / dpi;
+        return;
+    }
+    // phases 1 and 3: S1, S2 are sums of (r - m0), (r - m0)^2
+    const double dm = sc[SC_S1] / N;
+    double zz = sc[SC_S2] - sc[SC_S1] * dm;
+    if (zz < 0.0) zz = 0.0;
+    const double dp = sqrt(zz);
+    sc[SC_MEAN] = sc[SC_M0] + dm;
+    sc[SC_DP] = dp;
+    int it = (int)sc[SC_IT];
+    if (phase == 1) {
+        sc[SC_DP0] = dp;
+        sc[SC_TTOL] = fmax(sc[SC_RTOL] * dp, sc[SC_ABSTOL]);
+        sc[SC_BETA] = zz;
+        sc[SC_PWOLD] = 0.0;
+        if (hist && nhist > 0) hist[0] = dp;
+    } else {
+        it += 1;
+        sc[SC_IT] = it;
+        sc[SC_BETAOLD] = sc[SC_BETA];
+        sc[SC_BETA] = zz;
+        sc[SC_B] = zz / sc[SC_BETAOLD];
+        if (hist && it < nhist) hist[it] = dp;
+    }
+    if (dp != dp)
+        sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
+    else if (dp <= sc[SC_TTOL])
+        sc[SC_STATUS] = dp < sc[SC_ABSTOL] ? PBX_CONVERGED_ATOL : PBX_CONVERGED_RTOL;
+    else if (phase == 3 && dp >= 1.0e4 * sc[SC_DP0])
+        sc[SC_STATUS] = PBX_DIVERGED_DTOL;
+    else if (phase == 3 && it >= (int)sc[SC_MAXIT])
+        sc[SC_STATUS] = PBX_DIVERGED_ITS;
+}
+
+int vec_grid(size_t N)
+{
+    size_t nb = (N + (size_t)VT * 8 - 1) / ((size_t)VT * 8);
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+int cg_alloc(pbx_handle_s *h, int maxit)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    if (!h->cg_r) {
+        PBX_CUDA(cudaMalloc(&h->cg_r, N * sizeof(double)));
+        PBX_CUDA(cudaMalloc(&h->cg_p, N * sizeof(double)));
+        PBX_CUDA(cudaMalloc(&h->cg_w, N * sizeof(double)));
+        int np = vec_grid(N);
+        Brick g{h->nx, h->ny, h->nz};
+        if (h->fast_ok) {
+            int nz = fast_zpass_max_partials(g);
+            if (nz > np) np = nz;
+        }
+        h->cg_npartials = np;
+        PBX_CUDA(cudaMalloc(&h->cg_partials, 2 * (size_t)np * sizeof(double)));
+        PBX_CUDA(cudaMalloc(&h->cg_scal, SC_COUNT * sizeof(double)));
+        PBX_CUDA(cudaMallocHost(&h->cg_host, 2 * SC_COUNT * sizeof(double)));
+    }
+    if (h->cg_hist_cap < maxit + 1) {
+        if (h->cg_hist) cudaFree(h->cg_hist);
+        h->cg_hist = nullptr;
+        PBX_CUDA(cudaMalloc(&h->cg_hist, (size_t)(maxit + 1) * sizeof(double)));
+        h->cg_hist_cap = maxit + 1;
+    }
+    return PBX_OK;
+}
+
+__global__ void k_dot_generic(size_t N, const double *__restrict__ a, const double *__restrict__ b,
+                              double *__restrict__ part)
+{
+    __shared__ double sh[VT / 32];
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += VT) s = fma(a[i], b[i], s);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// w = A p and the local part of p.w into dst (device)
+int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int guarded)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    cudaStream_t s = h->stream;
+    int np;
+    if (h->nranks > 1) {
+        PBX_TRY(dist_lapl(h, p, w, p, h->cg_partials));
+        np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
+    } else if (h->mode == PBX_MODE_FAST) {
+        PBX_TRY(lapl_fast(h, p, w, p, h->cg_partials));
+        np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
+    } else {
+        PBX_TRY(lapl_reference(h, p, w));
+        np = vec_grid(N);
+        k_dot_generic<<<np, VT, 0, s>>>(N, p, w, h->cg_partials);
+        ++h->launches;
+    }
+    k_reduce<<<1, VT, 0, s>>>(h->cg_partials, np, np, 1, dst, h->cg_scal, guarded);
+    ++h->launches;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+}  // namespace
+
+void cg_free(pbx_handle_s *h)
+{
+    if (h->cg_r) cudaFree(h->cg_r);
+    if (h->cg_p) cudaFree(h->cg_p);
+    if (h->cg_w) cudaFree(h->cg_w);
+    if (h->cg_partials) cudaFree(h->cg_partials);
+    if (h->cg_scal) cudaFree(h->cg_scal);
+    if (h->cg_host) cudaFreeHost(h->cg_host);
+    if (h->cg_hist) cudaFree(h->cg_hist);
+    h->cg_r = h->cg_p = h->cg_w = h->cg_partials = h->cg_scal = h->cg_host = h->cg_hist = nullptr;
+    h->cg_hist_cap = 0;
+}
+
+int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev)
+{
+    PBX_TRY(cg_alloc(h, 1));
+    PBX_TRY(matmult_dot(h, f, out, dot_dev, 0));
+    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, dot_dev, 1));
+    return PBX_OK;
+}
+
+int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol, int maxit,
+             int *its, double *rnorm, int *reason, double *hist, int nhist)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    if (((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) != 0) {
+        set_last_error("pbx_cg_solve: b and x must be 16-byte aligned");
+        return PBX_ERR_ARG;
+    }
+    PBX_TRY(cg_alloc(h, maxit));
+    cudaStream_t s = h->stream;
+    double *sc = h->cg_scal, *part = h->cg_partials;
+    const int np = h->cg_npartials;
+    const int nb = vec_grid(N);
+    double *r = h->cg_r, *p = h->cg_p, *w = h->cg_w;
+
+    double init[SC_COUNT];
+    for (int i = 0; i < SC_COUNT; ++i) init[i] = 0.0;
+    init[SC_RTOL] = rtol;
+    init[SC_ABSTOL] = abstol;
+    init[SC_MAXIT] = (double)maxit;
+    init[SC_NTOT] = (double)N * (double)h->nranks;
+    PBX_CUDA(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, s));
+
+    // mean of b, then r = b, x = 0, p = z = b - mean, ||z||
+    k_sum<<<nb, VT, 0, s>>>(N, b, part);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
+    h->launches += 2;
+    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, sc + SC_S1, 1));
+    k_scalar<<<1, 1, 0, s>>>(sc, 0, nullptr, 0);
+    k_init<<<nb, VT, 0, s>>>(N, b, x, r, p, sc, part, np);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 0);
+    h->launches += 3;
+    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, sc + SC_S1, 2));
+    k_scalar<<<1, 1, 0, s>>>(sc, 1, h->cg_hist, h->cg_hist_cap);
+    ++h->launches;
+    PBX_CUDA(cudaGetLastError());
+
+    // The host runs one iteration ahead of the status it has seen: every kernel that changes
+    // solver state checks the device status word first, so iterations issued after convergence
+    // are no-ops.
+    cudaEvent_t ev[2];
+    PBX_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    PBX_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    double *hs = h->cg_host;
+    PBX_CUDA(cudaMemcpyAsync(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PBX_CUDA(cudaStreamSynchronize(s));
+    int rc = PBX_OK;
+    bool done = hs[SC_STATUS] != 0.0;
+    int issued = 0;
+    while (!done && issued < maxit) {
+        const int slot = issued & 1;
+        rc = matmult_dot(h, p, w, sc + SC_PW, 1);
+        if (rc != PBX_OK) break;
+        if (h->nranks > 1 && (rc = dist_allreduce_sum(h, sc + SC_PW, 1)) != PBX_OK) break;
+        k_scalar<<<1, 1, 0, s>>>(sc, 2, nullptr, 0);
+        k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
+        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 1);
+        h->launches += 3;
+        if (h->nranks > 1 && (rc = dist_allreduce_sum(h, sc + SC_S1, 2)) != PBX_OK) break;
+        k_scalar<<<1, 1, 0, s>>>(sc, 3, h->cg_hist, h->cg_hist_cap);
+        k_pupdate<<<vec_grid(N), VT, 0, s>>>(N, r, p, sc);
+        h->launches += 2;
+        cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double),
+                        cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(ev[slot], s);
+        ++issued;
+        if (issued >= 2) {
+            cudaEventSynchronize(ev[slot ^ 1]);
+            if (hs[(slot ^ 1) * SC_COUNT + SC_STATUS] != 0.0) done = true;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc != PBX_OK) return rc;
+    PBX_CUDA(e);
+    PBX_CUDA(cudaMemcpy(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+    int st = (int)hs[SC_STATUS];
+    int nit = (int)hs[SC_IT];
+    if (st == 0) st = PBX_DIVERGED_ITS;   // maxit == 0 or loop exhausted without a verdict
+    if (its) *its = nit;
+    if (rnorm) *rnorm = hs[SC_DP];
+    if (reason) *reason = st;
+    if (hist && nhist > 0) {
+        int cnt = nit + 1 < nhist ? nit + 1 : nhist;
+        PBX_CUDA(cudaMemcpy(hist, h->cg_hist, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+}  // namespace pbx

@@ -1,0 +1,186 @@
+// pbx_internal.h -- shared declarations of the poissbox-b200 CUDA library (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/pbx.h"
+
+namespace pbx {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+void set_last_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PBX_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return ::pbx::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PBX_TRY(call)                   \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != PBX_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Scheme constants (src/compact_schemes.f90:188-190 and :303-305)
+// ------------------------------------------------------------------------------------------------
+enum OpKind { OP_INTERP = 0, OP_DERIV = 1 };
+
+inline double scheme_alpha(OpKind k) { return k == OP_DERIV ? 9.0 / 62.0 : 3.0 / 10.0; }
+inline void scheme_ab(OpKind k, double dx, double *a, double *b)
+{
+    if (k == OP_DERIV) {
+        *a = 63.0 / 62.0 / dx;          // :188
+        *b = 17.0 / 62.0 / (3.0 * dx);  // :189
+    } else {
+        *a = 0.75;                      // :303
+        *b = 1.0 / 20.0;                // :304
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST schedule coefficients.
+//
+// A 1-D composite operator  O = P^+ P^-  (P = derivative or interpolation; ^- cell->vertex,
+// ^+ vertex->cell) is, because every factor is a circulant,  O = A^-2 S  with A = circ[al,1,al]
+// and S = B^+ B^- the symmetric 7-point product of the two 4-point right-hand-side stencils.
+// A = (1 - r E^-1)(1 - r E)/(1 + r^2) with r the root of al r^2 + r + al = 0 inside the unit
+// circle (E = shift), so A^-2 is two causal first-order recursions followed by two anti-causal
+// ones; the factor (1 + r^2)^2 is folded into S.
+// ------------------------------------------------------------------------------------------------
+constexpr int LC = 16;        // points per thread chunk, held in registers
+constexpr int MAXLOOK = 4;    // chunk-state look-back depth (r^(16*4) * 64 < 1e-29 for r = 1/3)
+
+struct CompositeCoef {
+    double c0, c1, c2, c3;    // S, scaled by (1 + r^2)^2
+    double r;                 // recursion pole (negative)
+    double pw[LC];            // r^(k+1), k = 0..LC-1
+    double look[MAXLOOK];     // r^(LC*m), m = 0..MAXLOOK-1  (look[0] = 1)
+    int nlook;                // look-back levels actually needed for < 1e-17 truncation
+    int pad_;
+};
+
+void make_composite_coef(OpKind kind, double dx, CompositeCoef *out);
+
+// ------------------------------------------------------------------------------------------------
+// REFERENCE schedule tables: the data-independent part of tdma_periodic on [al,1,al]
+// (src/tridsol.f90:51-70), computed on the host with the same IEEE operations the reference
+// performs, so that the device sweep reproduces the oracle bit for bit.
+// ------------------------------------------------------------------------------------------------
+struct RefLineTables {
+    int n = 0;
+    double alpha = 0;
+    double *w = nullptr;     // device: w(i) = a(i)/bmod(i-1), i = 1..n-1 (0-based; w[0] unused)
+    double *piv = nullptr;   // device: bmod after the forward sweep
+    double *u = nullptr;     // device: solution of the auxiliary system (:62-66)
+    double a1g = 0;          // a(1)/gamma
+    double den = 0;          // 1 + (u(1) + (a(1)/gamma) u(n))
+};
+int make_ref_tables(int n, double alpha, RefLineTables *t);
+void free_ref_tables(RefLineTables *t);
+
+// ------------------------------------------------------------------------------------------------
+// kernels' host-side launchers
+// ------------------------------------------------------------------------------------------------
+struct Brick {
+    int nx, ny, nz;
+    size_t N() const { return (size_t)nx * ny * nz; }
+};
+
+// REFERENCE-order 1-D line operator over every line of a brick along `dir`, or over a strided batch
+int ref_line_op(cudaStream_t s, int n, long long nlines1, long long nlines2, long long elem_stride,
+                long long line_stride1, long long line_stride2, OpKind kind, int stagger, double dx,
+                const RefLineTables &tab, const double *in, double *out, long long *launches);
+int ref_add(cudaStream_t s, size_t N, const double *a, const double *b, double *out,
+            long long *launches);
+
+// general-coefficient batched tridiagonal kernels (src/tridsol.f90)
+int tdma_fwd_batch(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *a,
+                   double *b, const double *c, double *d);
+int tdma_bwd_batch(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *b,
+                   const double *c, double *d);
+int tdma_periodic_batch(cudaStream_t s, int n, long long nl, long long es, long long ls,
+                        const double *a, const double *b, const double *c, double *d);
+
+// FAST schedule passes
+struct FastCoefs {
+    CompositeCoef D[3];   // derivative composite, per direction (depends on dx)
+    CompositeCoef M;      // interpolation composite
+};
+bool fast_supported(int nx, int ny, int nz);
+// xpass: f -> A = Dxx f, B = Mxx f
+int fast_xpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
+               double *B, long long *launches);
+// ypass: A,B -> C = Myy A + Dyy B, D = Myy B
+int fast_ypass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *A,
+               const double *B, double *C, double *D, long long *launches);
+// zpass: C,D -> out = Mzz C + Dzz D ; optional partial sums of p.out into dot_partials
+int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *C,
+               const double *D, double *out, const double *p, double *dot_partials,
+               int *n_partials, long long *launches);
+int fast_zpass_max_partials(const Brick &g);
+
+}  // namespace pbx
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+struct pbx_handle_s {
+    int nx = 0, ny = 0, nz = 0;
+    double dx[3] = {0, 0, 0};
+    int device = 0;
+    int mode = PBX_MODE_FAST;
+    cudaStream_t stream = nullptr;
+    void *comm = nullptr;   // ncclComm_t
+    int rank = 0, nranks = 1;
+    long long launches = 0;
+
+    pbx::FastCoefs fc;
+    bool fast_ok = false;
+
+    // REFERENCE-schedule tables: [dir][kind]
+    pbx::RefLineTables ref[3][2];
+
+    // scratch fields (device), allocated on first use
+    double *scratch[10] = {nullptr};
+    int nscratch = 0;
+
+    // CG workspace (pbx_cg.cu)
+    double *cg_r = nullptr, *cg_p = nullptr, *cg_w = nullptr;
+    double *cg_partials = nullptr;   // per-block partial sums, 2 x cg_npartials
+    int cg_npartials = 0;
+    double *cg_scal = nullptr;       // device scalar block
+    double *cg_host = nullptr;       // pinned host mirror of the scalar block
+    double *cg_hist = nullptr;       // device residual history
+    int cg_hist_cap = 0;
+
+    // z-slab decomposition (pbx_dist.cu)
+    void *dist = nullptr;
+};
+
+namespace pbx {
+int ensure_scratch(pbx_handle_s *h, int count);
+int lapl_reference(pbx_handle_s *h, const double *f, double *out);
+int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
+int grad_reference(pbx_handle_s *h, const double *f, double *df);
+int div_reference(pbx_handle_s *h, const double *f, double *out);
+int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger);
+int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol, int maxit,
+             int *its, double *rnorm, int *reason, double *hist, int nhist);
+int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);
+void cg_free(pbx_handle_s *h);
+// z-slab decomposition over an NCCL communicator
+int dist_attach(pbx_handle_s *h);
+void dist_free(pbx_handle_s *h);
+int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials);
+// sum `count` doubles in place over the handle's communicator (no-op for a single rank)
+int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count);
+}  // namespace pbx

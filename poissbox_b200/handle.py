@@ -1,0 +1,137 @@
+"""Device-resident operator handle: the counterpart of the reference's shell-matrix context
+`mat_ctx` (src/poissbox.f90:17-20), its MatMult callback `mfmult` (:300-322) and `solve` (:269-298).
+
+Fields are torch float64 CUDA tensors whose memory is Fortran column-major f(i,j,k), i.e. a
+C-contiguous tensor of shape (nz, ny, nx) (or (3, nz, ny, nx) for vector fields).  torch is used
+for device memory and streams only; every operation is a call into libpbx.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import LIB, check
+
+
+def fortran_to_torch(a, device="cuda"):
+    """numpy array f(i,j,k[,c]) in any order -> torch tensor (..., nz, ny, nx) with the same memory
+    layout as the Fortran array."""
+    import torch
+
+    a = np.asarray(a, dtype=np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a.transpose(*reversed(range(a.ndim))))).to(device)
+
+
+def torch_to_fortran(t):
+    """inverse of fortran_to_torch: returns a Fortran-ordered numpy array f(i,j,k[,c])"""
+    a = t.detach().cpu().numpy()
+    return np.asfortranarray(a.transpose(*reversed(range(a.ndim))))
+
+
+class Handle:
+    def __init__(self, nx, ny, nz, dx, device=0, comm=None):
+        import torch
+
+        self._torch = torch
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.dx = tuple(float(v) for v in dx)
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        check(LIB.pbx_create(self.nx, self.ny, self.nz, _lib._d3(*self.dx), self.device,
+                             ctypes.c_void_p(comm) if comm else None, ctypes.byref(self._h)))
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            LIB.pbx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def mode(self):
+        m = ctypes.c_int()
+        check(LIB.pbx_get_mode(self._h, ctypes.byref(m)))
+        return m.value
+
+    @mode.setter
+    def mode(self, m):
+        check(LIB.pbx_set_mode(self._h, int(m)))
+
+    def use_current_stream(self):
+        check(LIB.pbx_set_stream(self._h, ctypes.c_void_p(self._torch.cuda.current_stream().cuda_stream)))
+
+    def set_stream(self, stream_ptr):
+        check(LIB.pbx_set_stream(self._h, ctypes.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        check(LIB.pbx_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(LIB.pbx_launch_count(self._h))
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _field(self, t, ncomp=1):
+        torch = self._torch
+        n = self.nx * self.ny * self.nz * ncomp
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == n):
+            raise ValueError(f"expected a contiguous float64 CUDA tensor with {n} elements")
+        return ctypes.c_void_p(t.data_ptr())
+
+    def empty(self, ncomp=1):
+        shape = (self.nz, self.ny, self.nx) if ncomp == 1 else (ncomp, self.nz, self.ny, self.nx)
+        return self._torch.empty(shape, dtype=self._torch.float64, device=f"cuda:{self.device}")
+
+    # -- operators (compact_schemes) ------------------------------------------------------------
+    def lapl(self, f, out=None):
+        out = self.empty() if out is None else out
+        check(LIB.pbx_lapl_device(self._h, self._field(f), self._field(out)))
+        return out
+
+    def mult(self, x, y):
+        """MatMult of the shell matrix: y = A x (mfmult, src/poissbox.f90:300-322)"""
+        return self.lapl(x, y)
+
+    def lapl_dot(self, f, out=None):
+        out = self.empty() if out is None else out
+        dot = self._torch.zeros(1, dtype=self._torch.float64, device=f"cuda:{self.device}")
+        check(LIB.pbx_lapl_dot_device(self._h, self._field(f), self._field(out), ctypes.c_void_p(dot.data_ptr())))
+        return out, dot
+
+    def grad(self, f, out=None):
+        out = self.empty(3) if out is None else out
+        check(LIB.pbx_grad_device(self._h, self._field(f), self._field(out, 3)))
+        return out
+
+    def div(self, f, out=None):
+        out = self.empty() if out is None else out
+        check(LIB.pbx_div_device(self._h, self._field(f, 3), self._field(out)))
+        return out
+
+    def interp(self, f, stagger=-1, out=None):
+        out = self.empty() if out is None else out
+        check(LIB.pbx_interp_device(self._h, self._field(f), self._field(out), int(stagger)))
+        return out
+
+    # -- solve ----------------------------------------------------------------------------------
+    def cg_solve(self, b, x=None, rtol=1e-5, abstol=1e-50, maxit=10000):
+        """KSPSolve with -ksp_type cg -pc_type none (src/poissbox.f90:293-296).
+        Returns (x, its, rnorm, reason, history)."""
+        x = self.empty() if x is None else x
+        its, reason, rnorm = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        hist = np.zeros(maxit + 1)
+        check(LIB.pbx_cg_solve_device(self._h, self._field(b), self._field(x), rtol, abstol, int(maxit),
+                                      ctypes.byref(its), ctypes.byref(rnorm), ctypes.byref(reason),
+                                      hist.ctypes.data_as(_lib._dp), len(hist)))
+        return x, its.value, rnorm.value, reason.value, hist[: its.value + 1]

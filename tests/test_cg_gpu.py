@@ -1,0 +1,102 @@
+"""GPU: the device-resident CG (pbx_cg_solve_*) against the oracle's CG on the same inputs.
+
+Parity is UNPINNED on the reference side (the reference records no CG output; PETSc is absent):
+what is checked is that both implementations of the same KSPCG loop agree -- iteration counts
+within +-1 (BASELINE north_star), the same convergence reason, matching residual histories --
+and that the solution solves the system.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+import poissbox_b200 as pbx
+from poissbox_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def cg_host(b, dx, rtol, mode, maxit=10000):
+    import ctypes
+
+    b = np.asfortranarray(b)
+    nx, ny, nz = b.shape
+    x = np.zeros_like(b, order="F")
+    hist = np.zeros(maxit + 1)
+    its, reason, rnorm = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    pbx.check(pbx.LIB.pbx_cg_solve_host(nx, ny, nz, _lib._d3(*dx), b.ctypes.data_as(_lib._dp),
+                                        x.ctypes.data_as(_lib._dp), rtol, 1e-50, maxit, mode,
+                                        ctypes.byref(its), ctypes.byref(rnorm), ctypes.byref(reason),
+                                        hist.ctypes.data_as(_lib._dp), len(hist)))
+    return x, its.value, rnorm.value, reason.value, hist[: its.value + 1]
+
+
+def manufactured(n, kind):
+    if kind == "S3":   # full spectrum: x_true ~ U[-1,1], L = 1 (src/example.f90:30-35,180-181)
+        rng = np.random.default_rng(1234)
+        xt = np.asfortranarray(rng.uniform(-1, 1, (n, n, n)))
+        dx = (1.0 / n,) * 3
+    else:              # S4 smooth: u = exp(sin x + sin y + sin z), L = 2 pi
+        h = 2 * np.pi / n
+        c = (np.arange(n) + 0.5) * h
+        xt = np.asfortranarray(np.exp(np.sin(c)[:, None, None] + np.sin(c)[None, :, None] + np.sin(c)[None, None, :]))
+        dx = (h,) * 3
+    return xt, dx
+
+
+@pytest.mark.parametrize("n,kind,rtol", [(16, "S3", 1e-8), (32, "S3", 1e-8), (32, "S3", 1e-5),
+                                         (32, "S4", 1e-8), (64, "S3", 1e-8)])
+def test_cg_matches_oracle(n, kind, rtol):
+    xt, dx = manufactured(n, kind)
+    orc.set_threads(8)
+    try:
+        b = orc.lapl(xt, dx)   # demo recipe b = A x_true (src/example.f90:70-72)
+        xo, ito, rno, reo, ho = orc.cg_solve(b, dx, rtol=rtol)
+    finally:
+        orc.set_threads(1)
+    assert reo == 2
+    for mode in (pbx.MODE_REFERENCE, pbx.MODE_FAST):
+        xg, itg, rng_, reg, hg = cg_host(b, dx, rtol, mode)
+        assert reg == reo
+        assert abs(itg - ito) <= 1, (itg, ito)
+        m = min(len(hg), len(ho))
+        # residual histories agree while rounding differences have not yet been amplified
+        k = max(2, m // 2)
+        assert np.allclose(hg[:k], ho[:k], rtol=1e-6)
+        assert rng_ <= rtol * hg[0]
+        # the solution solves the system (true residual, oracle operator)
+        r = orc.lapl(xg, dx) - b
+        assert np.linalg.norm(r) <= 20 * rtol * np.linalg.norm(b)
+        # and equals the oracle's solution up to the convergence tolerance
+        assert np.linalg.norm(xg - xo) <= 1e3 * rtol * np.linalg.norm(xo)
+
+
+def test_cg_golden():
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+    b = G["cg16_b"]
+    x, its, rnorm, reason, hist = cg_host(b, (1 / 16,) * 3, 1e-8, pbx.MODE_REFERENCE)
+    assert reason == int(G["cg16_meta"][1]) and abs(its - int(G["cg16_meta"][0])) <= 1
+    assert np.allclose(hist[:10], G["cg16_hist"][:10], rtol=1e-10)
+    assert np.linalg.norm(x - G["cg16_x"]) <= 1e-5 * np.linalg.norm(G["cg16_x"])
+
+
+def test_cg_edge_cases():
+    n = 16
+    dx = (1.0 / n,) * 3
+    # zero right-hand side: converged at iteration 0 (rnorm 0 < abstol -> CONVERGED_ATOL)
+    x, its, rnorm, reason, hist = cg_host(np.zeros((n, n, n)), dx, 1e-8, pbx.MODE_FAST)
+    assert its == 0 and reason == 3 and rnorm == 0.0 and not x.any()
+    # constant right-hand side lies in the null space: z = r - mean(r) = 0
+    x, its, rnorm, reason, hist = cg_host(np.full((n, n, n), 3.25), dx, 1e-8, pbx.MODE_FAST)
+    assert its == 0 and reason == 3
+    # iteration cap
+    xt, dx = manufactured(n, "S3")
+    b = orc.lapl(xt, dx)
+    x, its, rnorm, reason, hist = cg_host(b, dx, 1e-14, pbx.MODE_FAST, maxit=5)
+    assert its == 5 and reason == -3
+    # a right-hand side with a large mean: the mean is carried, not amplified
+    x1, its1, *_ = cg_host(b, dx, 1e-8, pbx.MODE_FAST)
+    x2, its2, *_ = cg_host(b + 1.0e3, dx, 1e-8, pbx.MODE_FAST)
+    assert abs(its1 - its2) <= 1
+    assert np.linalg.norm(x1 - x2) <= 1e-5 * np.linalg.norm(x1)

@@ -1,0 +1,267 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libpbx.so), against the CPU oracle.
+
+Bars (BASELINE.json north_star; SURVEY 7 "hard parts"):
+  * REFERENCE schedule: BIT-IDENTICAL to the oracle (same operations in the same order, no FMA).
+  * FAST schedule: max|delta| <= 1e-12 * max|reference| (it re-associates the computation, so it
+    cannot be bit-identical; the measured agreement is ~1e-15), and per-element relative
+    difference <= 1e-12 wherever |reference| >= 1e-3 * max|reference|.
+  * tridsol batches: bit-identical to the oracle.
+The known-answer tests of the reference are restated through the host-side mirror of its module
+interface (poissbox_b200.compact_schemes / tridsol), so they read like the reference's own tests.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+import poissbox_b200 as pbx
+from poissbox_b200 import compact_schemes as cs
+from poissbox_b200 import tridsol
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+FAST_TOL = 1e-12
+
+
+def assert_fast_close(got, ref):
+    scale = np.max(np.abs(ref))
+    d = np.abs(got - ref)
+    assert np.max(d) <= FAST_TOL * scale, f"max|d|/max|ref| = {np.max(d) / scale:.3e}"
+    big = np.abs(ref) >= 1e-3 * scale
+    assert np.max(d[big] / np.abs(ref[big])) <= FAST_TOL
+
+
+# ------------------------------------------------------------------------------------ tridsol
+def tdma_init(n, rng, periodic=False):
+    a, b, c, x = (rng.random(n) for _ in range(4))
+    if not periodic:
+        a[0] = 0.0
+        c[n - 1] = 0.0
+    for i in range(n):
+        while abs(b[i]) < abs(a[i]) + abs(c[i]):
+            b[i] = 10 * b[i]
+    d = b * x + a * np.roll(x, 1) + c * np.roll(x, -1)
+    return a, b, c, x, d
+
+
+@pytest.mark.parametrize("n", [2, 3, 33, 128, 2048])
+def test_tridsol_bit_exact(n):
+    rng = np.random.default_rng(n)
+    for per in (False, True):
+        a, b, c, x, d = tdma_init(n, rng, per)
+        # fwd_sweep / bwd_sweep / tdma (tests/tridiag/test_tdma_sweeps.f90, test_tdma.f90)
+        bo, do = orc.fwd_sweep(a, b, c, d)
+        bg, dg = tridsol.fwd_sweep(a.copy(), b.copy(), c.copy(), d.copy())
+        assert np.array_equal(bo, bg) and np.array_equal(do, dg)
+        assert np.array_equal(orc.bwd_sweep(b, c, d), tridsol.bwd_sweep(b.copy(), c.copy(), d.copy()))
+        bb = b.copy()
+        got = tridsol.tdma(a.copy(), bb, c.copy(), d.copy())
+        assert np.array_equal(orc.tdma(a, b, c, d), got)
+        assert np.array_equal(bb, bo)   # b overwritten with the pivots (tridsol.f90:92)
+        # tdma_periodic (tests/tridiag/test_tdma_periodic.f90)
+        bb = b.copy()
+        got = tridsol.tdma_periodic(a.copy(), bb, c.copy(), d.copy())
+        assert np.array_equal(orc.tdma_periodic(a, b, c, d), got)
+        assert np.array_equal(bb, b)
+        if n >= 3:
+            err = np.sqrt(np.mean((got - x) ** 2)) if per else 0.0
+            assert err <= 4 * EPS * np.sqrt(np.mean(x**2)) * max(1, n / 128)
+
+
+def test_tridsol_golden():
+    for n in (33, 128):
+        for per in (0, 1):
+            k = f"tri_n{n}_p{per}"
+            a, b, c, d = (np.ascontiguousarray(v) for v in G[k + "_abcd"])
+            assert np.array_equal(tridsol.tdma(a.copy(), b.copy(), c.copy(), d.copy()), G[k + "_tdma"])
+            assert np.array_equal(tridsol.tdma_periodic(a.copy(), b.copy(), c.copy(), d.copy()), G[k + "_tdmap"])
+
+
+def test_tridsol_batch_strided():
+    """many lines in one launch, both memory layouts (line-major and element-major)"""
+    import ctypes
+
+    import torch
+
+    rng = np.random.default_rng(3)
+    n, nl = 64, 300
+    sys_ = [tdma_init(n, rng, True) for _ in range(nl)]
+    A, B, C, D = (np.stack([s[i] for s in sys_]) for i in (0, 1, 2, 4))   # [line][i]
+    want = np.stack([orc.tdma_periodic(*s[:3], s[4]) for s in sys_])
+    for layout in ("line_major", "elem_major"):
+        if layout == "line_major":
+            arrs = [torch.from_numpy(v.copy()).cuda() for v in (A, B, C, D)]
+            es, ls = 1, n
+        else:
+            arrs = [torch.from_numpy(np.ascontiguousarray(v.T)).cuda() for v in (A, B, C, D)]
+            es, ls = nl, 1
+        ptr = [ctypes.c_void_p(t.data_ptr()) for t in arrs]
+        pbx.check(pbx.LIB.pbx_tdma_periodic_batch_device(n, nl, es, ls, *ptr, None))
+        torch.cuda.synchronize()
+        got = arrs[3].cpu().numpy()
+        got = got if layout == "line_major" else got.T
+        assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------ 1-D operators
+@pytest.mark.parametrize("n", [3, 4, 5, 37, 128, 1000])
+def test_lines_bit_exact(n):
+    rng = np.random.default_rng(n)
+    f = rng.uniform(-1, 1, n)
+    dx = 0.37 / n
+    assert np.array_equal(cs.grad_1d(f, dx), orc.grad_1d(f, dx))
+    assert np.array_equal(cs.div_1d(f, dx), orc.div_1d(f, dx))
+    assert np.array_equal(cs.interp_1d(f), orc.interp_1d(f))
+    assert np.array_equal(cs.interp_1d_div(f), orc.interp_1d_div(f))
+
+
+def test_lines_golden():
+    for n in (37, 128):
+        f = G[f"l1_n{n}_f"]
+        assert np.array_equal(cs.grad_1d(f, 1.0 / n), G[f"l1_n{n}_grad"])
+        assert np.array_equal(cs.div_1d(f, 1.0 / n), G[f"l1_n{n}_div"])
+        assert np.array_equal(cs.interp_1d(f), G[f"l1_n{n}_interp"])
+        assert np.array_equal(cs.interp_1d_div(f), G[f"l1_n{n}_interpdiv"])
+
+
+def test_grad_1d_kat():
+    """tests/grad/test_grad_1d.f90:53-134 and tests/div/test_div_1d.f90:53-134 through the mirror"""
+    n = 128
+    dx = 2 * np.pi / n
+    f = np.full(n, 2.8170923)
+    df = np.full(n, 73.29)
+    cs.grad_1d(f, dx, df)
+    assert np.sqrt(np.sum(df**2) / n) <= 100 * EPS
+    assert np.sqrt(np.sum((cs.interp_1d(f) - f) ** 2) / n) <= 100 * EPS
+    xc, xv = (np.arange(n) + 0.5) * dx, np.arange(n) * dx
+    assert np.sqrt(np.mean((cs.grad_1d(np.sin(xc), dx) - np.cos(xv)) ** 2)) <= 1e-11
+    assert np.sqrt(np.mean((cs.interp_1d(np.sin(xc)) - np.sin(xv)) ** 2)) <= 1e-11
+    assert np.sqrt(np.mean((cs.div_1d(np.sin(xv), dx) - np.cos(xc)) ** 2)) <= 1e-11
+    assert np.sqrt(np.mean((cs.interp_1d_div(np.sin(xv)) - np.sin(xc)) ** 2)) <= 1e-11
+
+
+def test_size_mismatch_stop_7():
+    with pytest.raises(pbx.SizeMismatch):
+        cs.grad_1d(np.zeros(8), 0.1, df=np.zeros(7))
+
+
+# ------------------------------------------------------------------------------------ 3-D operators
+SHAPES = [((32, 16, 48), (1 / 32, 0.5 / 16, 2.0 / 48)), ((12, 9, 7), (0.1, 0.2, 0.3)),
+          ((64, 64, 64), (1 / 64,) * 3), ((3, 3, 3), (1.0, 1.0, 1.0))]
+
+
+@pytest.mark.parametrize("shape,dx", SHAPES)
+def test_fields_reference_bit_exact(shape, dx):
+    rng = np.random.default_rng(1234)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    v = np.asfortranarray(rng.uniform(-1, 1, shape + (3,)))
+    assert np.array_equal(cs.lapl(f, dx, mode=pbx.MODE_REFERENCE), orc.lapl(f, dx))
+    assert np.array_equal(cs.grad(f, dx), orc.grad(f, dx))
+    assert np.array_equal(cs.div(v, dx), orc.div(v, dx))
+    assert np.array_equal(cs.interp(f), orc.interp(f))
+    assert np.array_equal(cs.interp_div(f), orc.interp_div(f))
+
+
+def test_fields_golden():
+    for tag in "ab":
+        f, v, dx = G[f"f3{tag}_f"], G[f"f3{tag}_v"], G[f"f3{tag}_dx"]
+        assert np.array_equal(cs.lapl(f, dx, mode=pbx.MODE_REFERENCE), G[f"f3{tag}_lapl"])
+        assert np.array_equal(cs.grad(f, dx), G[f"f3{tag}_grad"])
+        assert np.array_equal(cs.div(v, dx), G[f"f3{tag}_div"])
+        assert np.array_equal(cs.interp(f), G[f"f3{tag}_interp"])
+        assert np.array_equal(cs.interp_div(f), G[f"f3{tag}_interpdiv"])
+    f, dx = G["f3a_f"], G["f3a_dx"]
+    assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), G["f3a_lapl"])
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 48), (64, 64, 64), (128, 32, 64),
+                                   (48, 80, 112), (1024, 16, 16), (16, 512, 16), (16, 16, 512)])
+def test_lapl_fast_vs_oracle(shape):
+    """S2 inputs: U[-1,1], default_rng(1234), dx = 1/n"""
+    rng = np.random.default_rng(1234)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    dx = tuple(1.0 / n for n in shape)
+    orc.set_threads(8)
+    try:
+        ref = orc.lapl(f, dx)
+    finally:
+        orc.set_threads(1)
+    assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), ref)
+
+
+def test_lapl_kat_both_modes():
+    """tests/lapl/test_lapl.f90:57-132 through the mirror, both schedules"""
+    n = 64
+    dx = 2 * np.pi / n
+    c = (np.arange(n) + 0.5) * dx
+    f = np.sin(c)[:, None, None] + np.sin(c)[None, :, None] + np.sin(c)[None, None, :]
+    const = np.full((n, n, n), 2.8170923)
+    for mode in (pbx.MODE_REFERENCE, pbx.MODE_FAST):
+        out = cs.lapl(const, [dx] * 3, mode=mode)
+        assert np.sqrt(np.sum(out**2) / n**3) <= 100 * EPS
+        out = cs.lapl(f, [dx] * 3, mode=mode)
+        rms = np.sqrt(np.mean((out + f) ** 2))
+        assert rms == rms and rms <= 1e-9
+    # smooth field: the two schedules differ by rounding only
+    a = cs.lapl(f, [dx] * 3, mode=pbx.MODE_REFERENCE)
+    b = cs.lapl(f, [dx] * 3, mode=pbx.MODE_FAST)
+    assert np.max(np.abs(a - b)) <= FAST_TOL * np.max(np.abs(a))
+
+
+def test_grad_div_3d_kat():
+    """tests/grad/test_grad_3d.f90:60-145 and tests/div/test_div_3d.f90:57-144 through the mirror"""
+    n = 64
+    dx = 2 * np.pi / n
+    c, v = (np.arange(n) + 0.5) * dx, np.arange(n) * dx
+
+    def bc(a, ax):
+        sh = [1, 1, 1]
+        sh[ax] = -1
+        return a.reshape(sh)
+
+    const = np.full((n, n, n), 2.8170923)
+    assert np.sqrt(np.sum(cs.grad(const, [dx] * 3) ** 2) / n**3 / 3) <= 100 * EPS
+    assert np.sqrt(np.sum((cs.interp(const) - const) ** 2) / n**3) <= 100 * EPS
+    f = bc(np.sin(c), 0) + bc(np.sin(c), 1) + bc(np.sin(c), 2)
+    df = cs.grad(f, [dx] * 3)
+    tot = sum(np.sqrt(np.sum((df[..., ax] - bc(np.cos(v), ax)) ** 2) / n) / n / n for ax in range(3))
+    assert tot / 3 <= 1e-11
+    F = np.empty((n, n, n, 3), order="F")
+    for ax in range(3):
+        F[..., ax] = np.broadcast_to(bc(np.sin(v), ax), (n, n, n))
+    expect = bc(np.cos(c), 0) + bc(np.cos(c), 1) + bc(np.cos(c), 2)
+    assert np.sqrt(np.mean((cs.div(F, [dx] * 3) - expect) ** 2)) <= 1e-9
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_lapl_full_size_properties():
+    """256^3 (BASELINE configs[2]) device-resident: agreement of the two schedules, constants in
+    the null space, linearity, symmetry <u, L v> = <L u, v>, and the fused p.Ap."""
+    import torch
+
+    n = 256
+    h = pbx.Handle(n, n, n, (1.0 / n,) * 3)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    u = torch.rand((n, n, n), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    v = torch.rand((n, n, n), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    h.mode = pbx.MODE_FAST
+    Lu, Lv = h.lapl(u), h.lapl(v)
+    h.mode = pbx.MODE_REFERENCE
+    Lu_ref = h.lapl(u)
+    scale = Lu_ref.abs().max().item()
+    assert (Lu - Lu_ref).abs().max().item() <= FAST_TOL * scale
+    h.mode = pbx.MODE_FAST
+    assert h.lapl(torch.full_like(u, 2.8170923)).abs().max().item() <= 1e-9 * scale
+    Lw = h.lapl(u + 0.5 * v)
+    assert (Lw - (Lu + 0.5 * Lv)).abs().max().item() <= 1e-13 * scale
+    a, b = torch.dot(u.flatten(), Lv.flatten()).item(), torch.dot(Lu.flatten(), v.flatten()).item()
+    assert abs(a - b) <= 1e-12 * (u.norm() * Lv.norm()).item()
+    w, dot = h.lapl_dot(u)
+    assert torch.equal(w, Lu)
+    ref = torch.dot(u.flatten(), Lu.flatten()).item()
+    assert abs(dot.item() - ref) <= 1e-13 * abs(ref)
+    assert ref < 0   # negative semi-definite
+    h.close()
