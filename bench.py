@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of poissbox-b200.
+
+Metric (BASELINE.json): GDoF/s of one compact-Laplacian apply (the MATSHELL MatMult of the CG
+Poisson solve) on a 512^3 fp64 periodic box, plus the CG time-to-1e-8 on the same grid.
+
+  step      one application of the compact Laplacian to one 512^3 field (N>1: each rank owns a
+            z-slab of the 512^2 x 512 box ... see --scaling)
+  value     whole-job GDoF/s with the field resident in HBM (CUDA events, max over ranks)
+  e2e       the same step through the host-pointer C-ABI call a Fortran caller makes
+            (pbx_lapl_host): pinned host buffers, H2D + D2H inside the timed region
+  roofline  the dominant kernel (y pass, 32 B/DoF algorithmic) against the measured HBM peak
+  cpu_baseline  the CPU oracle (op-for-op port of the reference Fortran; the reference itself
+            cannot be built here: no Fortran, MPI or PETSc) on a bounded sample, 1 core
+
+`--impl reference` times that CPU port with all host threads instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GDoF/s of compact Laplacian apply; CG time-to-1e-8 at 512^3 fp64, 1-8 B200"
+ALG_BYTES_MATMULT = 80.0     # B/DoF, one sweep per axis
+ALG_BYTES_PASS = {"x": 24.0, "y": 32.0, "z": 24.0}
+FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="global grid is n^3")
+    ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cg-rtol", type=float, default=1e-8)
+    ap.add_argument("--cg-maxit", type=int, default=20000)
+    return ap.parse_args()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs (one streaming
+    nvidia-smi process, a line every 50 ms)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def _run(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self, t_lo=None, t_hi=None):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.th:
+            self.th.join(timeout=5)
+        rows = [r for t, r in self.rows if (t_lo is None or t >= t_lo) and (t_hi is None or t <= t_hi)]
+        if len(rows) < 3:          # a very short timed region: keep every sample taken under load
+            rows = [r for _, r in self.rows]
+
+        def num(v):
+            try:
+                return float(v)
+            except Exception:
+                return None
+
+        sm = sorted(v for v in (num(r[0]) for r in rows if r) if v is not None)
+        mx = [v for v in (num(r[1]) for r in rows if len(r) > 1) if v is not None]
+        pw = [v for v in (num(r[2]) for r in rows if len(r) > 2) if v is not None]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle = op-for-op port of the reference; test infrastructure, used here only as the
+# reported CPU baseline / the --impl reference arm)
+# ------------------------------------------------------------------------------------------------
+def cpu_lapl_rate(n, threads, reps):
+    """GDoF/s of the oracle Laplacian on an n^3 S2 field with `threads` host threads"""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+
+    rng = np.random.default_rng(1234)
+    f = np.asfortranarray(rng.uniform(-1, 1, (n, n, n)))
+    dx = (1.0 / n,) * 3
+    orc.set_threads(threads)
+    try:
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            orc.lapl(f, dx)
+        dt = (time.perf_counter() - t0) / reps
+    finally:
+        orc.set_threads(1)
+    return n**3 / dt / 1e9, dt
+
+
+def cpu_baseline_block():
+    # bounded sample: one 256^3 brick of the 512^3 workload (same operator, same line layout;
+    # about 16 s on one core), after a 64^3 warm-up
+    cpu_lapl_rate(64, 1, 1)
+    n = 256
+    rate, dt = cpu_lapl_rate(n, 1, 1)
+    return {"value": rate, "unit": "GDoF/s", "cores": 1, "kind": "port",
+            "sample": f"one compact-Laplacian apply on a {n}^3 S2 brick ({dt:.1f} s), CPU oracle "
+                      "(C restatement of the reference Fortran, gcc -O2 no-FMA), 1 thread = the "
+                      "reference's serial behaviour"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # calibrate so that (steps + warmup) samples finish in about two minutes
+    rate64, _ = cpu_lapl_rate(64, cores, 1)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = 64
+    for cand in (96, 128, 192, 256, 384, 512):
+        if cand**3 / (rate64 * 1e9) <= budget and cand <= args.n:
+            n = cand
+    for _ in range(args.warmup):
+        cpu_lapl_rate(n, cores, 1)
+    rate, dt = cpu_lapl_rate(n, cores, max(1, args.steps))
+    sample = (f"each step = one compact-Laplacian apply on a {n}^3 S2 brick of the {args.n}^3 workload, "
+              f"CPU oracle (C port of the reference Fortran; the Fortran+PETSc reference cannot be built "
+              f"in this image), {cores} host threads over lines")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "GDoF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"compact Laplacian apply, {args.n}^3 fp64 periodic box, S2 random field",
+                   "grid": [args.n] * 3, "sample_grid": [n] * 3},
+        "cpu_baseline": {"value": rate, "unit": "GDoF/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import poissbox_b200 as pbx
+    from poissbox_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        import ctypes
+
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (ctypes.c_ubyte * 128)()
+            pbx.check(pbx.LIB.pbx_comm_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.to(dev)
+        dist.broadcast(idbuf, 0)
+        raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist())
+        c = ctypes.c_void_p()
+        pbx.check(pbx.LIB.pbx_comm_init_rank(raw, world, rank, local, ctypes.byref(c)))
+        comm = c.value
+
+    n = args.n
+    if n % world or (n // world) % 16:
+        raise SystemExit("n / gpus must be a multiple of 16")
+    nzl = n // world                       # strong scaling: the 512^3 box is z-slab partitioned
+    dx = (1.0 / n,) * 3
+    h = pbx.Handle(n, n, nzl, dx, device=local, comm=comm)
+    h.use_current_stream()
+    h.mode = pbx.MODE_FAST
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # S2 input: U[-1,1] (generated on the device: at 512^3 the field is 1 GiB)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    f = torch.rand((nzl, n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    out = h.empty()
+    ndof_total = float(n) ** 3
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # warm-up; at least 0.3 s of it so that the clock sampler sees the load the timed region runs under
+    tw = time.perf_counter()
+    nw = 0
+    while nw < max(3, args.warmup) or time.perf_counter() - tw < 0.3:
+        h.lapl(f, out)
+        nw += 1
+        if nw % 8 == 0:
+            torch.cuda.synchronize()
+    barrier()
+    t_lo = time.perf_counter() - 0.25
+    l0 = h.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        h.lapl(f, out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = h.launches - l0
+    clocks = sampler.stop(t_lo, time.perf_counter() + 0.05) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = ndof_total / (ms_per_step * 1e-3) / 1e9
+
+    # per-kernel durations (CUDA events between the launches) for the roofline of the dominant kernel
+    peak, peak_src = hbm_peak()
+    roof = None
+    if world == 1:
+        pm = h.lapl_profile(f, out, reps=max(3, min(10, args.steps)))
+        names = ("x", "y", "z")
+        per = {k: {"ms": pm[i], "alg_bytes_per_dof": ALG_BYTES_PASS[k],
+                   "achieved_GBs": ALG_BYTES_PASS[k] * ndof_total / (pm[i] * 1e-3) / 1e9}
+               for i, k in enumerate(names)}
+        dom = max(names, key=lambda k: per[k]["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"{dom}pass_{n}")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": f"{dom}pass_kernel", "achieved": per[dom]["achieved_GBs"],
+                "peak": peak, "unit": "GB/s", "frac": per[dom]["achieved_GBs"] / peak, "traffic": traffic,
+                "peak_source": peak_src, "passes": per,
+                "matmult": {"alg_bytes_per_dof": ALG_BYTES_MATMULT,
+                            "achieved_GBs": ALG_BYTES_MATMULT * value,
+                            "frac": ALG_BYTES_MATMULT * value / peak}}
+    else:
+        roof = {"bound": "hbm", "kernel": "matmult (x+y+z pass, z-slab)", "achieved": ALG_BYTES_MATMULT * value / world,
+                "peak": peak, "unit": "GB/s", "frac": ALG_BYTES_MATMULT * value / world / peak, "traffic": None,
+                "peak_source": peak_src}
+
+    # end to end through the host-pointer C-ABI call (what the Fortran shim calls), pinned buffers
+    e2e = None
+    if not args.no_e2e and world == 1:
+        import ctypes
+
+        fh = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
+        oh = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
+        fh.copy_(f)
+        torch.cuda.synchronize()
+        d3 = _lib._d3(*dx)
+        pf = ctypes.cast(fh.data_ptr(), _lib._dp)
+        po = ctypes.cast(oh.data_ptr(), _lib._dp)
+        for _ in range(2):
+            pbx.check(pbx.LIB.pbx_lapl_host(n, n, nzl, pf, d3, po, pbx.MODE_FAST))
+        ksteps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            pbx.check(pbx.LIB.pbx_lapl_host(n, n, nzl, pf, d3, po, pbx.MODE_FAST))
+        dt = (time.perf_counter() - t0) / ksteps
+        assert torch.equal(oh.to(dev), out), "host-pointer path disagrees with the device path"
+        pbx.LIB.pbx_host_cache_clear()
+        e2e = {"value": ndof_total / dt / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": int(8 * ndof_total),
+               "d2h_bytes_per_step": int(8 * ndof_total), "ms_per_step": dt * 1e3, "steps": ksteps,
+               "api": "pbx_lapl_host (pinned host buffers)"}
+        del fh, oh
+
+    # CG time-to-rtol on a manufactured smooth solution (S4), device resident
+    cg = None
+    if not args.no_cg:
+        hh = 2 * np.pi / n
+        c = (torch.arange(n, dtype=torch.float64, device=dev) + 0.5) * hh
+        cz = c[rank * nzl:(rank + 1) * nzl]
+        u = torch.exp(torch.sin(c)[None, None, :] + torch.sin(c)[None, :, None] + torch.sin(cz)[:, None, None]).contiguous()
+        h2 = pbx.Handle(n, n, nzl, (hh,) * 3, device=local, comm=comm)
+        h2.use_current_stream()
+        b = h2.lapl(u)
+        x = h2.empty()
+        del u
+        barrier()
+        l1 = h2.launches
+        t0 = time.perf_counter()
+        x, its, rnorm, reason, hist = h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=args.cg_maxit)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        cg = {"rhs": "S4 manufactured: b = A exp(sin x + sin y + sin z), L = 2 pi", "rtol": args.cg_rtol,
+              "time_s": dt, "its": its, "reason": reason, "rnorm_rel": rnorm / hist[0] if hist[0] else 0.0,
+              "ms_per_it": dt / max(1, its) * 1e3, "GDoF_it_per_s": ndof_total * its / dt / 1e9,
+              "alg_bytes_per_dof_it": 152.0, "frac_of_hbm_peak": 152.0 * ndof_total * its / dt / 1e9 / peak / world,
+              "gpu_launches": h2.launches - l1}
+        h2.close()
+        del b, x
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_block()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"compact Laplacian apply (FAST schedule), {n}^3 fp64 periodic box, S2 random field "
+                                   f"U[-1,1], dx = 1/{n}; N>1: z-slabs of {nzl} planes",
+                       "grid": [n, n, n], "local_brick": [n, n, nzl], "l2": "field (1 GiB at 512^3) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"zslab{world}"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "cg": cg,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        if comm:
+            pbx.LIB.pbx_comm_destroy(comm)
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,10 @@ int pbx_comm_destroy(void *comm);
 int pbx_lapl_device(pbx_handle h, const double *f, double *d2f);
 /* as above, and additionally *dot_dev (device double) <- sum f * d2f (the CG p.Ap, fused) */
 int pbx_lapl_dot_device(pbx_handle h, const double *f, double *d2f, double *dot_dev);
+/* Measurement aid (bench.py): runs the FAST Laplacian `reps` times and returns the average
+ * duration in milliseconds of each of its three kernels (x, y, z pass), taken with CUDA events
+ * recorded between the launches on the handle's stream.  Synchronises the stream. */
+int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps, double ms[3]);
 /* compact_schemes::grad  src/compact_schemes.f90:42-88;  df has 3 components */
 int pbx_grad_device(pbx_handle h, const double *f, double *df);
 /* compact_schemes::div   src/compact_schemes.f90:207-257;  f has 3 components */

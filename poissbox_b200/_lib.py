@@ -38,6 +38,7 @@ SIGNATURES = {
     "pbx_comm_destroy": (c_int, [c_void_p]),
     "pbx_lapl_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_dot_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pbx_lapl_profile_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, _d3]),
     "pbx_grad_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_div_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_interp_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

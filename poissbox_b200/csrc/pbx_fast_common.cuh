@@ -1,0 +1,303 @@
+// pbx_fast_common.cuh -- register-array building blocks of the FAST schedule, shared by the
+// TMA-pipelined kernels (pbx_fast_tma.cu) and the generic fallback kernels (pbx_fast_kernels.cu).
+//
+// A composite 1-D operator O = A^-2 S (pbx_internal.h) acts on a periodic line cut into chunks of
+// LC = 16 points; a thread owns one chunk of one line in registers.
+//
+//   derivative composite  (D = D+ G-):  STENCIL FIRST.  S_D is evaluated in difference form
+//        S_D f = c1 (s1 - 2 f0) + c2 (s2 - 2 f0) + c3 (s3 - 2 f0),  s_k = f_k + f_-k,
+//     so that a constant gives exactly zero, as the reference's f(i) - f(i-1) does
+//     (tests/lapl/test_lapl.f90:57-74); then the double recursion.
+//   interpolation composite (M = I+ I-):  SOLVE FIRST, then S_M on the solved values.  A^-2
+//     amplifies grid-scale noise by up to (1 - 2 al)^-2 = 6.25 while S_M annihilates it, so doing
+//     the smoothing stencil last keeps the rounding noise that the derivative operators of the
+//     other axes later amplify by ~4/dx^2 about 6x smaller (measured against a long-double
+//     evaluation: same error as the reference's own order of operations).
+//
+// The recursion: local causal sweep from zero state, y_k = s_k + r y_{k-1}, z_k = y_k + r z_{k-1};
+// the true incoming state is assembled from the neighbours' local end states (look-back over
+// nlook chunks, the influence of chunk t-m decaying as r^(16 m)); the chunk is corrected with the
+// homogeneous solution r^(k+1) (Z + (k+1) Y); then the same anti-causally.  Periodicity needs no
+// Sherman-Morrison step: the look-back wraps around the line.
+#pragma once
+
+#include "pbx_internal.h"
+
+namespace pbx {
+namespace fast {
+
+constexpr int NT = 256;   // compute threads per CTA
+
+template <bool DIFF>
+__device__ __forceinline__ double stencil_point(const CompositeCoef &c, double f0, double s1,
+                                                double s2, double s3)
+{
+    if (DIFF) {
+        double d1 = fma(-2.0, f0, s1), d2 = fma(-2.0, f0, s2), d3 = fma(-2.0, f0, s3);
+        return fma(c.c3, d3, fma(c.c2, d2, c.c1 * d1));
+    }
+    return fma(c.c3, s3, fma(c.c2, s2, fma(c.c1, s1, c.c0 * f0)));
+}
+
+// o = S e, e = { 3 halo points, LC chunk points, 3 halo points }
+template <bool DIFF>
+__device__ __forceinline__ void stencil(const CompositeCoef &c, const double (&e)[LC + 6],
+                                        double (&o)[LC])
+{
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+        double s1 = e[k + 2] + e[k + 4];
+        double s2 = e[k + 1] + e[k + 5];
+        double s3 = e[k] + e[k + 6];
+        o[k] = stencil_point<DIFF>(c, e[k + 3], s1, s2, s3);
+    }
+}
+
+__device__ __forceinline__ void fwd_local(double r, double (&v)[LC], double &ey, double &ez)
+{
+    double y = 0.0, z = 0.0;
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+        y = fma(r, y, v[k]);
+        z = fma(r, z, y);
+        v[k] = z;
+    }
+    ey = y;
+    ez = z;
+}
+
+__device__ __forceinline__ void bwd_local(double r, double (&v)[LC], double &ew, double &ex)
+{
+    double w = 0.0, x = 0.0;
+#pragma unroll
+    for (int k = LC - 1; k >= 0; --k) {
+        w = fma(r, w, v[k]);
+        x = fma(r, x, w);
+        v[k] = x;
+    }
+    ew = w;
+    ex = x;
+}
+
+// homogeneous correction for a true incoming causal state (Y, Z) = (y_-1, z_-1)
+__device__ __forceinline__ void fwd_fix(const CompositeCoef &c, double (&v)[LC], double Y, double Z)
+{
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[k], fma((double)(k + 1), Y, Z), v[k]);
+}
+
+// ... and for a true incoming anti-causal state (W, X) = (w_LC, x_LC)
+__device__ __forceinline__ void bwd_fix(const CompositeCoef &c, double (&v)[LC], double W, double X)
+{
+#pragma unroll
+    for (int k = 0; k < LC; ++k)
+        v[k] = fma(c.pw[LC - 1 - k], fma((double)(LC - k), W, X), v[k]);
+}
+
+// Shared-memory exchange area: slot s of thread q lives at sm[s*NT + q]; chunk t' of the same
+// line belongs to thread q + (t' - t)*tstride.
+struct Xchg {
+    double *sm;
+    int q, t, T, tstride;
+    __device__ __forceinline__ int nb(int dt) const
+    {
+        int tt = t + dt;
+        tt %= T;
+        if (tt < 0) tt += T;
+        return q + (tt - t) * tstride;
+    }
+    __device__ __forceinline__ void put(int slot, double v) const { sm[slot * NT + q] = v; }
+    __device__ __forceinline__ double get(int slot, int qq) const { return sm[slot * NT + qq]; }
+};
+
+// true incoming state from the local end states published in slots (sy, sz); dir = -1 looks at
+// chunks t-1, t-2, ... (causal), dir = +1 at t+1, t+2, ... (anti-causal)
+__device__ __forceinline__ void lookback(const CompositeCoef &c, const Xchg &x, int sy, int sz,
+                                         int dir, double &Y, double &Z)
+{
+    int q1 = x.nb(dir);
+    Y = x.get(sy, q1);
+    Z = x.get(sz, q1);
+#pragma unroll
+    for (int m = 2; m <= MAXLOOK; ++m) {
+        if (m <= c.nlook) {
+            int qm = x.nb(dir * m);
+            double ey = x.get(sy, qm), ez = x.get(sz, qm);
+            double p = c.look[m - 1];
+            Y = fma(p, ey, Y);
+            Z = fma(p, fma((double)(LC * (m - 1)), ey, ez), Z);
+        }
+    }
+}
+
+// publish the first and last three points of a chunk (slots s0 .. s0+5)
+__device__ __forceinline__ void put_halo(const Xchg &x, int s0, const double (&v)[LC])
+{
+    x.put(s0 + 0, v[0]);
+    x.put(s0 + 1, v[1]);
+    x.put(s0 + 2, v[2]);
+    x.put(s0 + 3, v[LC - 3]);
+    x.put(s0 + 4, v[LC - 2]);
+    x.put(s0 + 5, v[LC - 1]);
+}
+
+// assemble e = { last 3 of chunk t-1, v, first 3 of chunk t+1 }
+__device__ __forceinline__ void get_halo(const Xchg &x, int s0, const double (&v)[LC],
+                                         double (&e)[LC + 6])
+{
+    int ql = x.nb(-1), qr = x.nb(+1);
+    e[0] = x.get(s0 + 3, ql);
+    e[1] = x.get(s0 + 4, ql);
+    e[2] = x.get(s0 + 5, ql);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) e[k + 3] = v[k];
+    e[LC + 3] = x.get(s0 + 0, qr);
+    e[LC + 4] = x.get(s0 + 1, qr);
+    e[LC + 5] = x.get(s0 + 2, qr);
+}
+
+// CTA-wide barrier among the NT compute threads only (named barrier 1), so that a kernel may
+// carry extra producer warps that do not take part
+struct BarCompute {
+    __device__ __forceinline__ void operator()() const
+    {
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    }
+};
+struct BarAll {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// Solve NF right-hand sides in registers: v[f] <- A_f^-2 v[f].  Uses exchange slots
+// [s0, s0 + 4*NF); two barriers.  Every compute thread of the CTA must call it.
+template <int NF, class Bar>
+__device__ __forceinline__ void solve_chunks(const CompositeCoef *const (&c)[NF], const Xchg &x,
+                                             int s0, double (&v)[NF][LC], Bar bar)
+{
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double ey, ez;
+        fwd_local(c[f]->r, v[f], ey, ez);
+        x.put(s0 + 2 * f, ey);
+        x.put(s0 + 2 * f + 1, ez);
+    }
+    bar();
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double Y, Z, ew, ex;
+        lookback(*c[f], x, s0 + 2 * f, s0 + 2 * f + 1, -1, Y, Z);
+        fwd_fix(*c[f], v[f], Y, Z);
+        bwd_local(c[f]->r, v[f], ew, ex);
+        x.put(s0 + 2 * NF + 2 * f, ew);
+        x.put(s0 + 2 * NF + 2 * f + 1, ex);
+    }
+    bar();
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double W, X;
+        lookback(*c[f], x, s0 + 2 * NF + 2 * f, s0 + 2 * NF + 2 * f + 1, +1, W, X);
+        bwd_fix(*c[f], v[f], W, X);
+    }
+}
+
+// ---- the three pass bodies.  Inputs are the thread's chunk(s) in registers plus, for the field
+// the derivative stencil acts on, its 3-point halos (e = {halo, chunk, halo}).  Exchange slots
+// [0, nslots) are used; the caller guarantees that nobody still reads them from a previous tile.
+
+// x pass:  A = Dxx f , B = Mxx f.   slots: 8 (solve) + 6 (halo of the solved B) = 14
+constexpr int X_SLOTS = 14;
+template <class Bar>
+__device__ __forceinline__ void xpass_body(const CompositeCoef &M, const CompositeCoef &D,
+                                           const Xchg &xc, const double (&ef)[LC + 6],
+                                           double (&A)[LC], double (&B)[LC], Bar bar)
+{
+    double v[2][LC];
+    stencil<true>(D, ef, v[0]);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v[1][k] = ef[k + 3];
+    const CompositeCoef *const cs[2] = {&D, &M};
+    solve_chunks<2>(cs, xc, 0, v, bar);
+    put_halo(xc, 8, v[1]);
+    bar();
+    double e[LC + 6];
+    get_halo(xc, 8, v[1], e);
+    stencil<false>(M, e, B);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) A[k] = v[0][k];
+}
+
+// y pass:  C = Myy a + Dyy b , Dd = Myy b.   slots: 12 (solve) + 12 (halos) = 24
+constexpr int Y_SLOTS = 24;
+template <class Bar>
+__device__ __forceinline__ void ypass_body(const CompositeCoef &M, const CompositeCoef &D,
+                                           const Xchg &xc, const double (&a)[LC],
+                                           const double (&eb)[LC + 6], double (&C)[LC],
+                                           double (&Dd)[LC], Bar bar)
+{
+    double v[3][LC];   // v0 = a, v1 = S_D b, v2 = b
+    stencil<true>(D, eb, v[1]);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+        v[0][k] = a[k];
+        v[2][k] = eb[k + 3];
+    }
+    const CompositeCoef *const cs[3] = {&M, &D, &M};
+    solve_chunks<3>(cs, xc, 0, v, bar);
+    put_halo(xc, 12, v[0]);
+    put_halo(xc, 18, v[2]);
+    bar();
+    double e[LC + 6];
+    get_halo(xc, 12, v[0], e);
+    stencil<false>(M, e, C);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) C[k] += v[1][k];
+    get_halo(xc, 18, v[2], e);
+    stencil<false>(M, e, Dd);
+}
+
+// z pass:  out = Mzz c + Dzz d.   slots: 8 (solve) + 6 (halo) = 14
+constexpr int Z_SLOTS = 14;
+template <class Bar>
+__device__ __forceinline__ void zpass_body(const CompositeCoef &M, const CompositeCoef &D,
+                                           const Xchg &xc, const double (&c)[LC],
+                                           const double (&ed)[LC + 6], double (&out)[LC], Bar bar)
+{
+    double v[2][LC];   // v0 = c, v1 = S_D d
+    stencil<true>(D, ed, v[1]);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v[0][k] = c[k];
+    const CompositeCoef *const cs[2] = {&M, &D};
+    solve_chunks<2>(cs, xc, 0, v, bar);
+    put_halo(xc, 8, v[0]);
+    bar();
+    double e[LC + 6];
+    get_halo(xc, 8, v[0], e);
+    stencil<false>(M, e, out);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) out[k] += v[1][k];
+}
+
+// fixed-shape (deterministic) sum over the compute threads of a CTA through the exchange area;
+// result valid in thread q == 0.  Two barriers before the area may be reused.
+template <class Bar>
+__device__ __forceinline__ double block_sum_fixed(double v, double *sm, int q, int nthr, Bar bar)
+{
+    bar();
+    sm[q] = v;
+    bar();
+    double s = 0.0;
+    if (q < 32)
+        for (int i = q; i < nthr; i += 32) s += sm[i];
+    bar();
+    if (q < 32) sm[q] = s;
+    bar();
+    double tot = 0.0;
+    if (q == 0) {
+        const int m = nthr < 32 ? nthr : 32;
+        for (int i = 0; i < m; ++i) tot += sm[i];
+    }
+    return tot;
+}
+
+}  // namespace fast
+}  // namespace pbx

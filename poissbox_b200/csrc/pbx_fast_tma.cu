@@ -1,0 +1,551 @@
+// pbx_fast_tma.cu -- TMA-pipelined persistent kernels of the FAST schedule (sm_100a).
+//
+// Same arithmetic as the generic kernels of pbx_fast_kernels.cu (bit-identical results: both are
+// built from pbx_fast_common.cuh), different data movement:
+//
+//   * persistent CTAs (2 per SM), each looping over tiles;
+//   * a producer warp keeps the NEXT tile in flight with TMA (cp.async.bulk.tensor, completion on
+//     an mbarrier) while the 8 compute warps work on the current tile out of registers, so HBM
+//     requests are outstanding all the time instead of only between a CTA's start and its first
+//     barrier (the round-1a profile showed the generic kernels latency-bound: long-scoreboard
+//     stalls, 24 % warp occupancy, 35-59 % DRAM utilisation);
+//   * y / z pass: a tile is 8 x-columns x a whole line (x G lines), fetched as 3-D boxes
+//     (8, n, G) / (8, G, n); threads pick their chunk and the 3-point stencil halos straight out
+//     of the shared-memory tile; results go back with coalesced 64-byte row segments;
+//   * x pass: a tile is 256 consecutive 16-point chunks (8 lines of 512) seen as a 2-D tensor
+//     [chunks][16] and fetched with the 128-byte swizzle, which makes the one-chunk-per-lane
+//     128-bit reads bank-conflict free; chunk states and halos travel by warp shuffles (a line is
+//     at most one warp), and the two outputs leave through swizzled staging tiles and TMA stores.
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "pbx_fast_common.cuh"
+
+namespace pbx {
+
+using namespace fast;
+
+namespace {
+
+constexpr int XW = 8;
+constexpr int NTHR = NT + 32;                 // 8 compute warps + 1 producer warp
+constexpr int TILE_DOUBLES = 4096;            // 32 KiB per field per tile
+constexpr uint32_t TILE_BYTES = TILE_DOUBLES * 8;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a tile that never arrives traps the kernel instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// y / z pass
+// ---------------------------------------------------------------------------------------------
+struct YZT {
+    CompositeCoef M, D;
+    int nx, n, T, G, ng;      // x extent, line length, chunks per line, lines per tile, lines total
+    long long sl, sg;         // global strides along the line / between lines of a group
+    int se, sgm;              // shared-memory strides (doubles) along the line / between lines
+    int nbox, RB;             // boxes per field per tile, line points per box
+    int ntx, ntiles;          // tiles along x, total tiles
+    int zdir;                 // 0: y pass (box = (8, RB, G)), 1: z pass (box = (8, G, RB))
+};
+
+struct YZShared {
+    double tile[2][TILE_DOUBLES];
+    double xchg[Y_SLOTS * NT];
+    uint64_t full, empty;
+};
+
+template <bool ZPASS>
+__global__ void __maxnreg__(112)
+yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap map0,
+              const __grid_constant__ CUtensorMap map1, double *__restrict__ out0,
+              double *__restrict__ out1, const double *__restrict__ pv,
+              double *__restrict__ partials)
+{
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    YZShared &S = *reinterpret_cast<YZShared *>(smraw);
+    const int tid = threadIdx.x;
+    if ((smem_u32(smraw) & 127u) != 0) __trap();   // TMA destinations need 128-byte alignment
+
+    if (tid == 0) {
+        mbar_init(&S.full, 1);
+        mbar_init(&S.empty, NT);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= NT) {
+        // ===== producer warp: one lane keeps the next tile in flight =====
+        if (tid == NT) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+                if (it > 0) mbar_wait(&S.empty, (uint32_t)((it - 1) & 1));
+                const int x0 = (tile % p.ntx) * XW, g0 = (tile / p.ntx) * p.G;
+                mbar_expect_tx(&S.full, 2 * TILE_BYTES);
+                for (int b = 0; b < p.nbox; ++b) {
+                    const int i0 = b * p.RB;
+                    const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
+                    const int off = i0 * p.se;
+                    tma_load_3d(&S.tile[0][off], &map0, &S.full, x0, c1, c2);
+                    tma_load_3d(&S.tile[1][off], &map1, &S.full, x0, c1, c2);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    const int tx = tid & (XW - 1);
+    const int t = (tid >> 3) % p.T;
+    const int tz = tid / (XW * p.T);
+    Xchg xc{S.xchg, tid, t, p.T, XW};
+    const int soff = tz * p.sgm + tx;            // + i * se
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int x = (tile % p.ntx) * XW + tx;
+        const int g = (tile / p.ntx) * p.G + tz;
+        const bool live = (x < p.nx) && (g < p.ng) && (tz < p.G);
+        const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+
+        mbar_wait(&S.full, (uint32_t)(it & 1));
+        double a[LC], eb[LC + 6];
+        {
+            const double *ta = S.tile[0] + soff, *tb = S.tile[1] + soff;
+            const int i0 = t * LC;
+#pragma unroll
+            for (int k = 0; k < LC; ++k) a[k] = ta[(i0 + k) * p.se];
+#pragma unroll
+            for (int k = 0; k < LC; ++k) eb[k + 3] = tb[(i0 + k) * p.se];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int il = i0 - 3 + k, ir = i0 + LC + k;
+                if (il < 0) il += p.n;
+                if (ir >= p.n) ir -= p.n;
+                eb[k] = tb[il * p.se];
+                eb[LC + 3 + k] = tb[ir * p.se];
+            }
+        }
+        mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
+
+        if (!ZPASS) {
+            double c[LC], d[LC];
+            ypass_body(p.M, p.D, xc, a, eb, c, d, BarCompute());
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < LC; ++k) {
+                    out0[base + k * p.sl] = c[k];
+                    out1[base + k * p.sl] = d[k];
+                }
+            }
+        } else {
+            double o[LC];
+            zpass_body(p.M, p.D, xc, a, eb, o, BarCompute());
+            double dot = 0.0;
+            if (live) {
+                if (pv != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < LC; ++k) {
+                        dot = fma(__ldg(pv + base + k * p.sl), o[k], dot);
+                        out0[base + k * p.sl] = o[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < LC; ++k) out0[base + k * p.sl] = o[k];
+                }
+            }
+            if (pv != nullptr) {
+                // the halo slots (8..13) are free once everybody passed the first barrier inside
+                double tot = block_sum_fixed(dot, S.xchg + 8 * NT, tid, NT, BarCompute());
+                if (tid == 0) partials[tile] = tot;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x pass
+// ---------------------------------------------------------------------------------------------
+struct XT {
+    CompositeCoef M, D;
+    int T;                    // chunks per line (power of two, <= 32)
+    int ntiles;               // tiles of 256 chunks
+};
+
+struct XShared {
+    double tin[TILE_DOUBLES];
+    double sta[TILE_DOUBLES];
+    double stb[TILE_DOUBLES];
+    uint64_t full, empty;
+};
+
+// swizzled address of 16-byte piece j of row q (128-byte rows, TMA SWIZZLE_128B)
+__device__ __forceinline__ int swz(int q, int j) { return q * 16 + ((j ^ (q & 7)) << 1); }
+
+__device__ __forceinline__ double shfl_d(double v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src);
+}
+
+// shuffle counterpart of fast::lookback: states live in registers of the lanes of one line
+__device__ __forceinline__ void lookback_shfl(const CompositeCoef &c, double ey, double ez, int lane,
+                                              int T, int dir, double &Y, double &Z)
+{
+    const int seg = lane & ~(T - 1), t = lane & (T - 1);
+    int src = seg | ((t + dir) & (T - 1));
+    Y = shfl_d(ey, src);
+    Z = shfl_d(ez, src);
+#pragma unroll
+    for (int m = 2; m <= MAXLOOK; ++m) {
+        if (m <= c.nlook) {     // uniform across the warp
+            src = seg | ((t + dir * m) & (T - 1));
+            double y2 = shfl_d(ey, src), z2 = shfl_d(ez, src);
+            double pp = c.look[m - 1];
+            Y = fma(pp, y2, Y);
+            Z = fma(pp, fma((double)(LC * (m - 1)), y2, z2), Z);
+        }
+    }
+}
+
+__device__ __forceinline__ void solve_shfl(const CompositeCoef &c, double (&v)[LC], int lane, int T)
+{
+    double ey, ez, Y, Z;
+    fwd_local(c.r, v, ey, ez);
+    lookback_shfl(c, ey, ez, lane, T, -1, Y, Z);
+    fwd_fix(c, v, Y, Z);
+    bwd_local(c.r, v, ey, ez);
+    lookback_shfl(c, ey, ez, lane, T, +1, Y, Z);
+    bwd_fix(c, v, Y, Z);
+}
+
+__global__ void __maxnreg__(112)
+x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap mapF,
+             const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB)
+{
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    XShared &S = *reinterpret_cast<XShared *>(smraw);
+    const int tid = threadIdx.x;
+    if ((smem_u32(smraw) & 1023u) != 0) __trap();  // the 128-byte swizzle pattern repeats every 1 KiB
+    if (tid == 0) {
+        mbar_init(&S.full, 1);
+        mbar_init(&S.empty, NT);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= NT) {
+        if (tid == NT) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+                if (it > 0) mbar_wait(&S.empty, (uint32_t)((it - 1) & 1));
+                mbar_expect_tx(&S.full, TILE_BYTES);
+                tma_load_2d(S.tin, &mapF, &S.full, 0, tile * NT);
+            }
+        }
+        return;
+    }
+
+    const int lane = tid & 31;
+    const int T = p.T;
+    const int seg = lane & ~(T - 1), t = lane & (T - 1);
+    const int ql = (tid & ~31) | seg | ((t - 1) & (T - 1));   // row of the previous chunk of the line
+    const int qr = (tid & ~31) | seg | ((t + 1) & (T - 1));
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        mbar_wait(&S.full, (uint32_t)(it & 1));
+        double ef[LC + 6];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double2 v2 = *reinterpret_cast<const double2 *>(S.tin + swz(tid, j));
+            ef[3 + 2 * j] = v2.x;
+            ef[4 + 2 * j] = v2.y;
+        }
+        {
+            double2 l6 = *reinterpret_cast<const double2 *>(S.tin + swz(ql, 6));
+            double2 l7 = *reinterpret_cast<const double2 *>(S.tin + swz(ql, 7));
+            double2 r0 = *reinterpret_cast<const double2 *>(S.tin + swz(qr, 0));
+            double2 r1 = *reinterpret_cast<const double2 *>(S.tin + swz(qr, 1));
+            ef[0] = l6.y;
+            ef[1] = l7.x;
+            ef[2] = l7.y;
+            ef[LC + 3] = r0.x;
+            ef[LC + 4] = r0.y;
+            ef[LC + 5] = r1.x;
+        }
+        mbar_arrive(&S.empty);
+
+        double va[LC], vb[LC];
+        stencil<true>(p.D, ef, va);
+#pragma unroll
+        for (int k = 0; k < LC; ++k) vb[k] = ef[k + 3];
+        solve_shfl(p.D, va, lane, T);
+        solve_shfl(p.M, vb, lane, T);
+        {
+            // S_M on the solved values: halos of the neighbouring chunks by shuffle
+            double e[LC + 6];
+            const int sl = seg | ((t - 1) & (T - 1)), sr = seg | ((t + 1) & (T - 1));
+            e[0] = shfl_d(vb[LC - 3], sl);
+            e[1] = shfl_d(vb[LC - 2], sl);
+            e[2] = shfl_d(vb[LC - 1], sl);
+            e[LC + 3] = shfl_d(vb[0], sr);
+            e[LC + 4] = shfl_d(vb[1], sr);
+            e[LC + 5] = shfl_d(vb[2], sr);
+#pragma unroll
+            for (int k = 0; k < LC; ++k) e[k + 3] = vb[k];
+            stencil<false>(p.M, e, vb);
+        }
+
+        // staging tiles: wait until the previous tile's TMA stores have read them
+        if (tid == 0) tma_wait_read0();
+        BarCompute()();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<double2 *>(S.sta + swz(tid, j)) = make_double2(va[2 * j], va[2 * j + 1]);
+            *reinterpret_cast<double2 *>(S.stb + swz(tid, j)) = make_double2(vb[2 * j], vb[2 * j + 1]);
+        }
+        fence_proxy_async();
+        BarCompute()();
+        if (tid == 0) {
+            tma_store_2d(&mapA, S.sta, 0, tile * NT);
+            tma_store_2d(&mapB, S.stb, 0, tile * NT);
+            tma_commit();
+        }
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D map of a brick for the y / z pass tiles
+bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &p)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
+    cuuint64_t strides[2] = {(cuuint64_t)g.nx * 8, (cuuint64_t)g.nx * g.ny * 8};
+    cuuint32_t box[3] = {(cuuint32_t)XW, (cuuint32_t)(p.zdir ? p.G : p.RB),
+                         (cuuint32_t)(p.zdir ? p.RB : p.G)};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box,
+              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 2-D map [chunks][16] with the 128-byte swizzle for the x pass
+bool make_map_x(CUtensorMap *m, const double *base, size_t nchunks)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {16, (cuuint64_t)nchunks};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {16, (cuuint32_t)NT};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box,
+              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
+{
+    const int n = dir == 1 ? g.ny : g.nz;
+    if (n % LC || n < LC || n > 512 || (g.nx & 1)) return false;
+    p->nx = g.nx;
+    p->n = n;
+    p->T = n / LC;
+    if (NT % (XW * p->T)) return false;          // T must divide 32
+    p->G = NT / (XW * p->T);
+    p->ng = dir == 1 ? g.nz : g.ny;
+    p->sl = dir == 1 ? (long long)g.nx : (long long)g.nx * g.ny;
+    p->sg = dir == 1 ? (long long)g.nx * g.ny : (long long)g.nx;
+    p->zdir = dir == 2;
+    p->nbox = n > 256 ? 2 : 1;
+    p->RB = n / p->nbox;
+    if (p->nbox > 1 && p->G != 1) return false;
+    if (p->zdir) {          // smem layout [i][g][8]
+        p->se = p->G * XW;
+        p->sgm = XW;
+    } else {                // smem layout [g][i][8]
+        p->se = XW;
+        p->sgm = n * XW;
+    }
+    p->ntx = (g.nx + XW - 1) / XW;
+    p->ntiles = p->ntx * ((p->ng + p->G - 1) / p->G);
+    return true;
+}
+
+}  // namespace
+
+bool fast_tma_available() { return encode_fn() != nullptr; }
+
+// returns PBX_ERR_UNSUPPORTED when the shape does not fit the TMA kernels (caller falls back)
+int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
+                   double *B, long long *launches)
+{
+    const int T = g.nx / LC;
+    if (g.nx % LC || T > 32 || (T & (T - 1)) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    const size_t nchunks = g.N() / LC;
+    if (nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
+    XT p;
+    p.M = fc.M;
+    p.D = fc.D[0];
+    p.T = T;
+    p.ntiles = (int)((nchunks + NT - 1) / NT);
+    CUtensorMap mf, ma, mb;
+    if (!make_map_x(&mf, f, nchunks) || !make_map_x(&ma, A, nchunks) || !make_map_x(&mb, B, nchunks))
+        return PBX_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(XShared);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    int grid = 2 * sm_count();
+    if (grid > p.ntiles) grid = p.ntiles;
+    x_tma_kernel<<<grid, NTHR, smem, s>>>(p, mf, ma, mb);
+    if (launches) ++*launches;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
+                    const double *in1, double *out0, double *out1, const double *pvec,
+                    double *partials, long long *launches)
+{
+    YZT p;
+    if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
+    p.M = fc.M;
+    p.D = fc.D[dir];
+    CUtensorMap m0, m1;
+    if (!make_map_yz(&m0, in0, g, p) || !make_map_yz(&m1, in1, g, p)) return PBX_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(YZShared);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = 2 * sm_count();
+    if (grid > p.ntiles) grid = p.ntiles;
+    if (dir == 1)
+        yz_tma_kernel<false><<<grid, NTHR, smem, s>>>(p, m0, m1, out0, out1, nullptr, nullptr);
+    else
+        yz_tma_kernel<true><<<grid, NTHR, smem, s>>>(p, m0, m1, out0, nullptr, pvec, partials);
+    if (launches) ++*launches;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+}  // namespace pbx

@@ -127,6 +127,13 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
                const double *D, double *out, const double *p, double *dot_partials,
                int *n_partials, long long *launches);
 int fast_zpass_max_partials(const Brick &g);
+// TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
+bool fast_tma_available();
+int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
+                   double *B, long long *launches);
+int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
+                    const double *in1, double *out0, double *out1, const double *pvec,
+                    double *partials, long long *launches);
 
 }  // namespace pbx
 
@@ -145,6 +152,8 @@ struct pbx_handle_s {
 
     pbx::FastCoefs fc;
     bool fast_ok = false;
+    bool use_tma = true;     // PBX_NO_TMA=1 in the environment selects the generic kernels
+    bool use_tma_yz = false; // PBX_TMA_YZ=1: TMA-staged y/z passes as well
 
     // REFERENCE-schedule tables: [dir][kind]
     pbx::RefLineTables ref[3][2];
@@ -170,6 +179,8 @@ namespace pbx {
 int ensure_scratch(pbx_handle_s *h, int count);
 int lapl_reference(pbx_handle_s *h, const double *f, double *out);
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
+int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
+              double *out1, const double *p, double *partials);
 int grad_reference(pbx_handle_s *h, const double *f, double *df);
 int div_reference(pbx_handle_s *h, const double *f, double *out);
 int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger);

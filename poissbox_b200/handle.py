@@ -109,6 +109,12 @@ class Handle:
         check(LIB.pbx_lapl_dot_device(self._h, self._field(f), self._field(out), ctypes.c_void_p(dot.data_ptr())))
         return out, dot
 
+    def lapl_profile(self, f, out, reps=5):
+        """average ms of the x, y, z pass kernels of the FAST Laplacian (CUDA events)"""
+        ms = _lib._d3()
+        check(LIB.pbx_lapl_profile_device(self._h, self._field(f), self._field(out), int(reps), ms))
+        return tuple(ms)
+
     def grad(self, f, out=None):
         out = self.empty(3) if out is None else out
         check(LIB.pbx_grad_device(self._h, self._field(f), self._field(out, 3)))

@@ -59,9 +59,14 @@ def test_cg_matches_oracle(n, kind, rtol):
         assert reg == reo
         assert abs(itg - ito) <= 1, (itg, ito)
         m = min(len(hg), len(ho))
-        # residual histories agree while rounding differences have not yet been amplified
-        k = max(2, m // 2)
-        assert np.allclose(hg[:k], ho[:k], rtol=1e-6)
+        # residual histories agree while rounding differences have not yet been amplified (CG
+        # amplifies them exponentially; for the smooth S4 right-hand side the late iterations are
+        # governed by rounding noise, SURVEY 7 "hard parts")
+        assert np.allclose(hg[:6], ho[:6], rtol=1e-8)
+        if kind == "S3":
+            assert np.allclose(hg[: max(2, m // 2)], ho[: max(2, m // 2)], rtol=1e-6)
+        else:
+            assert np.allclose(hg[: max(2, m // 2)], ho[: max(2, m // 2)], rtol=1e-2)
         assert rng_ <= rtol * hg[0]
         # the solution solves the system (true residual, oracle operator)
         r = orc.lapl(xg, dx) - b

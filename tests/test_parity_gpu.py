@@ -265,3 +265,32 @@ def test_lapl_full_size_properties():
     assert abs(dot.item() - ref) <= 1e-13 * abs(ref)
     assert ref < 0   # negative semi-definite
     h.close()
+
+
+@pytest.mark.parametrize("shape", [(512, 512, 32), (64, 64, 64), (256, 128, 32), (32, 512, 512), (48, 80, 112)])
+def test_tma_and_generic_kernels_bit_identical(shape):
+    """the TMA-pipelined persistent kernels and the generic kernels share their arithmetic
+    (pbx_fast_common.cuh): same bits, including the fused p.Ap partial sums"""
+    import torch
+
+    nx, ny, nz = shape
+    dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    outs = []
+    for no_tma, tma_yz in (("0", "1"), ("1", "0"), ("0", "0")):
+        os.environ["PBX_NO_TMA"] = no_tma
+        os.environ["PBX_TMA_YZ"] = tma_yz
+        try:
+            h = pbx.Handle(nx, ny, nz, dx)
+        finally:
+            os.environ.pop("PBX_NO_TMA", None)
+            os.environ.pop("PBX_TMA_YZ", None)
+        h.mode = pbx.MODE_FAST
+        w, dot = h.lapl_dot(f)
+        torch.cuda.synchronize()
+        outs.append((w.clone(), dot.clone()))
+        h.close()
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0])
+        assert torch.equal(outs[0][1], o[1])
