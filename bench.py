@@ -339,7 +339,16 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
+        # independent check of the answer: true residual ||A x - b|| / ||b|| (outside the timed region)
+        rres = h2.lapl(x) - b
+        num, den = (rres * rres).sum(), (b * b).sum()
+        if world > 1:
+            dist.all_reduce(num)
+            dist.all_reduce(den)
+        true_rel = float(torch.sqrt(num / den).item())
+        del rres
         cg = {"rhs": "S4 manufactured: b = A exp(sin x + sin y + sin z), L = 2 pi", "rtol": args.cg_rtol,
+              "true_residual_rel": true_rel,
               "time_s": dt, "its": its, "reason": reason, "rnorm_rel": rnorm / hist[0] if hist[0] else 0.0,
               "ms_per_it": dt / max(1, its) * 1e3, "GDoF_it_per_s": ndof_total * its / dt / 1e9,
               "alg_bytes_per_dof_it": 152.0, "frac_of_hbm_peak": 152.0 * ndof_total * its / dt / 1e9 / peak / world,

@@ -144,9 +144,8 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
               double *out1, const double *p, double *partials)
 {
     Brick g{h->nx, h->ny, h->nz};
-    // measured on B200 at 512^3 (profiles/README.md): the TMA x pass runs at 80 % of the HBM
-    // peak against 45 % for the generic one; the 64-byte-row TMA y/z tiles are slower than the
-    // direct-load kernels (TMA row rate), so they are opt-in (PBX_TMA_YZ=1) until widened.
+    // measured on B200 at 512^3 (profiles/README.md): TMA-pipelined x / y / z passes run at
+    // 90 / 85 / 76 % of the measured HBM peak against 45 / 74 / 66 % for the generic kernels.
     if (h->use_tma && (dir == 0 || h->use_tma_yz)) {
         int rc = dir == 0 ? fast_xpass_tma(h->stream, g, h->fc, in0, out0, out1, &h->launches)
                           : fast_yzpass_tma(h->stream, g, h->fc, dir, in0, in1, out0, out1, p,
@@ -252,7 +251,7 @@ int pbx_create(int nx, int ny, int nz, const double dx[3], int device, void *ncc
         const char *e = getenv("PBX_NO_TMA");
         h->use_tma = !(e && e[0] == '1');
         e = getenv("PBX_TMA_YZ");
-        h->use_tma_yz = (e && e[0] == '1');
+        h->use_tma_yz = !(e && e[0] == '0');
     }
     h->mode = h->fast_ok ? PBX_MODE_FAST : PBX_MODE_REFERENCE;
     if (nccl_comm) {

@@ -3,14 +3,15 @@
 // Same arithmetic as the generic kernels of pbx_fast_kernels.cu (bit-identical results: both are
 // built from pbx_fast_common.cuh), different data movement:
 //
-//   * persistent CTAs (2 per SM), each looping over tiles;
-//   * a producer warp keeps the NEXT tile in flight with TMA (cp.async.bulk.tensor, completion on
-//     an mbarrier) while the 8 compute warps work on the current tile out of registers, so HBM
+//   * persistent CTAs (x pass: 2 per SM; y/z pass: 1 per SM with two compute groups), each
+//     looping over tiles;
+//   * thread 0 keeps the NEXT tile in flight with TMA (cp.async.bulk.tensor, completion on an
+//     mbarrier) while all warps work on the current tile out of registers, so HBM
 //     requests are outstanding all the time instead of only between a CTA's start and its first
 //     barrier (the round-1a profile showed the generic kernels latency-bound: long-scoreboard
 //     stalls, 24 % warp occupancy, 35-59 % DRAM utilisation);
-//   * y / z pass: a tile is 8 x-columns x a whole line (x G lines), fetched as 3-D boxes
-//     (8, n, G) / (8, G, n); threads pick their chunk and the 3-point stencil halos straight out
+//   * y / z pass: a tile is 16 x-columns x a whole line (x G lines), fetched as 3-D boxes
+//     (16, n, G) / (16, G, n); threads pick their chunk and the 3-point stencil halos straight out
 //     of the shared-memory tile; results go back with coalesced 64-byte row segments;
 //   * x pass: a tile is 256 consecutive 16-point chunks (8 lines of 512) seen as a 2-D tensor
 //     [chunks][16] and fetched with the 128-byte swizzle, which makes the one-chunk-per-lane
@@ -29,7 +30,6 @@ using namespace fast;
 namespace {
 
 constexpr int XW = 8;
-constexpr int NTHR = NT + 32;                 // 8 compute warps + 1 producer warp
 constexpr int TILE_DOUBLES = 4096;            // 32 KiB per field per tile
 constexpr uint32_t TILE_BYTES = TILE_DOUBLES * 8;
 
@@ -114,26 +114,60 @@ __device__ __forceinline__ void fence_mbar_init()
 }
 
 // ---------------------------------------------------------------------------------------------
-// y / z pass
+// y / z pass.  One CTA per SM: a producer warp and two independent compute groups of 256 threads.
+// A tile is 16 x-columns (128-byte rows, the granularity TMA moves at full rate; 64-byte rows ran
+// the TMA unit out of row throughput) x a whole line x G lines; group g works on columns
+// 8g .. 8g+7 with its own named barrier and exchange area, so the groups drift apart and one
+// computes while the other waits at a barrier.
 // ---------------------------------------------------------------------------------------------
+constexpr int XWT = 16;                        // tile width in x
+constexpr int NGRP = 2;                        // compute groups per CTA
+constexpr int NTHR_YZ = NGRP * NT;             // no separate producer warp: see issue_tile()
+constexpr int YZ_TILE_DOUBLES = 8192;          // 64 KiB per field per tile
+constexpr uint32_t YZ_TILE_BYTES = YZ_TILE_DOUBLES * 8;
+
 struct YZT {
     CompositeCoef M, D;
     int nx, n, T, G, ng;      // x extent, line length, chunks per line, lines per tile, lines total
     long long sl, sg;         // global strides along the line / between lines of a group
     int se, sgm;              // shared-memory strides (doubles) along the line / between lines
     int nbox, RB;             // boxes per field per tile, line points per box
-    int ntx, ntiles;          // tiles along x, total tiles
-    int zdir;                 // 0: y pass (box = (8, RB, G)), 1: z pass (box = (8, G, RB))
+    int ntx, ntx8, ntiles;    // tiles along x (16 wide), 8-wide sub-tiles along x, total tiles
+    int zdir;                 // 0: y pass (box = (16, RB, G)), 1: z pass (box = (16, G, RB))
 };
 
 struct YZShared {
-    double tile[2][TILE_DOUBLES];
-    double xchg[Y_SLOTS * NT];
+    double tile[2][YZ_TILE_DOUBLES];
+    double xchg[NGRP][Y_SLOTS * NT];
     uint64_t full, empty;
 };
 
+struct BarGroup {
+    int id;
+    __device__ __forceinline__ void operator()() const
+    {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory");
+    }
+};
+
+// thread 0 doubles as the TMA producer: a 17th warp would put five warps on one SM sub-partition
+// and cap the kernel at 96 registers per thread (16 K registers per sub-partition)
+__device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const CUtensorMap *map0,
+                                              const CUtensorMap *map1, int tile)
+{
+    const int x0 = (tile % p.ntx) * XWT, g0 = (tile / p.ntx) * p.G;
+    mbar_expect_tx(&S.full, 2 * YZ_TILE_BYTES);
+    for (int b = 0; b < p.nbox; ++b) {
+        const int i0 = b * p.RB;
+        const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
+        const int off = i0 * p.se;
+        tma_load_3d(&S.tile[0][off], map0, &S.full, x0, c1, c2);
+        tma_load_3d(&S.tile[1][off], map1, &S.full, x0, c1, c2);
+    }
+}
+
 template <bool ZPASS>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap map0,
               const __grid_constant__ CUtensorMap map1, double *__restrict__ out0,
               double *__restrict__ out1, const double *__restrict__ pv,
@@ -146,42 +180,27 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
 
     if (tid == 0) {
         mbar_init(&S.full, 1);
-        mbar_init(&S.empty, NT);
+        mbar_init(&S.empty, NTHR_YZ);
         fence_mbar_init();
+        if ((int)blockIdx.x < p.ntiles) yz_issue_tile(S, p, &map0, &map1, blockIdx.x);
     }
     __syncthreads();
 
-    if (tid >= NT) {
-        // ===== producer warp: one lane keeps the next tile in flight =====
-        if (tid == NT) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-                if (it > 0) mbar_wait(&S.empty, (uint32_t)((it - 1) & 1));
-                const int x0 = (tile % p.ntx) * XW, g0 = (tile / p.ntx) * p.G;
-                mbar_expect_tx(&S.full, 2 * TILE_BYTES);
-                for (int b = 0; b < p.nbox; ++b) {
-                    const int i0 = b * p.RB;
-                    const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
-                    const int off = i0 * p.se;
-                    tma_load_3d(&S.tile[0][off], &map0, &S.full, x0, c1, c2);
-                    tma_load_3d(&S.tile[1][off], &map1, &S.full, x0, c1, c2);
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== compute warps =====
-    const int tx = tid & (XW - 1);
-    const int t = (tid >> 3) % p.T;
-    const int tz = tid / (XW * p.T);
-    Xchg xc{S.xchg, tid, t, p.T, XW};
-    const int soff = tz * p.sgm + tx;            // + i * se
+    // ===== compute groups =====
+    const int grp = tid >> 8, lt = tid & (NT - 1);
+    const int tx = lt & (XW - 1);
+    const int t = (lt >> 3) % p.T;
+    const int tz = lt / (XW * p.T);
+    const BarGroup bar{1 + grp};
+    Xchg xc{S.xchg[grp], lt, t, p.T, XW};
+    const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int x = (tile % p.ntx) * XW + tx;
-        const int g = (tile / p.ntx) * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng) && (tz < p.G);
+        const int xt8 = (tile % p.ntx) * NGRP + grp;         // 8-wide sub-tile index along x
+        const int gt = tile / p.ntx;
+        const int x = xt8 * XW + tx;
+        const int g = gt * p.G + tz;
+        const bool live = (x < p.nx) && (g < p.ng);
         const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
 
         mbar_wait(&S.full, (uint32_t)(it & 1));
@@ -203,10 +222,14 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
             }
         }
         mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
+        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
+            mbar_wait(&S.empty, (uint32_t)(it & 1));       // ... and neither does anybody else
+            yz_issue_tile(S, p, &map0, &map1, tile + gridDim.x);
+        }
 
         if (!ZPASS) {
             double c[LC], d[LC];
-            ypass_body(p.M, p.D, xc, a, eb, c, d, BarCompute());
+            ypass_body(p.M, p.D, xc, a, eb, c, d, bar);
             if (live) {
 #pragma unroll
                 for (int k = 0; k < LC; ++k) {
@@ -216,7 +239,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
             }
         } else {
             double o[LC];
-            zpass_body(p.M, p.D, xc, a, eb, o, BarCompute());
+            zpass_body(p.M, p.D, xc, a, eb, o, bar);
             double dot = 0.0;
             if (live) {
                 if (pv != nullptr) {
@@ -231,9 +254,10 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
                 }
             }
             if (pv != nullptr) {
+                // one partial per 8-wide sub-tile, numbered as the generic kernel numbers its CTAs;
                 // the halo slots (8..13) are free once everybody passed the first barrier inside
-                double tot = block_sum_fixed(dot, S.xchg + 8 * NT, tid, NT, BarCompute());
-                if (tid == 0) partials[tile] = tot;
+                double tot = block_sum_fixed(dot, S.xchg[grp] + 8 * NT, lt, NT, bar);
+                if (lt == 0 && xt8 < p.ntx8) partials[gt * p.ntx8 + xt8] = tot;
             }
         }
     }
@@ -294,7 +318,7 @@ __device__ __forceinline__ void solve_shfl(const CompositeCoef &c, double (&v)[L
     bwd_fix(c, v, Y, Z);
 }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(NT, 2)
 x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap mapF,
              const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB)
 {
@@ -306,20 +330,12 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         mbar_init(&S.full, 1);
         mbar_init(&S.empty, NT);
         fence_mbar_init();
+        if ((int)blockIdx.x < p.ntiles) {
+            mbar_expect_tx(&S.full, TILE_BYTES);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, blockIdx.x * NT);
+        }
     }
     __syncthreads();
-
-    if (tid >= NT) {
-        if (tid == NT) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-                if (it > 0) mbar_wait(&S.empty, (uint32_t)((it - 1) & 1));
-                mbar_expect_tx(&S.full, TILE_BYTES);
-                tma_load_2d(S.tin, &mapF, &S.full, 0, tile * NT);
-            }
-        }
-        return;
-    }
 
     const int lane = tid & 31;
     const int T = p.T;
@@ -349,6 +365,11 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             ef[LC + 5] = r1.x;
         }
         mbar_arrive(&S.empty);
+        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
+            mbar_wait(&S.empty, (uint32_t)(it & 1));
+            mbar_expect_tx(&S.full, TILE_BYTES);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (tile + gridDim.x) * NT);
+        }
 
         double va[LC], vb[LC];
         stencil<true>(p.D, ef, va);
@@ -421,7 +442,7 @@ bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &
     if (!fn) return false;
     cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
     cuuint64_t strides[2] = {(cuuint64_t)g.nx * 8, (cuuint64_t)g.nx * g.ny * 8};
-    cuuint32_t box[3] = {(cuuint32_t)XW, (cuuint32_t)(p.zdir ? p.G : p.RB),
+    cuuint32_t box[3] = {(cuuint32_t)XWT, (cuuint32_t)(p.zdir ? p.G : p.RB),
                          (cuuint32_t)(p.zdir ? p.RB : p.G)};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box,
@@ -471,14 +492,15 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     p->nbox = n > 256 ? 2 : 1;
     p->RB = n / p->nbox;
     if (p->nbox > 1 && p->G != 1) return false;
-    if (p->zdir) {          // smem layout [i][g][8]
-        p->se = p->G * XW;
-        p->sgm = XW;
-    } else {                // smem layout [g][i][8]
-        p->se = XW;
-        p->sgm = n * XW;
+    if (p->zdir) {          // smem layout [i][g][16]
+        p->se = p->G * XWT;
+        p->sgm = XWT;
+    } else {                // smem layout [g][i][16]
+        p->se = XWT;
+        p->sgm = n * XWT;
     }
-    p->ntx = (g.nx + XW - 1) / XW;
+    p->ntx = (g.nx + XWT - 1) / XWT;
+    p->ntx8 = (g.nx + XW - 1) / XW;
     p->ntiles = p->ntx * ((p->ng + p->G - 1) / p->G);
     return true;
 }
@@ -512,7 +534,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     }
     int grid = 2 * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    x_tma_kernel<<<grid, NTHR, smem, s>>>(p, mf, ma, mb);
+    x_tma_kernel<<<grid, NT, smem, s>>>(p, mf, ma, mb);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
@@ -537,12 +559,12 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    int grid = 2 * sm_count();
+    int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     if (dir == 1)
-        yz_tma_kernel<false><<<grid, NTHR, smem, s>>>(p, m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false><<<grid, NTHR_YZ, smem, s>>>(p, m0, m1, out0, out1, nullptr, nullptr);
     else
-        yz_tma_kernel<true><<<grid, NTHR, smem, s>>>(p, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true><<<grid, NTHR_YZ, smem, s>>>(p, m0, m1, out0, nullptr, pvec, partials);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

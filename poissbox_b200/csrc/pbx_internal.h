@@ -153,7 +153,7 @@ struct pbx_handle_s {
     pbx::FastCoefs fc;
     bool fast_ok = false;
     bool use_tma = true;     // PBX_NO_TMA=1 in the environment selects the generic kernels
-    bool use_tma_yz = false; // PBX_TMA_YZ=1: TMA-staged y/z passes as well
+    bool use_tma_yz = true;  // PBX_TMA_YZ=0: generic y/z passes, TMA x pass
 
     // REFERENCE-schedule tables: [dir][kind]
     pbx::RefLineTables ref[3][2];
