@@ -101,6 +101,25 @@ int pbx_comm_init_rank(const void *id128, int nranks, int rank, int device, void
 int pbx_comm_destroy(void *comm);
 
 /* ---------------------------------------------------------------------------------------------
+ * z-slab decomposition driven phase by phase, without NCCL: for emulating P ranks in one process
+ * (tests on a single GPU) or for a host that owns the exchange itself.  A handle made by
+ * pbx_create with an ncclComm_t runs the same three steps inside pbx_lapl_device.
+ *   pbx_slab_phase1   x and y sweeps + the R <= 8 boundary "moments" per z-line for each neighbour
+ *   (exchange)        rank r's send-up array goes to rank r+1, its send-down array to rank r-1
+ *   pbx_slab_phase2   z sweep on the open slab + low-rank boundary corrections -> d2f
+ * pbx_dist_tables_host exposes the correction tables (host, no GPU needed): for each boundary
+ * s = 0 (bottom) / 1 (top), U[s][48][8], VnbM/VnbD[s][48][8] (neighbour planes) and
+ * VsM/VsD[s][48][8] (own planes, first *ncs rows), numerical rank R[s].
+ * ------------------------------------------------------------------------------------------- */
+int pbx_create_slab(int nx, int ny, int nz_local, const double dx[3], int device, int rank,
+                    int nranks, pbx_handle *h);
+int pbx_slab_phase1(pbx_handle h, const double *f);
+int pbx_slab_phase2(pbx_handle h, double *d2f);
+int pbx_slab_exchange_local(pbx_handle *hs, int n);
+int pbx_dist_tables_host(int nzl, double dz, int *ncs, int *nrow, int R[2], double *U,
+                         double *VnbM, double *VsM, double *VnbD, double *VsD);
+
+/* ---------------------------------------------------------------------------------------------
  * 3-D compact operators on device-resident fields (asynchronous on the handle's stream).
  * ------------------------------------------------------------------------------------------- */
 /* compact_schemes::lapl  src/compact_schemes.f90:17-37;  also the body of the MATSHELL MatMult

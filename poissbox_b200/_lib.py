@@ -36,6 +36,11 @@ SIGNATURES = {
     "pbx_comm_unique_id": (c_int, [c_void_p]),
     "pbx_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "pbx_comm_destroy": (c_int, [c_void_p]),
+    "pbx_create_slab": (c_int, [c_int, c_int, c_int, _d3, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "pbx_slab_phase1": (c_int, [c_void_p, c_void_p]),
+    "pbx_slab_phase2": (c_int, [c_void_p, c_void_p]),
+    "pbx_slab_exchange_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
+    "pbx_dist_tables_host": (c_int, [c_int, c_double, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),
     "pbx_lapl_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_dot_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_profile_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, _d3]),

@@ -141,20 +141,21 @@ int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger)
 // ------------------------------------------------------------------------------------------------
 // one pass (0 = x, 1 = y, 2 = z): the TMA-pipelined kernel when the shape fits, else the generic one
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
-              double *out1, const double *p, double *partials)
+              double *out1, const double *p, double *partials, const ZOpen *zop)
 {
     Brick g{h->nx, h->ny, h->nz};
+    const ZOpen zo = zop ? *zop : ZOpen();
     // measured on B200 at 512^3 (profiles/README.md): TMA-pipelined x / y / z passes run at
     // 90 / 85 / 76 % of the measured HBM peak against 45 / 74 / 66 % for the generic kernels.
     if (h->use_tma && (dir == 0 || h->use_tma_yz)) {
         int rc = dir == 0 ? fast_xpass_tma(h->stream, g, h->fc, in0, out0, out1, &h->launches)
                           : fast_yzpass_tma(h->stream, g, h->fc, dir, in0, in1, out0, out1, p,
-                                            partials, &h->launches);
+                                            partials, zo, &h->launches);
         if (rc != PBX_ERR_UNSUPPORTED) return rc;
     }
     if (dir == 0) return fast_xpass(h->stream, g, h->fc, in0, out0, out1, &h->launches);
     if (dir == 1) return fast_ypass(h->stream, g, h->fc, in0, in1, out0, out1, &h->launches);
-    return fast_zpass(h->stream, g, h->fc, in0, in1, out0, p, partials, nullptr, &h->launches);
+    return fast_zpass(h->stream, g, h->fc, in0, in1, out0, p, partials, nullptr, zo, &h->launches);
 }
 
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)

@@ -96,19 +96,70 @@ __device__ __forceinline__ void bwd_fix(const CompositeCoef &c, double (&v)[LC],
 
 // Shared-memory exchange area: slot s of thread q lives at sm[s*NT + q]; chunk t' of the same
 // line belongs to thread q + (t' - t)*tstride.
+// On an OPEN line (one slab of a z-decomposed box) chunks outside [0, T) do not exist: nb() returns
+// -1 for them and get() reads zero (zero recursion state, zero stencil halo); the coupling to the
+// neighbouring slabs is added afterwards as a low-rank correction (pbx_dist_tables.cu).
 struct Xchg {
     double *sm;
     int q, t, T, tstride;
+    int open = 0;
     __device__ __forceinline__ int nb(int dt) const
     {
         int tt = t + dt;
-        tt %= T;
-        if (tt < 0) tt += T;
+        if (open) {
+            if (tt < 0 || tt >= T) return -1;
+        } else {
+            tt %= T;
+            if (tt < 0) tt += T;
+        }
         return q + (tt - t) * tstride;
     }
     __device__ __forceinline__ void put(int slot, double v) const { sm[slot * NT + q] = v; }
-    __device__ __forceinline__ double get(int slot, int qq) const { return sm[slot * NT + qq]; }
+    __device__ __forceinline__ double get(int slot, int qq) const
+    {
+        return qq < 0 ? 0.0 : sm[slot * NT + qq];
+    }
 };
+
+// boundary correction of one chunk of an open z line: o[k] += sum_a U[row][a] m[a]
+__device__ __forceinline__ void open_correct(const ZOpen &zo, int t, int nzl, long long line,
+                                             double (&o)[LC])
+{
+    const int r0 = t * LC;
+    if (r0 < zo.nrow) {
+        double m[DIST_RMAX];
+#pragma unroll
+        for (int a = 0; a < DIST_RMAX; ++a)
+            m[a] = __ldg(zo.mA0 + a * zo.nlines + line) + __ldg(zo.mA1 + a * zo.nlines + line);
+#pragma unroll
+        for (int k = 0; k < LC; ++k) {
+            if (r0 + k < zo.nrow) {
+                const double *u = zo.UA + (size_t)(r0 + k) * DIST_RMAX;
+                double acc = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIST_RMAX; ++a) acc = fma(__ldg(u + a), m[a], acc);
+                o[k] += acc;
+            }
+        }
+    }
+    const int rb = r0 - (nzl - zo.nrow);   // row index within the top block (may be negative)
+    if (rb + LC > 0) {
+        double m[DIST_RMAX];
+#pragma unroll
+        for (int a = 0; a < DIST_RMAX; ++a)
+            m[a] = __ldg(zo.mB0 + a * zo.nlines + line) + __ldg(zo.mB1 + a * zo.nlines + line);
+#pragma unroll
+        for (int k = 0; k < LC; ++k) {
+            if (rb + k >= 0) {
+                const double *u = zo.UB + (size_t)(rb + k) * DIST_RMAX;
+                double acc = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIST_RMAX; ++a) acc = fma(__ldg(u + a), m[a], acc);
+                o[k] += acc;
+            }
+        }
+    }
+}
 
 // true incoming state from the local end states published in slots (sy, sz); dir = -1 looks at
 // chunks t-1, t-2, ... (causal), dir = +1 at t+1, t+2, ... (anti-causal)

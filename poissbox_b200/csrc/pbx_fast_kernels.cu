@@ -83,16 +83,17 @@ ypass_kernel(const __grid_constant__ YZParams p, const double *__restrict__ A,
 
 // z pass:  out = M c + D d ; optionally partial sums of pv . out (one per CTA, deterministic)
 __global__ void __launch_bounds__(NT, 2)
-zpass_kernel(const __grid_constant__ YZParams p, const double *__restrict__ Cc,
-             const double *__restrict__ Dd, double *__restrict__ out,
-             const double *__restrict__ pv, double *__restrict__ partials)
+zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen zo,
+             const double *__restrict__ Cc, const double *__restrict__ Dd,
+             double *__restrict__ out, const double *__restrict__ pv,
+             double *__restrict__ partials)
 {
     extern __shared__ double sm[];
     const int tx = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
     const int x = blockIdx.x * XW + tx;
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
-    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW};
+    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, zo.open};
     const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
 
     double c[LC], d[LC];
@@ -106,6 +107,7 @@ zpass_kernel(const __grid_constant__ YZParams p, const double *__restrict__ Cc,
     double ed[LC + 6], o[LC];
     get_halo(xc, Z_SLOTS, d, ed);
     zpass_body(p.M, p.D, xc, c, ed, o, BarAll());
+    if (zo.open && live) open_correct(zo, t, p.T * LC, (long long)x + (long long)p.nx * g, o);
 
     double dot = 0.0;
     if (live) {
@@ -290,7 +292,7 @@ int fast_zpass_max_partials(const Brick &g)
 
 int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *C,
                const double *D, double *out, const double *pvec, double *dot_partials,
-               int *n_partials, long long *launches)
+               int *n_partials, const ZOpen &zo, long long *launches)
 {
     YZParams p;
     p.M = fc.M;
@@ -303,7 +305,7 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
                                       (int)YZ_SMEM));
         attr_set = true;
     }
-    zpass_kernel<<<grid, block, YZ_SMEM, s>>>(p, C, D, out, pvec, dot_partials);
+    zpass_kernel<<<grid, block, YZ_SMEM, s>>>(p, zo, C, D, out, pvec, dot_partials);
     if (n_partials) *n_partials = (int)(grid.x * grid.y);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());

@@ -168,10 +168,10 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
 
 template <bool ZPASS>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
-yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap map0,
-              const __grid_constant__ CUtensorMap map1, double *__restrict__ out0,
-              double *__restrict__ out1, const double *__restrict__ pv,
-              double *__restrict__ partials)
+yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
+              const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+              double *__restrict__ out0, double *__restrict__ out1,
+              const double *__restrict__ pv, double *__restrict__ partials)
 {
     extern __shared__ __align__(1024) unsigned char smraw[];
     YZShared &S = *reinterpret_cast<YZShared *>(smraw);
@@ -192,7 +192,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
     const int t = (lt >> 3) % p.T;
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
-    Xchg xc{S.xchg[grp], lt, t, p.T, XW};
+    Xchg xc{S.xchg[grp], lt, t, p.T, XW, ZPASS ? zo.open : 0};
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -215,10 +215,13 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 int il = i0 - 3 + k, ir = i0 + LC + k;
-                if (il < 0) il += p.n;
-                if (ir >= p.n) ir -= p.n;
-                eb[k] = tb[il * p.se];
-                eb[LC + 3 + k] = tb[ir * p.se];
+                const bool lo = il < 0, hi = ir >= p.n;
+                if (lo) il += p.n;
+                if (hi) ir -= p.n;
+                const double vl = tb[il * p.se], vr = tb[ir * p.se];
+                const bool cut = ZPASS && zo.open;    // open line: nothing beyond the slab
+                eb[k] = (cut && lo) ? 0.0 : vl;
+                eb[LC + 3 + k] = (cut && hi) ? 0.0 : vr;
             }
         }
         mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
@@ -240,6 +243,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ CUtensorMap
         } else {
             double o[LC];
             zpass_body(p.M, p.D, xc, a, eb, o, bar);
+            if (zo.open && live) open_correct(zo, t, p.n, (long long)x + (long long)p.nx * g, o);
             double dot = 0.0;
             if (live) {
                 if (pv != nullptr) {
@@ -542,7 +546,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
 
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, long long *launches)
+                    double *partials, const ZOpen &zo, long long *launches)
 {
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
@@ -562,9 +566,9 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     if (dir == 1)
-        yz_tma_kernel<false><<<grid, NTHR_YZ, smem, s>>>(p, m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
     else
-        yz_tma_kernel<true><<<grid, NTHR_YZ, smem, s>>>(p, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/pbx.h"
 
@@ -110,6 +111,29 @@ int tdma_bwd_batch(cudaStream_t s, int n, long long nl, long long es, long long 
 int tdma_periodic_batch(cudaStream_t s, int n, long long nl, long long es, long long ls,
                         const double *a, const double *b, const double *c, double *d);
 
+// z-slab decomposition: low-rank boundary corrections (pbx_dist_tables.cu)
+constexpr int DIST_NB = 48;     // neighbour planes that matter (r^48 * 48 < 1e-21)
+constexpr int DIST_RMAX = 8;    // storage stride of the moment index (numerical rank is 7 / 5)
+struct DistSide {
+    int R = 0;
+    std::vector<double> U, VnbM, VsM, VnbD, VsD;   // row-major, DIST_RMAX columns
+};
+struct DistTables {
+    int nzl = 0, ncs = 0, nrow = 0;
+    DistSide side[2];   // 0 = bottom boundary ("A"), 1 = top boundary ("B")
+};
+int build_dist_tables(int nzl, const CompositeCoef &cm, const CompositeCoef &cd, DistTables *T);
+
+// what the z pass needs to know when the brick is one slab of a z-decomposed box
+struct ZOpen {
+    int open = 0;               // 0: periodic line (single rank); 1: open line + boundary corrections
+    int nrow = 0;               // boundary rows corrected on each side
+    const double *UA = nullptr, *UB = nullptr;           // device, [nrow][DIST_RMAX]
+    const double *mA0 = nullptr, *mA1 = nullptr;          // device, [DIST_RMAX][nlines]: received + own
+    const double *mB0 = nullptr, *mB1 = nullptr;
+    long long nlines = 0;
+};
+
 // FAST schedule passes
 struct FastCoefs {
     CompositeCoef D[3];   // derivative composite, per direction (depends on dx)
@@ -125,7 +149,7 @@ int fast_ypass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
 // zpass: C,D -> out = Mzz C + Dzz D ; optional partial sums of p.out into dot_partials
 int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *C,
                const double *D, double *out, const double *p, double *dot_partials,
-               int *n_partials, long long *launches);
+               int *n_partials, const ZOpen &zo, long long *launches);
 int fast_zpass_max_partials(const Brick &g);
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
 bool fast_tma_available();
@@ -133,7 +157,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
                    double *B, long long *launches);
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, long long *launches);
+                    double *partials, const ZOpen &zo, long long *launches);
 
 }  // namespace pbx
 
@@ -180,7 +204,7 @@ int ensure_scratch(pbx_handle_s *h, int count);
 int lapl_reference(pbx_handle_s *h, const double *f, double *out);
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
-              double *out1, const double *p, double *partials);
+              double *out1, const double *p, double *partials, const ZOpen *zo = nullptr);
 int grad_reference(pbx_handle_s *h, const double *f, double *df);
 int div_reference(pbx_handle_s *h, const double *f, double *out);
 int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger);
@@ -188,7 +212,10 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
              int *its, double *rnorm, int *reason, double *hist, int nhist);
 int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);
 void cg_free(pbx_handle_s *h);
-// z-slab decomposition over an NCCL communicator
+// z-slab decomposition over an NCCL communicator (or driven phase by phase by the caller)
+int dist_setup(pbx_handle_s *h, int rank, int nranks);
+int dist_phase1(pbx_handle_s *h, const double *f);
+int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials);
 int dist_attach(pbx_handle_s *h);
 void dist_free(pbx_handle_s *h);
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials);

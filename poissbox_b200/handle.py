@@ -29,7 +29,9 @@ def torch_to_fortran(t):
 
 
 class Handle:
-    def __init__(self, nx, ny, nz, dx, device=0, comm=None):
+    def __init__(self, nx, ny, nz, dx, device=0, comm=None, slab=None):
+        """nz is the LOCAL number of planes.  comm: an ncclComm_t (int) for the z-slab
+        decomposition over NCCL; slab=(rank, nranks): a phase-driven slab handle (no NCCL)."""
         import torch
 
         self._torch = torch
@@ -37,8 +39,26 @@ class Handle:
         self.dx = tuple(float(v) for v in dx)
         self.device = int(device)
         self._h = ctypes.c_void_p()
-        check(LIB.pbx_create(self.nx, self.ny, self.nz, _lib._d3(*self.dx), self.device,
-                             ctypes.c_void_p(comm) if comm else None, ctypes.byref(self._h)))
+        if slab is not None:
+            check(LIB.pbx_create_slab(self.nx, self.ny, self.nz, _lib._d3(*self.dx), self.device,
+                                      int(slab[0]), int(slab[1]), ctypes.byref(self._h)))
+        else:
+            check(LIB.pbx_create(self.nx, self.ny, self.nz, _lib._d3(*self.dx), self.device,
+                                 ctypes.c_void_p(comm) if comm else None, ctypes.byref(self._h)))
+
+    # -- phase-driven z-slab decomposition (single-process emulation; see include/pbx.h) ----------
+    def slab_phase1(self, f):
+        check(LIB.pbx_slab_phase1(self._h, self._field(f)))
+
+    def slab_phase2(self, out=None):
+        out = self.empty() if out is None else out
+        check(LIB.pbx_slab_phase2(self._h, self._field(out)))
+        return out
+
+    @staticmethod
+    def slab_exchange_local(handles):
+        arr = (ctypes.c_void_p * len(handles))(*[h._h for h in handles])
+        check(LIB.pbx_slab_exchange_local(arr, len(handles)))
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self):

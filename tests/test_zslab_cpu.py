@@ -1,0 +1,53 @@
+"""CPU tests of the N>1 (z-slab) path: the correction tables the C library builds, and the
+moments -> exchange -> correction protocol, first in one process and then across two processes with
+torch.distributed (gloo), against a dense periodic evaluation of the z pass."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import zslab_model as zm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("P,nzl,dz", [(2, 64, 1 / 128), (8, 64, 1 / 512), (4, 128, 2 * np.pi / 512), (3, 80, 0.01)])
+def test_slab_protocol_single_process(P, nzl, dz):
+    rng = np.random.default_rng(P * 1000 + nzl)
+    nl = 5
+    c = rng.uniform(-1, 1, (P * nzl, nl))
+    d = rng.uniform(-1, 1, (P * nzl, nl))
+    T = zm.tables(nzl, dz)
+    assert T["R"][0] <= 8 and T["R"][1] <= 8 and T["R"][0] >= 4
+    mom = [zm.moments(T, c[p * nzl:(p + 1) * nzl], d[p * nzl:(p + 1) * nzl]) for p in range(P)]
+    out = np.empty_like(c)
+    for p in range(P):
+        lo, up = (p - 1) % P, (p + 1) % P
+        loc = zm.local_open(c[p * nzl:(p + 1) * nzl], d[p * nzl:(p + 1) * nzl], dz)
+        m_a = mom[lo][0] + mom[p][2]      # lower's send_up + my self_a
+        m_b = mom[up][1] + mom[p][3]      # upper's send_dn + my self_b
+        out[p * nzl:(p + 1) * nzl] = zm.correct(T, loc, m_a, m_b)
+    truth = zm.periodic_truth(c, d, dz)
+    assert np.max(np.abs(out - truth)) <= 5e-15 * np.max(np.abs(truth))
+
+
+def test_too_thin_slab_rejected():
+    import poissbox_b200 as pbx
+
+    with pytest.raises(pbx.PbxError) as e:
+        zm.tables(48, 0.01)
+    assert e.value.code == 4
+
+
+def test_slab_protocol_gloo_world2():
+    """two processes, gloo: each owns one slab and exchanges its moments with send/recv"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "zslab_gloo_worker.py"), str(r), "2"],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ZSLAB_OK" in o, o

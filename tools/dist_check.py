@@ -1,0 +1,70 @@
+"""torchrun worker: checks the NCCL z-slab path (pbx_create with an ncclComm_t) on N GPUs against a
+single-GPU evaluation of the same global problem, for the Laplacian and for the CG.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29555 tools/dist_check.py [n]
+"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import poissbox_b200 as pbx
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+nzl = n // world
+
+idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    raw = (ctypes.c_ubyte * 128)()
+    pbx.check(pbx.LIB.pbx_comm_unique_id(raw))
+    idbuf = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+dist.broadcast(idbuf, 0)
+raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist())
+comm = ctypes.c_void_p()
+pbx.check(pbx.LIB.pbx_comm_init_rank(raw, world, rank, local, ctypes.byref(comm)))
+
+dx = (1.0 / n,) * 3
+g = torch.Generator(device=dev).manual_seed(1234)          # same seed: every rank builds the global field
+f = torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+whole = pbx.Handle(n, n, n, dx, device=local)
+ref = whole.lapl(f)
+h = pbx.Handle(n, n, nzl, dx, device=local, comm=comm.value)
+mine = f[rank * nzl:(rank + 1) * nzl].contiguous()
+out = h.lapl(mine)
+torch.cuda.synchronize()
+scale = ref.abs().max().item()
+err = (out - ref[rank * nzl:(rank + 1) * nzl]).abs().max().item() / scale
+w, dot = h.lapl_dot(mine)
+dref = torch.dot(f.flatten(), ref.flatten()).item()
+derr = abs(dot.item() - dref) / abs(dref)
+
+# CG: b = A x_true on the global grid; the slab solve must take the same iterations (+-1)
+b = ref
+x1, its1, rn1, why1, hist1 = whole.cg_solve(b, rtol=1e-8)
+bl = b[rank * nzl:(rank + 1) * nzl].contiguous()
+xs, its2, rn2, why2, hist2 = h.cg_solve(bl, rtol=1e-8)
+torch.cuda.synchronize()
+xerr = (xs - x1[rank * nzl:(rank + 1) * nzl]).norm().item() / x1.norm().item()
+m = min(len(hist1), len(hist2)) // 2
+herr = float(np.max(np.abs(hist1[:m] - hist2[:m]) / hist1[:m]))
+ok = err <= 1e-13 and derr <= 1e-12 and why1 == why2 == 2 and abs(its1 - its2) <= 1 and xerr <= 1e-5 and herr <= 1e-6
+res = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(res, op=dist.ReduceOp.MIN)
+print(f"rank {rank}/{world}: lapl err {err:.2e} dot err {derr:.2e} cg its {its1} vs {its2} reasons {why1},{why2} "
+      f"xerr {xerr:.2e} hist err {herr:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+h.close()
+whole.close()
+pbx.LIB.pbx_comm_destroy(comm)
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST_CHECK_OK" if res.item() == 1.0 else "DIST_CHECK_FAIL", flush=True)
+sys.exit(0 if res.item() == 1.0 else 1)
