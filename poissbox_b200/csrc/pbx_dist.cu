@@ -4,6 +4,8 @@
 // without NCCL and shares the copy a host process (e.g. PyTorch) has already loaded.
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -96,58 +98,121 @@ struct DistState {
     double *send_up, *send_dn, *recv_lo, *recv_up, *self_a, *self_b;
     long long nlines = 0;
     int lower = 0, upper = 0;
+    int rows_nb[2][2], rows_s[2][2];   // [side][M, D]: table rows that matter, from the boundary
+    int rows_u[2];                      // rows of U that matter
 };
 
 namespace {
 
-// moments of the boundary planes of the two z-pass inputs: one thread per z line, coalesced in x
+// Moments of the boundary planes of the two z-pass inputs.  blockIdx.y selects the boundary
+// (0: my bottom planes, 1: my top planes); a thread owns two z lines (x, x + 1) so that every
+// table entry fetched from shared memory feeds four FMAs.  For the boundary b the planes are both
+// "neighbour columns" of the adjacent rank's block (-> send array) and "own columns" of my block
+// (-> self array).  Table rows whose entries are all below 1e-19 of the largest are skipped
+// (nM / nD planes for the interpolation / derivative part).
+struct MomArgs {
+    const double *VnbM, *VnbD, *VsM, *VsD;   // device tables of the side, [plane][DIST_RMAX]
+    double *send, *self;                      // [DIST_RMAX][nlines]
+    int Rnb, Rs;                              // moments actually used
+    int nbM, nbD, nsM, nsD;                   // planes that matter, counted from the boundary
+};
+
 __global__ void __launch_bounds__(128)
 k_moments(long long nlines, int nzl, int ncs, const double *__restrict__ C,
-          const double *__restrict__ D, const double *__restrict__ VAnbM,
-          const double *__restrict__ VAnbD, const double *__restrict__ VAsM,
-          const double *__restrict__ VAsD, const double *__restrict__ VBnbM,
-          const double *__restrict__ VBnbD, const double *__restrict__ VBsM,
-          const double *__restrict__ VBsD, double *__restrict__ send_up,
-          double *__restrict__ send_dn, double *__restrict__ self_a, double *__restrict__ self_b)
+          const double *__restrict__ D, const __grid_constant__ MomArgs bot,
+          const __grid_constant__ MomArgs top)
 {
-    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlines) return;
-    double up[DIST_RMAX], dn[DIST_RMAX], sa[DIST_RMAX], sb[DIST_RMAX];
-#pragma unroll
-    for (int a = 0; a < DIST_RMAX; ++a) up[a] = dn[a] = sa[a] = sb[a] = 0.0;
-    // bottom planes: neighbour columns of the lower rank's top block (B), own columns of my block A
-    for (int k = 0; k < DIST_NB; ++k) {
-        const double c = __ldg(C + (long long)k * nlines + l), d = __ldg(D + (long long)k * nlines + l);
-#pragma unroll
-        for (int a = 0; a < DIST_RMAX; ++a)
-            dn[a] = fma(__ldg(VBnbM + k * DIST_RMAX + a), c, fma(__ldg(VBnbD + k * DIST_RMAX + a), d, dn[a]));
-        if (k < ncs) {
-#pragma unroll
-            for (int a = 0; a < DIST_RMAX; ++a)
-                sa[a] = fma(__ldg(VAsM + k * DIST_RMAX + a), c, fma(__ldg(VAsD + k * DIST_RMAX + a), d, sa[a]));
-        }
+    __shared__ __align__(16) double tab[4][DIST_NB][DIST_RMAX];
+    const bool is_top = blockIdx.y == 1;
+    const MomArgs &A = is_top ? top : bot;
+    for (int i = threadIdx.x; i < DIST_NB * DIST_RMAX; i += blockDim.x) {
+        const int k = i / DIST_RMAX;
+        (&tab[0][0][0])[i] = A.VnbM[i];
+        (&tab[1][0][0])[i] = A.VnbD[i];
+        (&tab[2][0][0])[i] = k < ncs ? A.VsM[i] : 0.0;
+        (&tab[3][0][0])[i] = k < ncs ? A.VsD[i] : 0.0;
     }
-    // top planes: neighbour columns of the upper rank's bottom block (A), own columns of my block B
-    for (int j = 0; j < DIST_NB; ++j) {
-        const int k = nzl - DIST_NB + j;
-        const double c = __ldg(C + (long long)k * nlines + l), d = __ldg(D + (long long)k * nlines + l);
+    __syncthreads();
+    const long long l = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (l >= nlines) return;
+    const bool two = l + 1 < nlines;
+    double nb0[DIST_RMAX], nb1[DIST_RMAX], sf0[DIST_RMAX], sf1[DIST_RMAX];
 #pragma unroll
-        for (int a = 0; a < DIST_RMAX; ++a)
-            up[a] = fma(__ldg(VAnbM + j * DIST_RMAX + a), c, fma(__ldg(VAnbD + j * DIST_RMAX + a), d, up[a]));
-        const int js = k - (nzl - ncs);
-        if (js >= 0) {
+    for (int a = 0; a < DIST_RMAX; ++a) nb0[a] = nb1[a] = sf0[a] = sf1[a] = 0.0;
+    // j counts planes in the table's own order: for the bottom boundary table row j is plane j;
+    // for the top boundary the neighbour table row j is plane nzl-NB+j and the own-column table
+    // row j is plane nzl-ncs+j
+    const int nmax = DIST_NB;
+    for (int j = 0; j < nmax; ++j) {
+        const int k = is_top ? nzl - DIST_NB + j : j;
+        const double2 c = two ? *reinterpret_cast<const double2 *>(C + (long long)k * nlines + l)
+                              : make_double2(C[(long long)k * nlines + l], 0.0);
+        const double2 d = two ? *reinterpret_cast<const double2 *>(D + (long long)k * nlines + l)
+                              : make_double2(D[(long long)k * nlines + l], 0.0);
+        // distance from the boundary decides whether the row still matters
+        const int dist = is_top ? DIST_NB - 1 - j : j;
+        if (dist < A.nbM) {
 #pragma unroll
-            for (int a = 0; a < DIST_RMAX; ++a)
-                sb[a] = fma(__ldg(VBsM + js * DIST_RMAX + a), c, fma(__ldg(VBsD + js * DIST_RMAX + a), d, sb[a]));
+            for (int a = 0; a < DIST_RMAX; ++a) {
+                const double v = tab[0][j][a];
+                nb0[a] = fma(v, c.x, nb0[a]);
+                nb1[a] = fma(v, c.y, nb1[a]);
+            }
+        }
+        if (dist < A.nbD) {
+#pragma unroll
+            for (int a = 0; a < DIST_RMAX; ++a) {
+                const double v = tab[1][j][a];
+                nb0[a] = fma(v, d.x, nb0[a]);
+                nb1[a] = fma(v, d.y, nb1[a]);
+            }
+        }
+        const int js = is_top ? k - (nzl - ncs) : j;     // row of the own-column table
+        if (js >= 0 && js < ncs) {
+            const int ds = is_top ? ncs - 1 - js : js;
+            if (ds < A.nsM) {
+#pragma unroll
+                for (int a = 0; a < DIST_RMAX; ++a) {
+                    const double v = tab[2][js][a];
+                    sf0[a] = fma(v, c.x, sf0[a]);
+                    sf1[a] = fma(v, c.y, sf1[a]);
+                }
+            }
+            if (ds < A.nsD) {
+#pragma unroll
+                for (int a = 0; a < DIST_RMAX; ++a) {
+                    const double v = tab[3][js][a];
+                    sf0[a] = fma(v, d.x, sf0[a]);
+                    sf1[a] = fma(v, d.y, sf1[a]);
+                }
+            }
         }
     }
 #pragma unroll
     for (int a = 0; a < DIST_RMAX; ++a) {
-        send_up[a * nlines + l] = up[a];
-        send_dn[a * nlines + l] = dn[a];
-        self_a[a * nlines + l] = sa[a];
-        self_b[a * nlines + l] = sb[a];
+        if (two) {
+            *reinterpret_cast<double2 *>(A.send + a * nlines + l) = make_double2(nb0[a], nb1[a]);
+            *reinterpret_cast<double2 *>(A.self + a * nlines + l) = make_double2(sf0[a], sf1[a]);
+        } else {
+            A.send[a * nlines + l] = nb0[a];
+            A.self[a * nlines + l] = sf0[a];
+        }
     }
+}
+
+// number of leading (distance-from-boundary ordered) rows of a table that matter
+int rows_that_matter(const std::vector<double> &V, int nrows, bool top_order)
+{
+    double mx = 0.0;
+    for (double v : V) mx = std::max(mx, std::fabs(v));
+    int need = 0;
+    for (int j = 0; j < nrows; ++j) {
+        double rm = 0.0;
+        for (int a = 0; a < DIST_RMAX; ++a) rm = std::max(rm, std::fabs(V[(size_t)j * DIST_RMAX + a]));
+        const int dist = top_order ? nrows - 1 - j : j;
+        if (rm > 1e-19 * mx) need = std::max(need, dist + 1);
+    }
+    return need;
 }
 
 }  // namespace
@@ -192,6 +257,21 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
     d->self_b = d->buf + 5 * per;
     d->lower = (rank + nranks - 1) % nranks;
     d->upper = (rank + 1) % nranks;
+    // neighbour columns of the bottom block (side 0) are the lower rank's TOP planes: the row
+    // nearest to the boundary is the last one; for the top block (side 1) it is the first one.
+    // Own columns: bottom block -> first row nearest, top block -> last row nearest.
+    for (int sd = 0; sd < 2; ++sd) {
+        const DistSide &S = d->tab.side[sd];
+        d->rows_nb[sd][0] = rows_that_matter(S.VnbM, DIST_NB, sd == 0);
+        d->rows_nb[sd][1] = rows_that_matter(S.VnbD, DIST_NB, sd == 0);
+        d->rows_s[sd][0] = rows_that_matter(S.VsM, d->tab.ncs, sd == 1);
+        d->rows_s[sd][1] = rows_that_matter(S.VsD, d->tab.ncs, sd == 1);
+        d->rows_u[sd] = rows_that_matter(S.U, d->tab.nrow, sd == 1);
+    }
+    if ((h->nx & 1) != 0) {
+        set_last_error("z-slab decomposition needs an even nx");
+        return PBX_ERR_UNSUPPORTED;
+    }
     return PBX_OK;
 }
 
@@ -236,12 +316,17 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     PBX_TRY(fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr));
     PBX_TRY(fast_pass(h, 1, S[0], S[1], S[0], S[1], nullptr, nullptr));
     const double *t = d->d_tab;
-    const unsigned nb = (unsigned)((d->nlines + 127) / 128);
-    k_moments<<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, d->tab.ncs, S[0], S[1], t + d->oVnbM[0],
-                                         t + d->oVnbD[0], t + d->oVsM[0], t + d->oVsD[0],
-                                         t + d->oVnbM[1], t + d->oVnbD[1], t + d->oVsM[1],
-                                         t + d->oVsD[1], d->send_up, d->send_dn, d->self_a,
-                                         d->self_b);
+    // my BOTTOM planes are neighbour columns of the lower rank's top block (side 1) and own
+    // columns of my bottom block (side 0); my TOP planes the other way round
+    MomArgs bot{t + d->oVnbM[1], t + d->oVnbD[1], t + d->oVsM[0], t + d->oVsD[0], d->send_dn, d->self_a,
+                d->tab.side[1].R, d->tab.side[0].R, d->rows_nb[1][0], d->rows_nb[1][1],
+                d->rows_s[0][0], d->rows_s[0][1]};
+    MomArgs top{t + d->oVnbM[0], t + d->oVnbD[0], t + d->oVsM[1], t + d->oVsD[1], d->send_up, d->self_b,
+                d->tab.side[0].R, d->tab.side[1].R, d->rows_nb[0][0], d->rows_nb[0][1],
+                d->rows_s[1][0], d->rows_s[1][1]};
+    const long long pairs = (d->nlines + 1) / 2;
+    dim3 grid((unsigned)((pairs + 127) / 128), 2);
+    k_moments<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, d->tab.ncs, S[0], S[1], bot, top);
     ++h->launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
@@ -256,6 +341,10 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
     ZOpen zo;
     zo.open = 1;
     zo.nrow = d->tab.nrow;
+    zo.nrowA = d->rows_u[0];
+    zo.nrowB = d->rows_u[1];
+    zo.RA = d->tab.side[0].R;
+    zo.RB = d->tab.side[1].R;
     zo.UA = d->d_tab + d->oU[0];
     zo.UB = d->d_tab + d->oU[1];
     zo.mA0 = d->recv_lo;

@@ -121,40 +121,57 @@ struct Xchg {
     }
 };
 
-// boundary correction of one chunk of an open z line: o[k] += sum_a U[row][a] m[a]
-__device__ __forceinline__ void open_correct(const ZOpen &zo, int t, int nzl, long long line,
-                                             double (&o)[LC])
+// boundary correction of one chunk of an open z line: o[k] += sum_a U[row][a] m[a].
+// `us` is a shared-memory copy of the two U tables, [2][DIST_NB][DIST_RMAX].
+constexpr int OPEN_SMEM_DOUBLES = 2 * DIST_NB * DIST_RMAX;
+
+__device__ __forceinline__ void open_load_tables(const ZOpen &zo, double *us, int tid, int nthr)
+{
+    for (int i = tid; i < DIST_NB * DIST_RMAX; i += nthr) {
+        const bool in = i < zo.nrow * DIST_RMAX;
+        us[i] = in ? zo.UA[i] : 0.0;
+        us[DIST_NB * DIST_RMAX + i] = in ? zo.UB[i] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void open_correct(const ZOpen &zo, const double *us, int t, int nzl,
+                                             long long line, double (&o)[LC])
 {
     const int r0 = t * LC;
-    if (r0 < zo.nrow) {
+    if (r0 < zo.nrowA) {
         double m[DIST_RMAX];
 #pragma unroll
         for (int a = 0; a < DIST_RMAX; ++a)
-            m[a] = __ldg(zo.mA0 + a * zo.nlines + line) + __ldg(zo.mA1 + a * zo.nlines + line);
+            m[a] = a < zo.RA ? __ldg(zo.mA0 + a * zo.nlines + line) + __ldg(zo.mA1 + a * zo.nlines + line)
+                             : 0.0;
 #pragma unroll
         for (int k = 0; k < LC; ++k) {
-            if (r0 + k < zo.nrow) {
-                const double *u = zo.UA + (size_t)(r0 + k) * DIST_RMAX;
+            if (r0 + k < zo.nrowA) {
+                const double *u = us + (r0 + k) * DIST_RMAX;
                 double acc = 0.0;
 #pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a) acc = fma(__ldg(u + a), m[a], acc);
+                for (int a = 0; a < DIST_RMAX; ++a)
+                    if (a < zo.RA) acc = fma(u[a], m[a], acc);
                 o[k] += acc;
             }
         }
     }
     const int rb = r0 - (nzl - zo.nrow);   // row index within the top block (may be negative)
-    if (rb + LC > 0) {
+    const int first = zo.nrow - zo.nrowB;  // rows of the top block before this one do not matter
+    if (rb + LC > first) {
         double m[DIST_RMAX];
 #pragma unroll
         for (int a = 0; a < DIST_RMAX; ++a)
-            m[a] = __ldg(zo.mB0 + a * zo.nlines + line) + __ldg(zo.mB1 + a * zo.nlines + line);
+            m[a] = a < zo.RB ? __ldg(zo.mB0 + a * zo.nlines + line) + __ldg(zo.mB1 + a * zo.nlines + line)
+                             : 0.0;
 #pragma unroll
         for (int k = 0; k < LC; ++k) {
-            if (rb + k >= 0) {
-                const double *u = zo.UB + (size_t)(rb + k) * DIST_RMAX;
+            if (rb + k >= first) {
+                const double *u = us + (DIST_NB + rb + k) * DIST_RMAX;
                 double acc = 0.0;
 #pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a) acc = fma(__ldg(u + a), m[a], acc);
+                for (int a = 0; a < DIST_RMAX; ++a)
+                    if (a < zo.RB) acc = fma(u[a], m[a], acc);
                 o[k] += acc;
             }
         }

@@ -127,7 +127,9 @@ int build_dist_tables(int nzl, const CompositeCoef &cm, const CompositeCoef &cd,
 // what the z pass needs to know when the brick is one slab of a z-decomposed box
 struct ZOpen {
     int open = 0;               // 0: periodic line (single rank); 1: open line + boundary corrections
-    int nrow = 0;               // boundary rows corrected on each side
+    int nrow = 0;               // boundary rows tabulated on each side
+    int nrowA = 0, nrowB = 0;   // ... of which this many (nearest the boundary) matter
+    int RA = 0, RB = 0;         // numerical ranks (moments used)
     const double *UA = nullptr, *UB = nullptr;           // device, [nrow][DIST_RMAX]
     const double *mA0 = nullptr, *mA1 = nullptr;          // device, [DIST_RMAX][nlines]: received + own
     const double *mB0 = nullptr, *mB1 = nullptr;
