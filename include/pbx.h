@@ -116,6 +116,10 @@ int pbx_create_slab(int nx, int ny, int nz_local, const double dx[3], int device
 int pbx_slab_phase1(pbx_handle h, const double *f);
 int pbx_slab_phase2(pbx_handle h, double *d2f);
 int pbx_slab_exchange_local(pbx_handle *hs, int n);
+/* the same exchange over the handle's NCCL communicator, and the CG's scalar all-reduce (exposed
+ * for profiling the communication steps on their own) */
+int pbx_slab_exchange(pbx_handle h);
+int pbx_allreduce_sum(pbx_handle h, double *dev, int count);
 int pbx_dist_tables_host(int nzl, double dz, int *ncs, int *nrow, int R[2], double *U,
                          double *VnbM, double *VsM, double *VnbD, double *VsD);
 

@@ -459,6 +459,22 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n)
     return PBX_OK;
 }
 
+// the exchange step alone, over the handle's communicator (profiling aid)
+int pbx_slab_exchange(pbx_handle h)
+{
+    if (!h || !h->dist || !h->comm) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return dist_exchange_nccl(h);
+}
+
+// sum `count` device doubles over the handle's communicator, in place (profiling aid)
+int pbx_allreduce_sum(pbx_handle h, double *dev, int count)
+{
+    if (!h || !dev || count < 1) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return dist_allreduce_sum(h, dev, count);
+}
+
 int pbx_comm_destroy(void *comm)
 {
     if (!comm) return PBX_OK;

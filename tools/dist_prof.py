@@ -1,0 +1,41 @@
+"""torchrun worker: times the pieces of the z-slab MatMult / CG iteration over NCCL"""
+import ctypes, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import poissbox_b200 as pbx
+from poissbox_b200 import LIB, check
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+nzl = n // world
+idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    raw = (ctypes.c_ubyte * 128)(); check(LIB.pbx_comm_unique_id(raw))
+    idbuf = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+dist.broadcast(idbuf, 0)
+raw = (ctypes.c_ubyte * 128)(*idbuf.cpu().tolist()); comm = ctypes.c_void_p()
+check(LIB.pbx_comm_init_rank(raw, world, rank, local, ctypes.byref(comm)))
+h = pbx.Handle(n, n, nzl, (1.0 / n,) * 3, device=local, comm=comm.value); h.use_current_stream()
+f = torch.rand((nzl, n, n), dtype=torch.float64, device=dev) * 2 - 1
+out = h.empty(); sc = torch.zeros(4, dtype=torch.float64, device=dev)
+def tm(fn, reps=50):
+    for _ in range(5): fn()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3, (time.perf_counter() - t0) / reps * 1e6
+res = {}
+res["phase1"] = tm(lambda: h.slab_phase1(f))
+res["exchange"] = tm(lambda: check(LIB.pbx_slab_exchange(h._h)))
+res["phase2"] = tm(lambda: h.slab_phase2(out))
+res["lapl"] = tm(lambda: h.lapl(f, out))
+res["allreduce_pbx(2 doubles)"] = tm(lambda: check(LIB.pbx_allreduce_sum(h._h, ctypes.c_void_p(sc.data_ptr()), 2)))
+res["allreduce_torch(2 doubles)"] = tm(lambda: dist.all_reduce(sc[:2]))
+big = torch.zeros(2 * 1024 * 1024, dtype=torch.float64, device=dev)
+res["torch p2p 16MiB ring"] = tm(lambda: [r.wait() for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, big, (rank + 1) % world), dist.P2POp(dist.irecv, out.view(-1)[:big.numel()], (rank - 1) % world)])], reps=20)
+if rank == 0:
+    for k, (dv, host) in res.items(): print(f"{k:32s} device {dv:9.1f} us   host {host:9.1f} us", flush=True)
+h.close(); LIB.pbx_comm_destroy(comm); dist.destroy_process_group()
