@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -301,6 +302,8 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
         set_last_error("this slab handle has no communicator (phase-driven handles cannot reduce)");
         return PBX_ERR_UNSUPPORTED;
     }
+    static const bool skip = getenv("PBX_DEBUG_NO_ALLREDUCE") != nullptr;   // timing experiments only
+    if (skip) return PBX_OK;
     PBX_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->comm,
                               h->stream));
     return PBX_OK;
@@ -380,7 +383,8 @@ int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, do
         return PBX_ERR_ARG;
     }
     PBX_TRY(dist_phase1(h, f));
-    PBX_TRY(dist_exchange_nccl(h));
+    static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;   // timing experiments only
+    if (!skipx) PBX_TRY(dist_exchange_nccl(h));
     return dist_phase2(h, out, p, partials);
 }
 
