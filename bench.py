@@ -25,6 +25,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the slab exchange is two 16 MiB neighbour messages per rank: give NCCL's send/recv path more
+# channels than its default of a few per peer (must be set before NCCL initialises)
+os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
+os.environ.setdefault("NCCL_NCHANNELS_PER_NET_PEER", "16")
 
 METRIC = "GDoF/s of compact Laplacian apply; CG time-to-1e-8 at 512^3 fp64, 1-8 B200"
 ALG_BYTES_MATMULT = 80.0     # B/DoF, one sweep per axis
@@ -329,6 +334,9 @@ def run_ours(args):
         b = h2.lapl(u)
         x = h2.empty()
         del u
+        # warm-up solve (5 iterations): workspace allocation and, for N>1, NCCL's lazy
+        # peer-to-peer connection set-up are not part of the time-to-solution
+        h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=5)
         barrier()
         l1 = h2.launches
         t0 = time.perf_counter()

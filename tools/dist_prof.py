@@ -1,5 +1,7 @@
 """torchrun worker: times the pieces of the z-slab MatMult / CG iteration over NCCL"""
 import ctypes, os, sys, time
+if os.environ.get("PBX_P2P_CH"):
+    os.environ["NCCL_MIN_P2P_NCHANNELS"]=os.environ["PBX_P2P_CH"]; os.environ["NCCL_MAX_P2P_NCHANNELS"]="32"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import poissbox_b200 as pbx
