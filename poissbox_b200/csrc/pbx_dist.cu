@@ -361,13 +361,14 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 static int dist_exchange_nccl(pbx_handle_s *h)
 {
     DistState *d = (DistState *)h->dist;
-    const size_t cnt = (size_t)DIST_RMAX * d->nlines;
+    // only the R moments that exist travel: 7 planes of nx*ny doubles up, 5 down
+    const size_t cup = (size_t)d->tab.side[0].R * d->nlines, cdn = (size_t)d->tab.side[1].R * d->nlines;
     ncclComm_t c = (ncclComm_t)h->comm;
     PBX_NCCL(g_nccl.GroupStart());
-    PBX_NCCL(g_nccl.Send(d->send_up, cnt, ncclFloat64, d->upper, c, h->stream));
-    PBX_NCCL(g_nccl.Send(d->send_dn, cnt, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_lo, cnt, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_up, cnt, ncclFloat64, d->upper, c, h->stream));
+    PBX_NCCL(g_nccl.Send(d->send_up, cup, ncclFloat64, d->upper, c, h->stream));
+    PBX_NCCL(g_nccl.Send(d->send_dn, cdn, ncclFloat64, d->lower, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_lo, cup, ncclFloat64, d->lower, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_up, cdn, ncclFloat64, d->upper, c, h->stream));
     PBX_NCCL(g_nccl.GroupEnd());
     return PBX_OK;
 }
