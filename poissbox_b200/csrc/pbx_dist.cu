@@ -20,7 +20,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 
 struct Nccl {
@@ -31,6 +31,7 @@ struct Nccl {
     int (*CommCount)(const ncclComm_t, int *) = nullptr;
     int (*CommUserRank)(const ncclComm_t, int *) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -63,6 +64,7 @@ int nccl_load()
     SYM(CommCount, "ncclCommCount");
     SYM(CommUserRank, "ncclCommUserRank");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
@@ -95,8 +97,16 @@ struct DistState {
     DistTables tab;
     double *d_tab = nullptr;      // device copy of the tables, see offsets below
     size_t oU[2], oVnbM[2], oVsM[2], oVnbD[2], oVsD[2];
-    double *buf = nullptr;        // 6 moment arrays [DIST_RMAX][nlines]
-    double *send_up, *send_dn, *recv_lo, *recv_up, *self_a, *self_b;
+    double *buf = nullptr;        // 4 local moment arrays [DIST_RMAX][nlines]
+    double *send_up, *send_dn, *self_a, *self_b;
+    double *rbuf = nullptr;       // receive arrays, 2 parities x (recv_lo, recv_up); shared by cudaIpc
+    double *recv_lo[2], *recv_up[2];
+    // NVLink peer mappings of the neighbours' receive arrays (nullptr: use ncclSend/Recv)
+    void *peer_map_up = nullptr, *peer_map_lo = nullptr;
+    double *peer_up_recv_lo[2] = {nullptr, nullptr};   // where my send_up lands in the upper rank
+    double *peer_lo_recv_up[2] = {nullptr, nullptr};   // where my send_dn lands in the lower rank
+    double *sync_word = nullptr;  // device scalar all-reduced as the inter-rank barrier
+    unsigned long long epoch = 0; // MatMult counter: parity selects the receive arrays
     long long nlines = 0;
     int lower = 0, upper = 0;
     int rows_nb[2][2], rows_s[2][2];   // [side][M, D]: table rows that matter, from the boundary
@@ -248,14 +258,20 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
     PBX_CUDA(cudaMemcpy(d->d_tab, pk.data(), pk.size() * sizeof(double), cudaMemcpyHostToDevice));
     d->nlines = (long long)h->nx * h->ny;
     const size_t per = (size_t)DIST_RMAX * d->nlines;
-    PBX_CUDA(cudaMalloc(&d->buf, 6 * per * sizeof(double)));
-    PBX_CUDA(cudaMemset(d->buf, 0, 6 * per * sizeof(double)));
+    PBX_CUDA(cudaMalloc(&d->buf, 4 * per * sizeof(double)));
+    PBX_CUDA(cudaMemset(d->buf, 0, 4 * per * sizeof(double)));
     d->send_up = d->buf;
     d->send_dn = d->buf + per;
-    d->recv_lo = d->buf + 2 * per;
-    d->recv_up = d->buf + 3 * per;
-    d->self_a = d->buf + 4 * per;
-    d->self_b = d->buf + 5 * per;
+    d->self_a = d->buf + 2 * per;
+    d->self_b = d->buf + 3 * per;
+    PBX_CUDA(cudaMalloc(&d->rbuf, 4 * per * sizeof(double)));
+    PBX_CUDA(cudaMemset(d->rbuf, 0, 4 * per * sizeof(double)));
+    for (int par = 0; par < 2; ++par) {
+        d->recv_lo[par] = d->rbuf + (size_t)(2 * par) * per;
+        d->recv_up[par] = d->rbuf + (size_t)(2 * par + 1) * per;
+    }
+    PBX_CUDA(cudaMalloc(&d->sync_word, sizeof(double)));
+    PBX_CUDA(cudaMemset(d->sync_word, 0, sizeof(double)));
     d->lower = (rank + nranks - 1) % nranks;
     d->upper = (rank + 1) % nranks;
     // neighbour columns of the bottom block (side 0) are the lower rank's TOP planes: the row
@@ -282,15 +298,72 @@ int dist_attach(pbx_handle_s *h)
     int n = 1, r = 0;
     PBX_NCCL(g_nccl.CommCount((ncclComm_t)h->comm, &n));
     PBX_NCCL(g_nccl.CommUserRank((ncclComm_t)h->comm, &r));
-    return dist_setup(h, r, n);
+    PBX_TRY(dist_setup(h, r, n));
+    if (n <= 1) return PBX_OK;
+    // Exchange cudaIpc handles of the receive arrays and map the two neighbours' arrays, so that
+    // the moments kernel stores its results straight into the neighbour's memory over NVLink.
+    // Any failure leaves the ncclSend/Recv path in place.
+    DistState *d = (DistState *)h->dist;
+    const char *e = getenv("PBX_NO_PEER");
+    if (e && e[0] == '1') return PBX_OK;
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, d->rbuf) != cudaSuccess) {
+        cudaGetLastError();
+        return PBX_OK;
+    }
+    char *dall = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    PBX_CUDA(cudaMalloc(&dall, hb * (size_t)(n + 1)));
+    PBX_CUDA(cudaMemcpy(dall + hb * n, &mine, hb, cudaMemcpyHostToDevice));
+    int rc = g_nccl.AllGather(dall + hb * n, dall, hb, ncclInt8, (ncclComm_t)h->comm, h->stream);
+    std::vector<cudaIpcMemHandle_t> all(n);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    if (rc == ncclSuccess && ce == cudaSuccess)
+        ce = cudaMemcpy(all.data(), dall, hb * n, cudaMemcpyDeviceToHost);
+    cudaFree(dall);
+    if (rc != ncclSuccess || ce != cudaSuccess) {
+        cudaGetLastError();
+        return PBX_OK;
+    }
+    bool ok = cudaIpcOpenMemHandle(&d->peer_map_up, all[d->upper], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (ok) {
+        if (d->lower == d->upper)
+            d->peer_map_lo = d->peer_map_up;
+        else
+            ok = cudaIpcOpenMemHandle(&d->peer_map_lo, all[d->lower], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    // every rank must take the same path: agree on success with an all-reduce
+    double flag = ok ? 0.0 : 1.0;
+    PBX_CUDA(cudaMemcpy(d->sync_word, &flag, sizeof flag, cudaMemcpyHostToDevice));
+    PBX_NCCL(g_nccl.AllReduce(d->sync_word, d->sync_word, 1, ncclFloat64, ncclSum, (ncclComm_t)h->comm, h->stream));
+    PBX_CUDA(cudaMemcpyAsync(&flag, d->sync_word, sizeof flag, cudaMemcpyDeviceToHost, h->stream));
+    PBX_CUDA(cudaStreamSynchronize(h->stream));
+    cudaGetLastError();
+    if (flag != 0.0) {
+        if (d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_up);
+        if (d->peer_map_lo && d->peer_map_lo != d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_lo);
+        d->peer_map_up = d->peer_map_lo = nullptr;
+        cudaGetLastError();
+        return PBX_OK;
+    }
+    const size_t per = (size_t)DIST_RMAX * d->nlines;
+    for (int par = 0; par < 2; ++par) {
+        d->peer_up_recv_lo[par] = (double *)d->peer_map_up + (size_t)(2 * par) * per;
+        d->peer_lo_recv_up[par] = (double *)d->peer_map_lo + (size_t)(2 * par + 1) * per;
+    }
+    return PBX_OK;
 }
 
 void dist_free(pbx_handle_s *h)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return;
+    if (d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_up);
+    if (d->peer_map_lo && d->peer_map_lo != d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_lo);
     if (d->d_tab) cudaFree(d->d_tab);
     if (d->buf) cudaFree(d->buf);
+    if (d->rbuf) cudaFree(d->rbuf);
+    if (d->sync_word) cudaFree(d->sync_word);
     delete d;
     h->dist = nullptr;
 }
@@ -321,10 +394,15 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     const double *t = d->d_tab;
     // my BOTTOM planes are neighbour columns of the lower rank's top block (side 1) and own
     // columns of my bottom block (side 0); my TOP planes the other way round
-    MomArgs bot{t + d->oVnbM[1], t + d->oVnbD[1], t + d->oVsM[0], t + d->oVsD[0], d->send_dn, d->self_a,
+    ++d->epoch;
+    const int par = (int)(d->epoch & 1);
+    // with peer mappings the "send" arrays ARE the neighbours' receive arrays of this parity
+    double *dst_dn = d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn;
+    double *dst_up = d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up;
+    MomArgs bot{t + d->oVnbM[1], t + d->oVnbD[1], t + d->oVsM[0], t + d->oVsD[0], dst_dn, d->self_a,
                 d->tab.side[1].R, d->tab.side[0].R, d->rows_nb[1][0], d->rows_nb[1][1],
                 d->rows_s[0][0], d->rows_s[0][1]};
-    MomArgs top{t + d->oVnbM[0], t + d->oVnbD[0], t + d->oVsM[1], t + d->oVsD[1], d->send_up, d->self_b,
+    MomArgs top{t + d->oVnbM[0], t + d->oVnbD[0], t + d->oVsM[1], t + d->oVsD[1], dst_up, d->self_b,
                 d->tab.side[0].R, d->tab.side[1].R, d->rows_nb[0][0], d->rows_nb[0][1],
                 d->rows_s[1][0], d->rows_s[1][1]};
     const long long pairs = (d->nlines + 1) / 2;
@@ -350,9 +428,10 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
     zo.RB = d->tab.side[1].R;
     zo.UA = d->d_tab + d->oU[0];
     zo.UB = d->d_tab + d->oU[1];
-    zo.mA0 = d->recv_lo;
+    const int par = (int)(d->epoch & 1);
+    zo.mA0 = d->recv_lo[par];
     zo.mA1 = d->self_a;
-    zo.mB0 = d->recv_up;
+    zo.mB0 = d->recv_up[par];
     zo.mB1 = d->self_b;
     zo.nlines = d->nlines;
     return fast_pass(h, 2, S[0], S[1], out, nullptr, p, partials, &zo);
@@ -361,14 +440,21 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 static int dist_exchange_nccl(pbx_handle_s *h)
 {
     DistState *d = (DistState *)h->dist;
+    ncclComm_t c = (ncclComm_t)h->comm;
+    const int par = (int)(d->epoch & 1);
+    if (d->peer_map_up) {
+        // the moments kernel has already stored into the neighbours' arrays over NVLink; a
+        // one-word all-reduce is the barrier that orders their kernels before my z pass
+        PBX_NCCL(g_nccl.AllReduce(d->sync_word, d->sync_word, 1, ncclFloat64, ncclSum, c, h->stream));
+        return PBX_OK;
+    }
     // only the R moments that exist travel: 7 planes of nx*ny doubles up, 5 down
     const size_t cup = (size_t)d->tab.side[0].R * d->nlines, cdn = (size_t)d->tab.side[1].R * d->nlines;
-    ncclComm_t c = (ncclComm_t)h->comm;
     PBX_NCCL(g_nccl.GroupStart());
     PBX_NCCL(g_nccl.Send(d->send_up, cup, ncclFloat64, d->upper, c, h->stream));
     PBX_NCCL(g_nccl.Send(d->send_dn, cdn, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_lo, cup, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_up, cdn, ncclFloat64, d->upper, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_lo[par], cup, ncclFloat64, d->lower, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_up[par], cdn, ncclFloat64, d->upper, c, h->stream));
     PBX_NCCL(g_nccl.GroupEnd());
     return PBX_OK;
 }
@@ -458,8 +544,8 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n)
         DistState *d = (DistState *)hs[r]->dist;
         DistState *up = (DistState *)hs[d->upper]->dist, *lo = (DistState *)hs[d->lower]->dist;
         const size_t by = (size_t)DIST_RMAX * d->nlines * sizeof(double);
-        PBX_CUDA(cudaMemcpy(up->recv_lo, d->send_up, by, cudaMemcpyDeviceToDevice));
-        PBX_CUDA(cudaMemcpy(lo->recv_up, d->send_dn, by, cudaMemcpyDeviceToDevice));
+        PBX_CUDA(cudaMemcpy(up->recv_lo[up->epoch & 1], d->send_up, by, cudaMemcpyDeviceToDevice));
+        PBX_CUDA(cudaMemcpy(lo->recv_up[lo->epoch & 1], d->send_dn, by, cudaMemcpyDeviceToDevice));
     }
     return PBX_OK;
 }
