@@ -94,136 +94,108 @@ int nccl_fail(int e, const char *what)
 // z-slab state of a handle
 // ------------------------------------------------------------------------------------------------
 struct DistState {
-    DistTables tab;
-    double *d_tab = nullptr;      // device copy of the tables, see offsets below
-    size_t oU[2], oVnbM[2], oVsM[2], oVnbD[2], oVsD[2];
-    double *buf = nullptr;        // 4 local moment arrays [DIST_RMAX][nlines]
-    double *send_up, *send_dn, *self_a, *self_b;
+    double *buf = nullptr;        // local send arrays (used when there is no peer mapping)
+    double *send_up, *send_dn;    // [DIST_MSG][nlines]
     double *rbuf = nullptr;       // receive arrays, 2 parities x (recv_lo, recv_up); shared by cudaIpc
     double *recv_lo[2], *recv_up[2];
     // NVLink peer mappings of the neighbours' receive arrays (nullptr: use ncclSend/Recv)
     void *peer_map_up = nullptr, *peer_map_lo = nullptr;
-    double *peer_up_recv_lo[2] = {nullptr, nullptr};   // where my send_up lands in the upper rank
-    double *peer_lo_recv_up[2] = {nullptr, nullptr};   // where my send_dn lands in the lower rank
+    double *peer_up_recv_lo[2] = {nullptr, nullptr};   // where my "up" message lands in the upper rank
+    double *peer_lo_recv_up[2] = {nullptr, nullptr};   // where my "down" message lands in the lower rank
     double *sync_word = nullptr;  // device scalar all-reduced as the inter-rank barrier
     unsigned long long epoch = 0; // MatMult counter: parity selects the receive arrays
     long long nlines = 0;
     int lower = 0, upper = 0;
-    int rows_nb[2][2], rows_s[2][2];   // [side][M, D]: table rows that matter, from the boundary
-    int rows_u[2];                      // rows of U that matter
+    ZOpen zo;                     // constants of the slab z pass
 };
 
 namespace {
 
-// Moments of the boundary planes of the two z-pass inputs.  blockIdx.y selects the boundary
-// (0: my bottom planes, 1: my top planes); a thread owns two z lines (x, x + 1) so that every
-// table entry fetched from shared memory feeds four FMAs.  For the boundary b the planes are both
-// "neighbour columns" of the adjacent rank's block (-> send array) and "own columns" of my block
-// (-> self array).  Table rows whose entries are all below 1e-19 of the largest are skipped
-// (nM / nD planes for the interpolation / derivative part).
-struct MomArgs {
-    const double *VnbM, *VnbD, *VsM, *VsD;   // device tables of the side, [plane][DIST_RMAX]
-    double *send, *self;                      // [DIST_RMAX][nlines]
-    int Rnb, Rs;                              // moments actually used
-    int nbM, nbD, nsM, nsD;                   // planes that matter, counted from the boundary
-};
+constexpr int BM = 48;   // boundary planes swept for the interpolation recursion (r^48 * 48 < 1e-21)
+constexpr int BD = 24;   // ... for the derivative recursion (0.148^24 * 24 < 1e-18)
 
-__global__ void __launch_bounds__(128)
-k_moments(long long nlines, int nzl, int ncs, const double *__restrict__ C,
-          const double *__restrict__ D, const __grid_constant__ MomArgs bot,
-          const __grid_constant__ MomArgs top)
+// zero-halo derivative stencil at window position i of w[0..n): points outside the window are 0
+__device__ __forceinline__ double sd_at(const CompositeCoef &D, const double *w, int n, int i)
 {
-    __shared__ __align__(16) double tab[4][DIST_NB][DIST_RMAX];
-    const bool is_top = blockIdx.y == 1;
-    const MomArgs &A = is_top ? top : bot;
-    for (int i = threadIdx.x; i < DIST_NB * DIST_RMAX; i += blockDim.x) {
-        const int k = i / DIST_RMAX;
-        (&tab[0][0][0])[i] = A.VnbM[i];
-        (&tab[1][0][0])[i] = A.VnbD[i];
-        (&tab[2][0][0])[i] = k < ncs ? A.VsM[i] : 0.0;
-        (&tab[3][0][0])[i] = k < ncs ? A.VsD[i] : 0.0;
-    }
-    __syncthreads();
-    const long long l = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (l >= nlines) return;
-    const bool two = l + 1 < nlines;
-    double nb0[DIST_RMAX], nb1[DIST_RMAX], sf0[DIST_RMAX], sf1[DIST_RMAX];
-#pragma unroll
-    for (int a = 0; a < DIST_RMAX; ++a) nb0[a] = nb1[a] = sf0[a] = sf1[a] = 0.0;
-    // j counts planes in the table's own order: for the bottom boundary table row j is plane j;
-    // for the top boundary the neighbour table row j is plane nzl-NB+j and the own-column table
-    // row j is plane nzl-ncs+j
-    const int nmax = DIST_NB;
-    for (int j = 0; j < nmax; ++j) {
-        const int k = is_top ? nzl - DIST_NB + j : j;
-        const double2 c = two ? *reinterpret_cast<const double2 *>(C + (long long)k * nlines + l)
-                              : make_double2(C[(long long)k * nlines + l], 0.0);
-        const double2 d = two ? *reinterpret_cast<const double2 *>(D + (long long)k * nlines + l)
-                              : make_double2(D[(long long)k * nlines + l], 0.0);
-        // distance from the boundary decides whether the row still matters
-        const int dist = is_top ? DIST_NB - 1 - j : j;
-        if (dist < A.nbM) {
-#pragma unroll
-            for (int a = 0; a < DIST_RMAX; ++a) {
-                const double v = tab[0][j][a];
-                nb0[a] = fma(v, c.x, nb0[a]);
-                nb1[a] = fma(v, c.y, nb1[a]);
-            }
-        }
-        if (dist < A.nbD) {
-#pragma unroll
-            for (int a = 0; a < DIST_RMAX; ++a) {
-                const double v = tab[1][j][a];
-                nb0[a] = fma(v, d.x, nb0[a]);
-                nb1[a] = fma(v, d.y, nb1[a]);
-            }
-        }
-        const int js = is_top ? k - (nzl - ncs) : j;     // row of the own-column table
-        if (js >= 0 && js < ncs) {
-            const int ds = is_top ? ncs - 1 - js : js;
-            if (ds < A.nsM) {
-#pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a) {
-                    const double v = tab[2][js][a];
-                    sf0[a] = fma(v, c.x, sf0[a]);
-                    sf1[a] = fma(v, c.y, sf1[a]);
-                }
-            }
-            if (ds < A.nsD) {
-#pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a) {
-                    const double v = tab[3][js][a];
-                    sf0[a] = fma(v, d.x, sf0[a]);
-                    sf1[a] = fma(v, d.y, sf1[a]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < DIST_RMAX; ++a) {
-        if (two) {
-            *reinterpret_cast<double2 *>(A.send + a * nlines + l) = make_double2(nb0[a], nb1[a]);
-            *reinterpret_cast<double2 *>(A.self + a * nlines + l) = make_double2(sf0[a], sf1[a]);
-        } else {
-            A.send[a * nlines + l] = nb0[a];
-            A.self[a * nlines + l] = sf0[a];
-        }
-    }
+    auto at = [&](int k) { return (k < 0 || k >= n) ? 0.0 : w[k]; };
+    const double f0 = w[i];
+    const double d1 = fma(-2.0, f0, at(i - 1) + at(i + 1));
+    const double d2 = fma(-2.0, f0, at(i - 2) + at(i + 2));
+    const double d3 = fma(-2.0, f0, at(i - 3) + at(i + 3));
+    return fma(D.c3, d3, fma(D.c2, d2, D.c1 * d1));
 }
 
-// number of leading (distance-from-boundary ordered) rows of a table that matter
-int rows_that_matter(const std::vector<double> &V, int nrows, bool top_order)
+// Boundary sweep of the two z-pass inputs: what each neighbour needs from my slab (ZOpen in
+// pbx_internal.h lists the nine numbers of either message).  One thread per z line, coalesced in
+// x; blockIdx.y = 0 sweeps my bottom planes (message to the lower rank), 1 my top planes (to the
+// upper rank).  About 3 flops per plane for the interpolation part, 12 for the derivative part.
+__global__ void __launch_bounds__(128)
+k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
+           const __grid_constant__ CompositeCoef D, const double *__restrict__ C,
+           const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up)
 {
-    double mx = 0.0;
-    for (double v : V) mx = std::max(mx, std::fabs(v));
-    int need = 0;
-    for (int j = 0; j < nrows; ++j) {
-        double rm = 0.0;
-        for (int a = 0; a < DIST_RMAX; ++a) rm = std::max(rm, std::fabs(V[(size_t)j * DIST_RMAX + a]));
-        const int dist = top_order ? nrows - 1 - j : j;
-        if (rm > 1e-19 * mx) need = std::max(need, dist + 1);
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines) return;
+    if (blockIdx.y == 0) {
+        // ---- bottom planes: moments sum r^j u_j, sum j r^j u_j by Horner from plane BM-1 down
+        double P = 0.0, Q = 0.0;
+        double c0 = 0.0, c1 = 0.0;
+        for (int j = BM - 1; j >= 0; --j) {
+            const double c = __ldg(C + (long long)j * nlines + l);
+            Q = M.r * (Q + P);
+            P = fma(M.r, P, c);
+            if (j == 1) c1 = c;
+            if (j == 0) c0 = c;
+        }
+        double w[BD + 3];
+#pragma unroll
+        for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)j * nlines + l);
+        double PD = 0.0, QD = 0.0;
+#pragma unroll
+        for (int j = BD - 1; j >= 0; --j) {
+            const double sj = sd_at(D, w, BD + 3, j);
+            QD = D.r * (QD + PD);
+            PD = fma(D.r, PD, sj);
+        }
+        msg_dn[0 * nlines + l] = P;
+        msg_dn[1 * nlines + l] = Q;
+        msg_dn[2 * nlines + l] = PD;
+        msg_dn[3 * nlines + l] = QD;
+        msg_dn[4 * nlines + l] = w[0];
+        msg_dn[5 * nlines + l] = w[1];
+        msg_dn[6 * nlines + l] = w[2];
+        msg_dn[7 * nlines + l] = c0;
+        msg_dn[8 * nlines + l] = c1;
+    } else {
+        // ---- top planes: causal double recursion from zero state, BM (BD) planes below the top
+        double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
+        for (int j = nzl - BM; j < nzl; ++j) {
+            const double c = __ldg(C + (long long)j * nlines + l);
+            y = fma(M.r, y, c);
+            z2 = z1;
+            z1 = z;
+            z = fma(M.r, z, y);
+        }
+        double w[BD + 3];
+#pragma unroll
+        for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)(nzl - BD - 3 + j) * nlines + l);
+        double yD = 0.0, zD = 0.0;
+#pragma unroll
+        for (int j = 3; j < BD + 3; ++j) {
+            const double sj = sd_at(D, w, BD + 3, j);
+            yD = fma(D.r, yD, sj);
+            zD = fma(D.r, zD, yD);
+        }
+        msg_up[0 * nlines + l] = y;
+        msg_up[1 * nlines + l] = z;
+        msg_up[2 * nlines + l] = z1;
+        msg_up[3 * nlines + l] = z2;
+        msg_up[4 * nlines + l] = yD;
+        msg_up[5 * nlines + l] = zD;
+        msg_up[6 * nlines + l] = w[BD + 2];
+        msg_up[7 * nlines + l] = w[BD + 1];
+        msg_up[8 * nlines + l] = w[BD];
     }
-    return need;
 }
 
 }  // namespace
@@ -237,33 +209,18 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
         set_last_error("the z-slab decomposition needs the FAST schedule (sizes multiples of 16)");
         return PBX_ERR_UNSUPPORTED;
     }
+    if (h->nz < 64) {
+        set_last_error("z-slab decomposition needs at least 64 planes per rank");
+        return PBX_ERR_UNSUPPORTED;
+    }
     DistState *d = new DistState();
     h->dist = d;
-    PBX_TRY(build_dist_tables(h->nz, h->fc.M, h->fc.D[2], &d->tab));
-    // pack the tables for the device
-    std::vector<double> pk;
-    for (int s = 0; s < 2; ++s) {
-        const DistSide &S = d->tab.side[s];
-        auto add = [&](const std::vector<double> &v, size_t *off) {
-            *off = pk.size();
-            pk.insert(pk.end(), v.begin(), v.end());
-        };
-        add(S.U, &d->oU[s]);
-        add(S.VnbM, &d->oVnbM[s]);
-        add(S.VsM, &d->oVsM[s]);
-        add(S.VnbD, &d->oVnbD[s]);
-        add(S.VsD, &d->oVsD[s]);
-    }
-    PBX_CUDA(cudaMalloc(&d->d_tab, pk.size() * sizeof(double)));
-    PBX_CUDA(cudaMemcpy(d->d_tab, pk.data(), pk.size() * sizeof(double), cudaMemcpyHostToDevice));
     d->nlines = (long long)h->nx * h->ny;
-    const size_t per = (size_t)DIST_RMAX * d->nlines;
-    PBX_CUDA(cudaMalloc(&d->buf, 4 * per * sizeof(double)));
-    PBX_CUDA(cudaMemset(d->buf, 0, 4 * per * sizeof(double)));
+    const size_t per = (size_t)DIST_MSG * d->nlines;
+    PBX_CUDA(cudaMalloc(&d->buf, 2 * per * sizeof(double)));
+    PBX_CUDA(cudaMemset(d->buf, 0, 2 * per * sizeof(double)));
     d->send_up = d->buf;
     d->send_dn = d->buf + per;
-    d->self_a = d->buf + 2 * per;
-    d->self_b = d->buf + 3 * per;
     PBX_CUDA(cudaMalloc(&d->rbuf, 4 * per * sizeof(double)));
     PBX_CUDA(cudaMemset(d->rbuf, 0, 4 * per * sizeof(double)));
     for (int par = 0; par < 2; ++par) {
@@ -274,21 +231,22 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
     PBX_CUDA(cudaMemset(d->sync_word, 0, sizeof(double)));
     d->lower = (rank + nranks - 1) % nranks;
     d->upper = (rank + 1) % nranks;
-    // neighbour columns of the bottom block (side 0) are the lower rank's TOP planes: the row
-    // nearest to the boundary is the last one; for the top block (side 1) it is the first one.
-    // Own columns: bottom block -> first row nearest, top block -> last row nearest.
-    for (int sd = 0; sd < 2; ++sd) {
-        const DistSide &S = d->tab.side[sd];
-        d->rows_nb[sd][0] = rows_that_matter(S.VnbM, DIST_NB, sd == 0);
-        d->rows_nb[sd][1] = rows_that_matter(S.VnbD, DIST_NB, sd == 0);
-        d->rows_s[sd][0] = rows_that_matter(S.VsM, d->tab.ncs, sd == 1);
-        d->rows_s[sd][1] = rows_that_matter(S.VsD, d->tab.ncs, sd == 1);
-        d->rows_u[sd] = rows_that_matter(S.U, d->tab.nrow, sd == 1);
+    // closed-form responses of the anti-causal state at the first plane above the slab
+    // (sums of geometric series in q = r^2; derivation in DESIGN.md section 6)
+    ZOpen &zo = d->zo;
+    zo.open = 1;
+    zo.nlines = d->nlines;
+    const CompositeCoef *cc[2] = {&h->fc.M, &h->fc.D[2]};
+    for (int f = 0; f < 2; ++f) {
+        const double r = cc[f]->r, q = r * r, i1 = 1.0 / (1.0 - q);
+        zo.gw[f] = i1 * i1;
+        zo.gx0[f] = (1.0 + q) * i1 * i1 * i1;
+        zo.kwz[f] = r * i1;
+        zo.kwy[f] = r * i1 * i1;
+        zo.kxz[f] = r * i1 * i1;
+        zo.kxy[f] = r * (1.0 + q) * i1 * i1 * i1;
     }
-    if ((h->nx & 1) != 0) {
-        set_last_error("z-slab decomposition needs an even nx");
-        return PBX_ERR_UNSUPPORTED;
-    }
+    zo.rinv = 1.0 / h->fc.M.r;
     return PBX_OK;
 }
 
@@ -346,7 +304,7 @@ int dist_attach(pbx_handle_s *h)
         cudaGetLastError();
         return PBX_OK;
     }
-    const size_t per = (size_t)DIST_RMAX * d->nlines;
+    const size_t per = (size_t)DIST_MSG * d->nlines;
     for (int par = 0; par < 2; ++par) {
         d->peer_up_recv_lo[par] = (double *)d->peer_map_up + (size_t)(2 * par) * per;
         d->peer_lo_recv_up[par] = (double *)d->peer_map_lo + (size_t)(2 * par + 1) * per;
@@ -360,7 +318,6 @@ void dist_free(pbx_handle_s *h)
     if (!d) return;
     if (d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_up);
     if (d->peer_map_lo && d->peer_map_lo != d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_lo);
-    if (d->d_tab) cudaFree(d->d_tab);
     if (d->buf) cudaFree(d->buf);
     if (d->rbuf) cudaFree(d->rbuf);
     if (d->sync_word) cudaFree(d->sync_word);
@@ -382,7 +339,7 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
     return PBX_OK;
 }
 
-// x and y sweeps (local) and the moments of the boundary planes of the z-pass inputs
+// x and y sweeps (local) and the boundary sweep that produces the two neighbour messages
 int dist_phase1(pbx_handle_s *h, const double *f)
 {
     DistState *d = (DistState *)h->dist;
@@ -391,49 +348,29 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     double **S = h->scratch;
     PBX_TRY(fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr));
     PBX_TRY(fast_pass(h, 1, S[0], S[1], S[0], S[1], nullptr, nullptr));
-    const double *t = d->d_tab;
-    // my BOTTOM planes are neighbour columns of the lower rank's top block (side 1) and own
-    // columns of my bottom block (side 0); my TOP planes the other way round
     ++d->epoch;
     const int par = (int)(d->epoch & 1);
-    // with peer mappings the "send" arrays ARE the neighbours' receive arrays of this parity
+    // with peer mappings the messages are stored straight into the neighbours' receive arrays
     double *dst_dn = d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn;
     double *dst_up = d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up;
-    MomArgs bot{t + d->oVnbM[1], t + d->oVnbD[1], t + d->oVsM[0], t + d->oVsD[0], dst_dn, d->self_a,
-                d->tab.side[1].R, d->tab.side[0].R, d->rows_nb[1][0], d->rows_nb[1][1],
-                d->rows_s[0][0], d->rows_s[0][1]};
-    MomArgs top{t + d->oVnbM[0], t + d->oVnbD[0], t + d->oVsM[1], t + d->oVsD[1], dst_up, d->self_b,
-                d->tab.side[0].R, d->tab.side[1].R, d->rows_nb[0][0], d->rows_nb[0][1],
-                d->rows_s[1][0], d->rows_s[1][1]};
-    const long long pairs = (d->nlines + 1) / 2;
-    dim3 grid((unsigned)((pairs + 127) / 128), 2);
-    k_moments<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, d->tab.ncs, S[0], S[1], bot, top);
+    dim3 grid((unsigned)((d->nlines + 127) / 128), 2);
+    k_boundary<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn,
+                                            dst_up);
     ++h->launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
 }
 
-// z sweep on the open slab with the boundary corrections (needs recv_lo / recv_up filled)
+// z sweep on the slab, the neighbours' messages of this parity in place
 int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return PBX_ERR_ARG;
     double **S = h->scratch;
-    ZOpen zo;
-    zo.open = 1;
-    zo.nrow = d->tab.nrow;
-    zo.nrowA = d->rows_u[0];
-    zo.nrowB = d->rows_u[1];
-    zo.RA = d->tab.side[0].R;
-    zo.RB = d->tab.side[1].R;
-    zo.UA = d->d_tab + d->oU[0];
-    zo.UB = d->d_tab + d->oU[1];
     const int par = (int)(d->epoch & 1);
-    zo.mA0 = d->recv_lo[par];
-    zo.mA1 = d->self_a;
-    zo.mB0 = d->recv_up[par];
-    zo.mB1 = d->self_b;
-    zo.nlines = d->nlines;
+    ZOpen zo = d->zo;
+    zo.from_lo = d->recv_lo[par];
+    zo.from_up = d->recv_up[par];
     return fast_pass(h, 2, S[0], S[1], out, nullptr, p, partials, &zo);
 }
 
@@ -443,18 +380,17 @@ static int dist_exchange_nccl(pbx_handle_s *h)
     ncclComm_t c = (ncclComm_t)h->comm;
     const int par = (int)(d->epoch & 1);
     if (d->peer_map_up) {
-        // the moments kernel has already stored into the neighbours' arrays over NVLink; a
+        // the boundary sweep has already stored into the neighbours' arrays over NVLink; a
         // one-word all-reduce is the barrier that orders their kernels before my z pass
         PBX_NCCL(g_nccl.AllReduce(d->sync_word, d->sync_word, 1, ncclFloat64, ncclSum, c, h->stream));
         return PBX_OK;
     }
-    // only the R moments that exist travel: 7 planes of nx*ny doubles up, 5 down
-    const size_t cup = (size_t)d->tab.side[0].R * d->nlines, cdn = (size_t)d->tab.side[1].R * d->nlines;
+    const size_t cnt = (size_t)DIST_MSG * d->nlines;   // nine planes of nx*ny doubles each way
     PBX_NCCL(g_nccl.GroupStart());
-    PBX_NCCL(g_nccl.Send(d->send_up, cup, ncclFloat64, d->upper, c, h->stream));
-    PBX_NCCL(g_nccl.Send(d->send_dn, cdn, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_lo[par], cup, ncclFloat64, d->lower, c, h->stream));
-    PBX_NCCL(g_nccl.Recv(d->recv_up[par], cdn, ncclFloat64, d->upper, c, h->stream));
+    PBX_NCCL(g_nccl.Send(d->send_up, cnt, ncclFloat64, d->upper, c, h->stream));
+    PBX_NCCL(g_nccl.Send(d->send_dn, cnt, ncclFloat64, d->lower, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_lo[par], cnt, ncclFloat64, d->lower, c, h->stream));
+    PBX_NCCL(g_nccl.Recv(d->recv_up[par], cnt, ncclFloat64, d->upper, c, h->stream));
     PBX_NCCL(g_nccl.GroupEnd());
     return PBX_OK;
 }
@@ -543,7 +479,7 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n)
     for (int r = 0; r < n; ++r) {
         DistState *d = (DistState *)hs[r]->dist;
         DistState *up = (DistState *)hs[d->upper]->dist, *lo = (DistState *)hs[d->lower]->dist;
-        const size_t by = (size_t)DIST_RMAX * d->nlines * sizeof(double);
+        const size_t by = (size_t)DIST_MSG * d->nlines * sizeof(double);
         PBX_CUDA(cudaMemcpy(up->recv_lo[up->epoch & 1], d->send_up, by, cudaMemcpyDeviceToDevice));
         PBX_CUDA(cudaMemcpy(lo->recv_up[lo->epoch & 1], d->send_dn, by, cudaMemcpyDeviceToDevice));
     }

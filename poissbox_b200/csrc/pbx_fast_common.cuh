@@ -121,63 +121,6 @@ struct Xchg {
     }
 };
 
-// boundary correction of one chunk of an open z line: o[k] += sum_a U[row][a] m[a].
-// `us` is a shared-memory copy of the two U tables, [2][DIST_NB][DIST_RMAX].
-constexpr int OPEN_SMEM_DOUBLES = 2 * DIST_NB * DIST_RMAX;
-
-__device__ __forceinline__ void open_load_tables(const ZOpen &zo, double *us, int tid, int nthr)
-{
-    for (int i = tid; i < DIST_NB * DIST_RMAX; i += nthr) {
-        const bool in = i < zo.nrow * DIST_RMAX;
-        us[i] = in ? zo.UA[i] : 0.0;
-        us[DIST_NB * DIST_RMAX + i] = in ? zo.UB[i] : 0.0;
-    }
-}
-
-__device__ __forceinline__ void open_correct(const ZOpen &zo, const double *us, int t, int nzl,
-                                             long long line, double (&o)[LC])
-{
-    const int r0 = t * LC;
-    if (r0 < zo.nrowA) {
-        double m[DIST_RMAX];
-#pragma unroll
-        for (int a = 0; a < DIST_RMAX; ++a)
-            m[a] = a < zo.RA ? __ldg(zo.mA0 + a * zo.nlines + line) + __ldg(zo.mA1 + a * zo.nlines + line)
-                             : 0.0;
-#pragma unroll
-        for (int k = 0; k < LC; ++k) {
-            if (r0 + k < zo.nrowA) {
-                const double *u = us + (r0 + k) * DIST_RMAX;
-                double acc = 0.0;
-#pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a)
-                    if (a < zo.RA) acc = fma(u[a], m[a], acc);
-                o[k] += acc;
-            }
-        }
-    }
-    const int rb = r0 - (nzl - zo.nrow);   // row index within the top block (may be negative)
-    const int first = zo.nrow - zo.nrowB;  // rows of the top block before this one do not matter
-    if (rb + LC > first) {
-        double m[DIST_RMAX];
-#pragma unroll
-        for (int a = 0; a < DIST_RMAX; ++a)
-            m[a] = a < zo.RB ? __ldg(zo.mB0 + a * zo.nlines + line) + __ldg(zo.mB1 + a * zo.nlines + line)
-                             : 0.0;
-#pragma unroll
-        for (int k = 0; k < LC; ++k) {
-            if (rb + k >= first) {
-                const double *u = us + (DIST_NB + rb + k) * DIST_RMAX;
-                double acc = 0.0;
-#pragma unroll
-                for (int a = 0; a < DIST_RMAX; ++a)
-                    if (a < zo.RB) acc = fma(u[a], m[a], acc);
-                o[k] += acc;
-            }
-        }
-    }
-}
-
 // true incoming state from the local end states published in slots (sy, sz); dir = -1 looks at
 // chunks t-1, t-2, ... (causal), dir = +1 at t+1, t+2, ... (anti-causal)
 __device__ __forceinline__ void lookback(const CompositeCoef &c, const Xchg &x, int sy, int sz,
@@ -340,6 +283,192 @@ __device__ __forceinline__ void zpass_body(const CompositeCoef &M, const Composi
     bar();
     double e[LC + 6];
     get_halo(xc, 8, v[0], e);
+    stencil<false>(M, e, out);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) out[k] += v[1][k];
+}
+
+// ---- z pass of one slab of a z-decomposed box (ZOpen.open == 1) --------------------------------
+// Same computation as zpass_body on an open line, with the neighbours' influence entering as
+// (i) true stencil halos of the derivative input, (ii) a VIRTUAL chunk -1 / T whose published
+// "end state" is the true recursion state at the slab boundary (the look-back then propagates it
+// exactly: S_t = E_(t-1) + Phi S_(t-1)), (iii) true halos of the solved interpolation values.
+// Chunk 0 and chunk T-1 of each line assemble these from the received numbers (ZOpen) and
+// publish the virtual states in slots [ZV, ZV + 8).   slots: 14 + 8 = 22
+constexpr int ZV = 14;
+constexpr int ZNAT_SLOTS = 22;
+
+// look-back that knows the virtual chunk: published states in slots (sy, sz), virtual ones in
+// (vy, vz) of the thread that owns chunk 0 (dir = -1) or chunk T-1 (dir = +1) of the same line
+__device__ __forceinline__ void lookback_nat(const CompositeCoef &c, const Xchg &x, int sy, int sz,
+                                             int vy, int vz, int dir, double &Y, double &Z)
+{
+    Y = 0.0;
+    Z = 0.0;
+    const int qv = x.q + ((dir < 0 ? 0 : x.T - 1) - x.t) * x.tstride;
+#pragma unroll
+    for (int m = 1; m <= MAXLOOK; ++m) {
+        if (m <= c.nlook) {
+            const int tt = x.t + dir * m;
+            double ey = 0.0, ez = 0.0;
+            if (tt >= 0 && tt < x.T) {
+                const int qm = x.q + (tt - x.t) * x.tstride;
+                ey = x.sm[sy * NT + qm];
+                ez = x.sm[sz * NT + qm];
+            } else if (tt == -1 || tt == x.T) {
+                ey = x.sm[vy * NT + qv];
+                ez = x.sm[vz * NT + qv];
+            }
+            if (m == 1) {
+                Y = ey;
+                Z = ez;
+            } else {
+                const double p = c.look[m - 1];
+                Y = fma(p, ey, Y);
+                Z = fma(p, fma((double)(LC * (m - 1)), ey, ez), Z);
+            }
+        }
+    }
+}
+
+template <class Bar>
+__device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
+                                                const ZOpen &zo, const Xchg &xc, long long line,
+                                                const double (&c)[LC], double (&ed)[LC + 6],
+                                                double (&out)[LC], Bar bar)
+{
+    const bool first = xc.t == 0, last = xc.t == xc.T - 1;
+    double lo9[DIST_MSG], up9[DIST_MSG];
+#pragma unroll
+    for (int a = 0; a < DIST_MSG; ++a) {
+        lo9[a] = first ? __ldg(zo.from_lo + a * zo.nlines + line) : 0.0;
+        up9[a] = last ? __ldg(zo.from_up + a * zo.nlines + line) : 0.0;
+    }
+    // (i) true halos of the derivative input
+    if (first) {
+        ed[0] = lo9[8];
+        ed[1] = lo9[7];
+        ed[2] = lo9[6];
+    }
+    if (last) {
+        ed[LC + 3] = up9[4];
+        ed[LC + 4] = up9[5];
+        ed[LC + 5] = up9[6];
+    }
+    double v[2][LC];   // v0 = c (interpolation, solve first), v1 = S_D d (derivative, stencil first)
+    stencil<true>(D, ed, v[1]);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v[0][k] = c[k];
+
+    // (ii) virtual causal states at plane -1, published by chunk 0
+    if (first) {
+        const double d0 = ed[3], d1 = ed[4], d2 = ed[5], r = D.r;
+        // the lower rank's derivative recursion ran on a zero-halo stencil: add what my first
+        // three planes contribute to its last three right-hand sides
+        const double s1 = fma(D.c3, d2, fma(D.c2, d1, D.c1 * d0));
+        const double s2 = fma(D.c3, d1, D.c2 * d0);
+        const double s3 = D.c3 * d0;
+        xc.put(ZV + 0, lo9[0]);
+        xc.put(ZV + 1, lo9[1]);
+        xc.put(ZV + 2, lo9[4] + fma(r, fma(r, s3, s2), s1));
+        xc.put(ZV + 3, lo9[5] + fma(r, fma(3.0 * r, s3, 2.0 * s2), s1));
+    }
+    double ey[2], ez[2];
+    fwd_local(M.r, v[0], ey[0], ez[0]);
+    fwd_local(D.r, v[1], ey[1], ez[1]);
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        xc.put(2 * f, ey[f]);
+        xc.put(2 * f + 1, ez[f]);
+    }
+    bar();
+    double WT = 0.0, XT = 0.0, yMe = 0.0, zMe = 0.0;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const CompositeCoef &cf = f == 0 ? M : D;
+        double Y, Z, ew, ex;
+        lookback_nat(cf, xc, 2 * f, 2 * f + 1, ZV + 2 * f, ZV + 2 * f + 1, -1, Y, Z);
+        fwd_fix(cf, v[f], Y, Z);
+        if (last) {
+            // my true outgoing causal state, and with it the true anti-causal state at plane T*16
+            const double yt = fma(cf.pw[LC - 1], Y, ey[f]), zt = v[f][LC - 1];
+            double a0 = up9[2 * f], a1 = up9[2 * f + 1];
+            if (f == 1) {
+                // my last three planes contribute to the upper rank's first three right-hand sides
+                const double dm1 = ed[LC + 2], dm2 = ed[LC + 1], dm3 = ed[LC], r = D.r;
+                const double e0 = fma(D.c3, dm3, fma(D.c2, dm2, D.c1 * dm1));
+                const double e1 = fma(D.c3, dm2, D.c2 * dm1);
+                const double e2 = D.c3 * dm1;
+                a0 += fma(r, fma(r, e2, e1), e0);
+                a1 += r * fma(2.0 * r, e2, e1);
+            }
+            const double W = fma(zo.gw[f], a0, fma(zo.kwz[f], zt, zo.kwy[f] * yt));
+            const double X = fma(zo.gx0[f], a0, fma(zo.gw[f], a1, fma(zo.kxz[f], zt, zo.kxy[f] * yt)));
+            xc.put(ZV + 4 + 2 * f, W);
+            xc.put(ZV + 5 + 2 * f, X);
+            if (f == 0) {
+                WT = W;
+                XT = X;
+                yMe = yt;
+                zMe = zt;
+            }
+        }
+        bwd_local(cf.r, v[f], ew, ex);
+        xc.put(4 + 2 * f, ew);
+        xc.put(5 + 2 * f, ex);
+    }
+    bar();
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const CompositeCoef &cf = f == 0 ? M : D;
+        double W, X;
+        lookback_nat(cf, xc, 4 + 2 * f, 5 + 2 * f, ZV + 4 + 2 * f, ZV + 5 + 2 * f, +1, W, X);
+        bwd_fix(cf, v[f], W, X);
+    }
+    // (iii) halos of the solved interpolation values
+    put_halo(xc, 8, v[0]);
+    double hl[3] = {0, 0, 0}, hh[3] = {0, 0, 0};
+    if (first) {
+        // continue the anti-causal recursion into the lower rank's top three planes
+        const double r = M.r;
+        double x = v[0][0], w = fma(-r, v[0][1], x);
+        w = fma(r, w, lo9[1]);
+        x = fma(r, x, w);
+        hl[2] = x;
+        w = fma(r, w, lo9[2]);
+        x = fma(r, x, w);
+        hl[1] = x;
+        w = fma(r, w, lo9[3]);
+        x = fma(r, x, w);
+        hl[0] = x;
+    }
+    if (last) {
+        // x at the first plane above is the virtual state itself; two more planes by running the
+        // recursion upwards, with the true causal values there (upper rank's raw c0, c1 plus the
+        // homogeneous solution of my outgoing state)
+        const double r = M.r, ri = zo.rinv;
+        const double zt0 = fma(r, zMe + yMe, up9[7]);
+        const double zt1 = fma(r * r, fma(2.0, yMe, zMe), fma(2.0 * r, up9[7], up9[8]));
+        const double w1 = (WT - zt0) * ri, x1 = (XT - WT) * ri;
+        const double w2 = (w1 - zt1) * ri, x2 = (x1 - w1) * ri;
+        (void)w2;
+        hh[0] = XT;
+        hh[1] = x1;
+        hh[2] = x2;
+    }
+    bar();
+    double e[LC + 6];
+    get_halo(xc, 8, v[0], e);
+    if (first) {
+        e[0] = hl[0];
+        e[1] = hl[1];
+        e[2] = hl[2];
+    }
+    if (last) {
+        e[LC + 3] = hh[0];
+        e[LC + 4] = hh[1];
+        e[LC + 5] = hh[2];
+    }
     stencil<false>(M, e, out);
 #pragma unroll
     for (int k = 0; k < LC; ++k) out[k] += v[1][k];

@@ -94,8 +94,6 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
     Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, zo.open};
-    double *us = sm + (Z_SLOTS + 6) * NT;   // U tables of the open-line corrections
-    if (zo.open) open_load_tables(zo, us, xc.q, blockDim.x * blockDim.y * blockDim.z);
     const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
 
     double c[LC], d[LC];
@@ -104,12 +102,16 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
         c[k] = live ? __ldg(Cc + base + k * p.sl) : 0.0;
         d[k] = live ? __ldg(Dd + base + k * p.sl) : 0.0;
     }
-    put_halo(xc, Z_SLOTS, d);
+    put_halo(xc, ZNAT_SLOTS, d);
     __syncthreads();
     double ed[LC + 6], o[LC];
-    get_halo(xc, Z_SLOTS, d, ed);
-    zpass_body(p.M, p.D, xc, c, ed, o, BarAll());
-    if (zo.open && live) open_correct(zo, us, t, p.T * LC, (long long)x + (long long)p.nx * g, o);
+    get_halo(xc, ZNAT_SLOTS, d, ed);
+    if (zo.open) {
+        const long long line = live ? (long long)x + (long long)p.nx * g : 0;
+        zpass_body_slab(p.M, p.D, zo, xc, line, c, ed, o, BarAll());
+    } else {
+        zpass_body(p.M, p.D, xc, c, ed, o, BarAll());
+    }
 
     double dot = 0.0;
     if (live) {

@@ -193,11 +193,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
     Xchg xc{S.xchg[grp], lt, t, p.T, XW, ZPASS ? zo.open : 0};
-    double *us = S.xchg[grp] + Z_SLOTS * NT;    // z pass: slots 14.. are free for the U tables
-    if (ZPASS && zo.open) {
-        open_load_tables(zo, us, lt, NT);
-        bar();
-    }
+
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -247,8 +243,12 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             }
         } else {
             double o[LC];
-            zpass_body(p.M, p.D, xc, a, eb, o, bar);
-            if (zo.open && live) open_correct(zo, us, t, p.n, (long long)x + (long long)p.nx * g, o);
+            if (zo.open) {
+                const long long line = live ? (long long)x + (long long)p.nx * g : 0;
+                zpass_body_slab(p.M, p.D, zo, xc, line, a, eb, o, bar);
+            } else {
+                zpass_body(p.M, p.D, xc, a, eb, o, bar);
+            }
             double dot = 0.0;
             if (live) {
                 if (pv != nullptr) {

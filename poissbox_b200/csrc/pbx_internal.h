@@ -124,16 +124,29 @@ struct DistTables {
 };
 int build_dist_tables(int nzl, const CompositeCoef &cm, const CompositeCoef &cd, DistTables *T);
 
-// what the z pass needs to know when the brick is one slab of a z-decomposed box
+// What the z pass needs to know when the brick is one slab of a z-decomposed box (pbx_dist.cu).
+// The slab is an OPEN line; everything the rest of the periodic line contributes enters through
+// the pass's native inputs at the two slab boundaries -- recursion states and stencil halos --
+// reconstructed per z-line from DIST_MSG numbers received from each neighbour:
+//   from the lower rank (its "up" message):  0 yM, 1 zM, 2 zM', 3 zM''   causal state of the
+//       interpolation recursion at its top plane and the two previous z values,
+//       4 yD, 5 zD   causal state of the derivative recursion on its zero-halo stencil,
+//       6 d(-1), 7 d(-2), 8 d(-3)   its top three planes of the derivative input;
+//   from the upper rank (its "down" message):  0 A0M, 1 A1M, 2 A0D, 3 A1D   the moments
+//       sum r^j u_j and sum j r^j u_j of its bottom planes (u = c, resp. its zero-halo stencil of d),
+//       4 d(0), 5 d(1), 6 d(2),  7 c(0), 8 c(1).
+constexpr int DIST_MSG = 9;
 struct ZOpen {
-    int open = 0;               // 0: periodic line (single rank); 1: open line + boundary corrections
-    int nrow = 0;               // boundary rows tabulated on each side
-    int nrowA = 0, nrowB = 0;   // ... of which this many (nearest the boundary) matter
-    int RA = 0, RB = 0;         // numerical ranks (moments used)
-    const double *UA = nullptr, *UB = nullptr;           // device, [nrow][DIST_RMAX]
-    const double *mA0 = nullptr, *mA1 = nullptr;          // device, [DIST_RMAX][nlines]: received + own
-    const double *mB0 = nullptr, *mB1 = nullptr;
+    int open = 0;                                   // 0: periodic line (single rank); 1: slab
+    const double *from_lo = nullptr, *from_up = nullptr;   // device, [DIST_MSG][nlines]
     long long nlines = 0;
+    // response of the anti-causal state (w, x) at the first plane above the slab, per operator
+    // (0 = interpolation, 1 = derivative):
+    //   to the neighbour's moments:        w = gw A0,            x = gx0 A0 + gw A1
+    //   to my own outgoing causal state:   w = kwz Z + kwy Y,    x = kxz Z + kxy Y
+    double gw[2] = {0, 0}, gx0[2] = {0, 0};
+    double kwy[2] = {0, 0}, kwz[2] = {0, 0}, kxy[2] = {0, 0}, kxz[2] = {0, 0};
+    double rinv = 0;                                // 1 / r of the interpolation recursion
 };
 
 // FAST schedule passes

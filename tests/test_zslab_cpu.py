@@ -33,6 +33,21 @@ def test_slab_protocol_single_process(P, nzl, dz):
     assert np.max(np.abs(out - truth)) <= 5e-15 * np.max(np.abs(truth))
 
 
+@pytest.mark.parametrize("P,nzl,dz", [(2, 64, 1 / 128), (8, 64, 1 / 512), (4, 128, 2 * np.pi / 512), (3, 80, 0.01)])
+def test_slab_protocol_native_inputs(P, nzl, dz):
+    """the protocol the CUDA path uses: states and halos rebuilt from 9 numbers per direction"""
+    rng = np.random.default_rng(P * 77 + nzl)
+    c = rng.uniform(-1, 1, (P * nzl, 4))
+    d = rng.uniform(-1, 1, (P * nzl, 4))
+    msgs = [zm.boundary_messages(c[p * nzl:(p + 1) * nzl], d[p * nzl:(p + 1) * nzl], dz) for p in range(P)]
+    out = np.empty_like(c)
+    for p in range(P):
+        out[p * nzl:(p + 1) * nzl] = zm.slab_zpass(c[p * nzl:(p + 1) * nzl], d[p * nzl:(p + 1) * nzl], dz,
+                                                   msgs[(p - 1) % P][0], msgs[(p + 1) % P][1])
+    truth = zm.periodic_truth(c, d, dz)
+    assert np.max(np.abs(out - truth)) <= 5e-15 * np.max(np.abs(truth))
+
+
 def test_too_thin_slab_rejected():
     import poissbox_b200 as pbx
 

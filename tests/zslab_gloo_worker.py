@@ -17,8 +17,7 @@ rng = np.random.default_rng(42)                      # same stream on every rank
 c = rng.uniform(-1, 1, (world * nzl, nl))
 d = rng.uniform(-1, 1, (world * nzl, nl))
 cl, dl = c[rank * nzl:(rank + 1) * nzl], d[rank * nzl:(rank + 1) * nzl]
-T = zm.tables(nzl, dz)
-up, dn, sa, sb = zm.moments(T, cl, dl)
+up, dn = (np.stack(m) for m in zm.boundary_messages(cl, dl, dz))     # [9, nl] each
 lower, upper = (rank - 1) % world, (rank + 1) % world
 recv_lo, recv_up = torch.zeros(up.shape, dtype=torch.float64), torch.zeros(dn.shape, dtype=torch.float64)
 # the exchange of the CUDA path (pbx_dist.cu: dist_exchange_nccl): send up / send down, receive from below / above
@@ -28,7 +27,7 @@ ops = [dist.P2POp(dist.isend, torch.from_numpy(np.ascontiguousarray(up)), upper,
        dist.P2POp(dist.irecv, recv_up, upper, tag=1)]
 for r in dist.batch_isend_irecv(ops):
     r.wait()
-out = zm.correct(T, zm.local_open(cl, dl, dz), recv_lo.numpy() + sa, recv_up.numpy() + sb)
+out = zm.slab_zpass(cl, dl, dz, list(recv_lo.numpy()), list(recv_up.numpy()))
 truth = zm.periodic_truth(c, d, dz)[rank * nzl:(rank + 1) * nzl]
 err = np.max(np.abs(out - truth)) / np.max(np.abs(truth))
 # a global dot product the way the CG does it: local partial, then all-reduce

@@ -102,3 +102,101 @@ def periodic_truth(c, d, dz):
 
         res = res + (sten(Ai2 @ v) if kind == "M" else Ai2 @ sten(v))
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# The protocol the CUDA path uses (pbx_dist.cu: k_boundary, pbx_fast_common.cuh: zpass_body_slab):
+# the neighbours' influence enters the slab's z pass through its native inputs -- recursion states
+# and stencil halos -- rebuilt from nine numbers per z-line and direction.
+# ------------------------------------------------------------------------------------------------
+BM, BD = 48, 24
+
+
+def _causal(u, r, Y=0.0, Z=0.0):
+    y = np.zeros_like(u[0]) + Y
+    z = np.zeros_like(u[0]) + Z
+    out = np.empty_like(u)
+    for i in range(u.shape[0]):
+        y = u[i] + r * y
+        z = y + r * z
+        out[i] = z
+    return out, y, z
+
+
+def _anticausal(zv, r, W=0.0, X=0.0):
+    w = np.zeros_like(zv[0]) + W
+    x = np.zeros_like(zv[0]) + X
+    out = np.empty_like(zv)
+    for i in range(zv.shape[0] - 1, -1, -1):
+        w = zv[i] + r * w
+        x = w + r * x
+        out[i] = x
+    return out, w, x
+
+
+def _stencil_halo(v, c, lo, hi):
+    n = v.shape[0]
+    pad = np.concatenate([lo, v, hi], 0)
+    out = c[0] * pad[3:n + 3]
+    for k in (1, 2, 3):
+        out = out + c[k] * (pad[3 - k:n + 3 - k] + pad[3 + k:n + 3 + k])
+    return out
+
+
+def boundary_messages(c, d, dz):
+    """(msg_up, msg_dn): nine arrays each, what k_boundary computes from one slab"""
+    cm, rm, _ = composite_coef("M", dz)
+    cd, rd, _ = composite_coef("D", dz)
+    z3 = np.zeros((3,) + c.shape[1:])
+    zM, yM, zMe = _causal(c[-BM:], rm)
+    sD = _stencil_halo(d[-(BD + 3):], cd, z3, z3)[3:]
+    _, yD, zD = _causal(sD, rd)
+    up = [yM, zMe, zM[-2], zM[-3], yD, zD, d[-1], d[-2], d[-3]]
+    j = np.arange(BM).reshape((-1,) + (1,) * (c.ndim - 1))
+    A0M, A1M = np.sum(rm**j * c[:BM], 0), np.sum(j * rm**j * c[:BM], 0)
+    sDb = _stencil_halo(d[:BD + 3], cd, z3, z3)[:BD]
+    j = np.arange(BD).reshape((-1,) + (1,) * (c.ndim - 1))
+    A0D, A1D = np.sum(rd**j * sDb, 0), np.sum(j * rd**j * sDb, 0)
+    dn = [A0M, A1M, A0D, A1D, d[0], d[1], d[2], c[0], c[1]]
+    return up, dn
+
+
+def slab_zpass(c, d, dz, from_lo, from_up):
+    """the slab's z pass with the neighbours' messages (zpass_body_slab)"""
+    cm, rm, _ = composite_coef("M", dz)
+    cd, rd, _ = composite_coef("D", dz)
+    yMl, zMl, zMl1, zMl2, yDl, zDl, dl1, dl2, dl3 = from_lo
+    A0M, A1M, A0D, A1D, du0, du1, du2, cu0, cu1 = from_up
+
+    def G(a0, a1, r):
+        q = r * r
+        return a0 / (1 - q) ** 2, a0 * (1 + q) / (1 - q) ** 3 + a1 / (1 - q) ** 2
+
+    def K(Y, Z, r):
+        q = r * r
+        return Z * r / (1 - q) + Y * r / (1 - q) ** 2, Z * r / (1 - q) ** 2 + Y * r * (1 + q) / (1 - q) ** 3
+
+    s = _stencil_halo(d, cd, np.stack([dl3, dl2, dl1]), np.stack([du0, du1, du2]))
+    s1, s2, s3 = cd[1] * d[0] + cd[2] * d[1] + cd[3] * d[2], cd[2] * d[0] + cd[3] * d[1], cd[3] * d[0]
+    zDv, yDe, zDe = _causal(s, rd, yDl + s1 + rd * s2 + rd * rd * s3, zDl + s1 + 2 * rd * s2 + 3 * rd * rd * s3)
+    e0, e1, e2 = cd[1] * d[-1] + cd[2] * d[-2] + cd[3] * d[-3], cd[2] * d[-1] + cd[3] * d[-2], cd[3] * d[-1]
+    Wg, Xg = G(A0D + e0 + rd * e1 + rd * rd * e2, A1D + rd * e1 + 2 * rd * rd * e2, rd)
+    Wk, Xk = K(yDe, zDe, rd)
+    outD, _, _ = _anticausal(zDv, rd, Wg + Wk, Xg + Xk)
+
+    zMv, yMe, zMe = _causal(c, rm, yMl, zMl)
+    Wg, Xg = G(A0M, A1M, rm)
+    Wk, Xk = K(yMe, zMe, rm)
+    WT, XT = Wg + Wk, Xg + Xk
+    xM, w, x = _anticausal(zMv, rm, WT, XT)
+    lo = []
+    for zt in (zMl, zMl1, zMl2):
+        w = zt + rm * w
+        x = w + rm * x
+        lo.append(x)
+    zt0 = cu0 + rm * (zMe + yMe)
+    zt1 = cu1 + 2 * rm * cu0 + rm * rm * (zMe + 2 * yMe)
+    w1, x1 = (WT - zt0) / rm, (XT - WT) / rm
+    x2 = (x1 - w1) / rm
+    del zt1
+    return _stencil_halo(xM, cm, np.stack(lo[::-1]), np.stack([XT, x1, x2])) + outD
