@@ -331,19 +331,28 @@ __device__ __forceinline__ void lookback_nat(const CompositeCoef &c, const Xchg 
     }
 }
 
-template <class Bar>
-__device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
-                                                const ZOpen &zo, const Xchg &xc, long long line,
-                                                const double (&c)[LC], double (&ed)[LC + 6],
-                                                double (&out)[LC], Bar bar)
+// the neighbours' messages of one z line; issued early by the boundary chunks so that the loads
+// overlap the wait for the tile instead of sitting in front of the first barrier
+__device__ __forceinline__ void slab_load_messages(const ZOpen &zo, bool first, bool last,
+                                                   long long line, double (&lo9)[DIST_MSG],
+                                                   double (&up9)[DIST_MSG])
 {
-    const bool first = xc.t == 0, last = xc.t == xc.T - 1;
-    double lo9[DIST_MSG], up9[DIST_MSG];
 #pragma unroll
     for (int a = 0; a < DIST_MSG; ++a) {
         lo9[a] = first ? __ldg(zo.from_lo + a * zo.nlines + line) : 0.0;
         up9[a] = last ? __ldg(zo.from_up + a * zo.nlines + line) : 0.0;
     }
+}
+
+template <class Bar>
+__device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
+                                                const ZOpen &zo, const Xchg &xc,
+                                                const double (&lo9)[DIST_MSG],
+                                                const double (&up9)[DIST_MSG],
+                                                const double (&c)[LC], double (&ed)[LC + 6],
+                                                double (&out)[LC], Bar bar)
+{
+    const bool first = xc.t == 0, last = xc.t == xc.T - 1;
     // (i) true halos of the derivative input
     if (first) {
         ed[0] = lo9[8];

@@ -102,13 +102,15 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
         c[k] = live ? __ldg(Cc + base + k * p.sl) : 0.0;
         d[k] = live ? __ldg(Dd + base + k * p.sl) : 0.0;
     }
+    double lo9[DIST_MSG], up9[DIST_MSG];
+    if (zo.open)
+        slab_load_messages(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, lo9, up9);
     put_halo(xc, ZNAT_SLOTS, d);
     __syncthreads();
     double ed[LC + 6], o[LC];
     get_halo(xc, ZNAT_SLOTS, d, ed);
     if (zo.open) {
-        const long long line = live ? (long long)x + (long long)p.nx * g : 0;
-        zpass_body_slab(p.M, p.D, zo, xc, line, c, ed, o, BarAll());
+        zpass_body_slab(p.M, p.D, zo, xc, lo9, up9, c, ed, o, BarAll());
     } else {
         zpass_body(p.M, p.D, xc, c, ed, o, BarAll());
     }

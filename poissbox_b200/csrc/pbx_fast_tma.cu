@@ -166,7 +166,7 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
     }
 }
 
-template <bool ZPASS>
+template <bool ZPASS, bool SLAB>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -192,7 +192,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     const int t = (lt >> 3) % p.T;
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
-    Xchg xc{S.xchg[grp], lt, t, p.T, XW, ZPASS ? zo.open : 0};
+    Xchg xc{S.xchg[grp], lt, t, p.T, XW, SLAB ? 1 : 0};
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
@@ -204,6 +204,9 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         const bool live = (x < p.nx) && (g < p.ng);
         const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
 
+        double lo9[DIST_MSG], up9[DIST_MSG];
+        if (SLAB)
+            slab_load_messages(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, lo9, up9);
         mbar_wait(&S.full, (uint32_t)(it & 1));
         double a[LC], eb[LC + 6];
         {
@@ -220,7 +223,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                 if (lo) il += p.n;
                 if (hi) ir -= p.n;
                 const double vl = tb[il * p.se], vr = tb[ir * p.se];
-                const bool cut = ZPASS && zo.open;    // open line: nothing beyond the slab
+                const bool cut = SLAB;    // open line: nothing beyond the slab
                 eb[k] = (cut && lo) ? 0.0 : vl;
                 eb[LC + 3 + k] = (cut && hi) ? 0.0 : vr;
             }
@@ -243,9 +246,8 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             }
         } else {
             double o[LC];
-            if (zo.open) {
-                const long long line = live ? (long long)x + (long long)p.nx * g : 0;
-                zpass_body_slab(p.M, p.D, zo, xc, line, a, eb, o, bar);
+            if (SLAB) {
+                zpass_body_slab(p.M, p.D, zo, xc, lo9, up9, a, eb, o, bar);
             } else {
                 zpass_body(p.M, p.D, xc, a, eb, o, bar);
             }
@@ -562,18 +564,22 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     const size_t smem = sizeof(YZShared);
     static bool attr_set = false;
     if (!attr_set) {
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false>,
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true>,
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     if (dir == 1)
-        yz_tma_kernel<false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    else if (!zo.open)
+        yz_tma_kernel<true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     else
-        yz_tma_kernel<true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
