@@ -240,13 +240,12 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # warm-up; at least 0.3 s of it so that the clock sampler sees the load the timed region runs under
-    tw = time.perf_counter()
-    nw = 0
-    while nw < max(3, args.warmup) or time.perf_counter() - tw < 0.3:
+    # warm-up; long enough (~0.3 s) for the clock sampler to see the load the timed region runs
+    # under.  The count is the same on every rank: with N>1 each apply contains collectives.
+    nw = max(3, args.warmup, int(0.3 / (2.2e-3 / world)))
+    for i in range(nw):
         h.lapl(f, out)
-        nw += 1
-        if nw % 8 == 0:
+        if i % 8 == 7:
             torch.cuda.synchronize()
     barrier()
     t_lo = time.perf_counter() - 0.25
