@@ -483,6 +483,24 @@ __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const Co
     for (int k = 0; k < LC; ++k) out[k] += v[1][k];
 }
 
+// Deterministic sum over `nthr` compute threads (q = 0 .. nthr-1), result valid in thread q == 0.
+// Full warps: fixed shuffle tree per warp, warp sums through `ws` (>= 32 doubles that nobody else
+// touches between two calls), ONE barrier.  Otherwise the generic fixed-order version below.
+template <class Bar>
+__device__ __forceinline__ double block_sum_warps(double v, double *ws, int q, int nthr, Bar bar)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((q & 31) == 0) ws[q >> 5] = v;
+    bar();
+    double tot = 0.0;
+    if (q == 0) {
+        const int nw = nthr >> 5;
+        for (int i = 0; i < nw; ++i) tot += ws[i];
+    }
+    return tot;
+}
+
 // fixed-shape (deterministic) sum over the compute threads of a CTA through the exchange area;
 // result valid in thread q == 0.  Two barriers before the area may be reused.
 template <class Bar>

@@ -130,7 +130,9 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
     }
     if (pv != nullptr) {
         const int nthr = blockDim.x * blockDim.y * blockDim.z;
-        double tot = block_sum_fixed(dot, sm, xc.q, nthr, BarAll());
+        // same association as the TMA kernel whenever the CTA consists of full warps
+        double tot = (nthr & 31) == 0 ? block_sum_warps(dot, sm + (Y_SLOTS + 5) * NT, xc.q, nthr, BarAll())
+                                      : block_sum_fixed(dot, sm, xc.q, nthr, BarAll());
         if (xc.q == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = tot;
     }
 }
@@ -239,11 +241,13 @@ int fast_xpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.nlines = (long long)g.ny * g.nz;
     if (p.R > p.nlines) p.R = (int)p.nlines;
     const size_t smem = sizeof(double) * (XK_SLOTS * NT + 2 * (size_t)p.R * p.T * CPAD);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBX_CUDA(cudaFuncSetAttribute(xpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       112 * 1024));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     dim3 block(p.T, p.R);
     unsigned grid = (unsigned)((p.nlines + p.R - 1) / p.R);
@@ -276,11 +280,13 @@ int fast_ypass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.D = fc.D[1];
     dim3 grid, block;
     yz_geometry(g, 1, &p, &grid, &block);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBX_CUDA(cudaFuncSetAttribute(ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)YZ_SMEM));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     ypass_kernel<<<grid, block, YZ_SMEM, s>>>(p, A, B, C, D);
     if (launches) ++*launches;
@@ -305,11 +311,13 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.D = fc.D[2];
     dim3 grid, block;
     yz_geometry(g, 2, &p, &grid, &block);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBX_CUDA(cudaFuncSetAttribute(zpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)YZ_SMEM));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     zpass_kernel<<<grid, block, YZ_SMEM, s>>>(p, zo, C, D, out, pvec, dot_partials);
     if (n_partials) *n_partials = (int)(grid.x * grid.y);

