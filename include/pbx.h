@@ -135,6 +135,8 @@ int pbx_lapl_dot_device(pbx_handle h, const double *f, double *d2f, double *dot_
  * duration in milliseconds of each of its three kernels (x, y, z pass), taken with CUDA events
  * recorded between the launches on the handle's stream.  Synchronises the stream. */
 int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps, double ms[3]);
+/* grad / div / interp follow the handle's mode: REFERENCE = thread-per-line Thomas sweeps, FAST =
+ * chunked-recursion line operators in the same stage order (pbx_fast_lineop.cu). */
 /* compact_schemes::grad  src/compact_schemes.f90:42-88;  df has 3 components */
 int pbx_grad_device(pbx_handle h, const double *f, double *df);
 /* compact_schemes::div   src/compact_schemes.f90:207-257;  f has 3 components */
@@ -207,6 +209,10 @@ int pbx_bwd_sweep_host(int n, const double *b, const double *c, double *d);
 int pbx_cg_solve_host(int nx, int ny, int nz, const double dx[3], const double *b, double *x,
                       double rtol, double abstol, int maxit, int mode, int *its, double *rnorm,
                       int *reason, double *hist, int nhist);
+/* schedule used by the grad / div / interp host variants (they carry no mode argument, as the
+ * reference's routines do not): PBX_MODE_REFERENCE (default, bit-identical to the reference order
+ * of operations) or PBX_MODE_FAST (chunked-recursion line operators, agrees to rounding) */
+int pbx_host_set_mode(int mode);
 /* drop the cached handles of the *_host calls (frees their device memory) */
 int pbx_host_cache_clear(void);
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "pbx_fwd_sweep_host": (c_int, [c_int, _dp, _dp, _dp, _dp]),
     "pbx_bwd_sweep_host": (c_int, [c_int, _dp, _dp, _dp]),
     "pbx_cg_solve_host": (c_int, [c_int, c_int, c_int, _d3, _dp, _dp, c_double, c_double, c_int, c_int, _ip, _dp, _ip, _dp, c_int]),
+    "pbx_host_set_mode": (c_int, [c_int]),
     "pbx_host_cache_clear": (c_int, []),
 }
 

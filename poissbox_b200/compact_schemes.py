@@ -25,6 +25,12 @@ def _poisoned(shape):
     return np.full(shape, 73.29, order="F")
 
 
+def set_host_mode(mode):
+    """schedule of grad / div / interp below (they have no mode argument in the reference):
+    MODE_REFERENCE (default, bit-identical to the reference's order of operations) or MODE_FAST"""
+    check(LIB.pbx_host_set_mode(int(mode)))
+
+
 def lapl(f, dx, mode=MODE_FAST):
     """compact_schemes::lapl, src/compact_schemes.f90:17-37"""
     f = _f(f)

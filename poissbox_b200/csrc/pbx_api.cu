@@ -56,8 +56,12 @@ Lines lines_of(const pbx_handle_s *h, int dir)
     }
 }
 
-int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in, double *out)
+int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in, double *out,
+            bool fast = false)
 {
+    if (fast)
+        return fast_line_op(h->stream, Brick{h->nx, h->ny, h->nz}, dir, kind, stagger, h->dx[dir], in,
+                            out, &h->launches);
     Lines L = lines_of(h, dir);
     return ref_line_op(h->stream, L.n, L.nl1, L.nl2, L.es, L.ls1, L.ls2, kind, stagger, h->dx[dir],
                        h->ref[dir][kind], in, out, &h->launches);
@@ -66,42 +70,44 @@ int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in
 }  // namespace
 
 // src/compact_schemes.f90:42-88 (Z -> Y -> X, backward stagger).  S = 5 scratch fields.
-static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2, double *o3)
+static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2, double *o3,
+                       bool fast = false)
 {
     PBX_TRY(ensure_scratch(h, 5));
     double **S = h->scratch;
     const int B = PBX_STAGGER_BACKWARD;
-    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0]));      // dff1 (= dff2, :63)
-    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1]));       // dff3
-    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[0], S[2]));   // dfe1
-    PBX_TRY(line_op(h, 1, OP_DERIV, B, S[0], S[3]));    // dfe2
-    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[1], S[4]));   // dfe3
-    PBX_TRY(line_op(h, 0, OP_DERIV, B, S[2], o1));      // df1
-    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[3], o2));     // df2
-    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[4], o3));     // df3
+    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0], fast));      // dff1 (= dff2, :63)
+    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1], fast));       // dff3
+    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[0], S[2], fast));   // dfe1
+    PBX_TRY(line_op(h, 1, OP_DERIV, B, S[0], S[3], fast));    // dfe2
+    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[1], S[4], fast));   // dfe3
+    PBX_TRY(line_op(h, 0, OP_DERIV, B, S[2], o1, fast));      // df1
+    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[3], o2, fast));     // df2
+    PBX_TRY(line_op(h, 0, OP_INTERP, B, S[4], o3, fast));     // df3
     return PBX_OK;
 }
 
 // src/compact_schemes.f90:207-257 (X -> Y -> Z, forward stagger).  i1..i3 may be scratch 0..2.
 static int div_stages(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
-                      double *out)
+                      double *out, bool fast = false)
 {
     PBX_TRY(ensure_scratch(h, 5));
     double **S = h->scratch;
     const int F = PBX_STAGGER_FORWARD;
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     // order chosen so that an input living in S[0..2] is consumed before its slot is reused
-    PBX_TRY(line_op(h, 0, OP_DERIV, F, i1, S[3]));      // dfe1
-    PBX_TRY(line_op(h, 0, OP_INTERP, F, i2, S[4]));     // dfe2
+    PBX_TRY(line_op(h, 0, OP_DERIV, F, i1, S[3], fast));      // dfe1
+    PBX_TRY(line_op(h, 0, OP_INTERP, F, i2, S[4], fast));     // dfe2
     double *e3 = S[0];                                  // i1 (possibly S[0]) is consumed by now
-    PBX_TRY(line_op(h, 0, OP_INTERP, F, i3, e3));       // dfe3
-    PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1]));   // dff1
-    PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2]));    // dff2
-    PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3]));     // dff3
+    PBX_TRY(line_op(h, 0, OP_INTERP, F, i3, e3, fast));       // dfe3
+    PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));   // dff1
+    PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast));    // dff2
+    PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3], fast));     // dff3
     PBX_TRY(ref_add(h->stream, N, S[1], S[2], S[4], &h->launches));   // :249
-    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0]));   // dfc
-    PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], out));     // df
-    PBX_TRY(ref_add(h->stream, N, out, S[0], out, &h->launches));     // :251
+    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0], fast));   // dfc
+    // the z derivative goes to a scratch field first: FAST line operators cannot run in place
+    PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], S[1], fast));    // df
+    PBX_TRY(ref_add(h->stream, N, S[1], S[0], out, &h->launches));    // :251
     return PBX_OK;
 }
 
@@ -113,26 +119,27 @@ int lapl_reference(pbx_handle_s *h, const double *f, double *out)
     return div_stages(h, S[0], S[1], S[2], out);
 }
 
-int grad_reference(pbx_handle_s *h, const double *f, double *df)
+int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
-    return grad_stages(h, f, df, df + N, df + 2 * N);
+    return grad_stages(h, f, df, df + N, df + 2 * N, fast && h->fast_ok);
 }
 
-int div_reference(pbx_handle_s *h, const double *f, double *out)
+int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
-    return div_stages(h, f, f + N, f + 2 * N, out);
+    return div_stages(h, f, f + N, f + 2 * N, out, fast && h->fast_ok);
 }
 
 // src/compact_schemes.f90:93-142
-int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger)
+int interp_stages_run(pbx_handle_s *h, const double *f, double *fi, int stagger, bool fast)
 {
     PBX_TRY(ensure_scratch(h, 2));
     double **S = h->scratch;
-    PBX_TRY(line_op(h, 2, OP_INTERP, stagger, f, S[0]));
-    PBX_TRY(line_op(h, 1, OP_INTERP, stagger, S[0], S[1]));
-    PBX_TRY(line_op(h, 0, OP_INTERP, stagger, S[1], fi));
+    fast = fast && h->fast_ok;
+    PBX_TRY(line_op(h, 2, OP_INTERP, stagger, f, S[0], fast));
+    PBX_TRY(line_op(h, 1, OP_INTERP, stagger, S[0], S[1], fast));
+    PBX_TRY(line_op(h, 0, OP_INTERP, stagger, S[1], fi, fast));
     return PBX_OK;
 }
 
@@ -382,7 +389,7 @@ int pbx_grad_device(pbx_handle h, const double *f, double *df)
     if (!h || !f || !df) return PBX_ERR_ARG;
     if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
-    return grad_reference(h, f, df);
+    return grad_stages_run(h, f, df, h->mode == PBX_MODE_FAST);
 }
 
 int pbx_div_device(pbx_handle h, const double *f, double *df)
@@ -390,7 +397,7 @@ int pbx_div_device(pbx_handle h, const double *f, double *df)
     if (!h || !f || !df) return PBX_ERR_ARG;
     if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
-    return div_reference(h, f, df);
+    return div_stages_run(h, f, df, h->mode == PBX_MODE_FAST);
 }
 
 int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger)
@@ -398,7 +405,7 @@ int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger)
     if (!h || !f || !fi || (stagger != -1 && stagger != 1)) return PBX_ERR_ARG;
     if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
-    return interp_reference(h, f, fi, stagger);
+    return interp_stages_run(h, f, fi, stagger, h->mode == PBX_MODE_FAST);
 }
 
 // ---- batched 1-D operators ---------------------------------------------------------------------
@@ -521,6 +528,7 @@ struct HostEntry {
 };
 std::mutex g_host_mutex;
 std::vector<HostEntry> g_host;
+int g_host_mode = PBX_MODE_REFERENCE;   // schedule of the grad / div / interp host variants
 
 int host_entry(int nx, int ny, int nz, const double dx[3], HostEntry **out)
 {
@@ -606,22 +614,42 @@ int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], d
     });
 }
 
+static int host_mode_for(HostEntry *e)
+{
+    int m = g_host_mode;
+    if (m == PBX_MODE_FAST && !e->h->fast_ok) m = PBX_MODE_REFERENCE;
+    return pbx_set_mode(e->h, m);
+}
+
+int pbx_host_set_mode(int mode)
+{
+    if (mode != PBX_MODE_FAST && mode != PBX_MODE_REFERENCE) return PBX_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_host_mutex);
+    g_host_mode = mode;
+    return PBX_OK;
+}
+
 int pbx_grad_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df)
 {
-    return host_run(nx, ny, nz, dx, f, 1, df, 3,
-                    [&](HostEntry *e) { return pbx_grad_device(e->h, e->din, e->dout); });
+    return host_run(nx, ny, nz, dx, f, 1, df, 3, [&](HostEntry *e) {
+        PBX_TRY(host_mode_for(e));
+        return pbx_grad_device(e->h, e->din, e->dout);
+    });
 }
 
 int pbx_div_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df)
 {
-    return host_run(nx, ny, nz, dx, f, 3, df, 1,
-                    [&](HostEntry *e) { return pbx_div_device(e->h, e->din, e->dout); });
+    return host_run(nx, ny, nz, dx, f, 3, df, 1, [&](HostEntry *e) {
+        PBX_TRY(host_mode_for(e));
+        return pbx_div_device(e->h, e->din, e->dout);
+    });
 }
 
 int pbx_interp_host(int nx, int ny, int nz, const double *f, double *fi, int stagger)
 {
     const double dx[3] = {1.0, 1.0, 1.0};
     return host_run(nx, ny, nz, dx, f, 1, fi, 1, [&](HostEntry *e) {
+        PBX_TRY(host_mode_for(e));
         return pbx_interp_device(e->h, e->din, e->dout, stagger);
     });
 }

@@ -166,6 +166,9 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
                const double *D, double *out, const double *p, double *dot_partials,
                int *n_partials, const ZOpen &zo, long long *launches);
 int fast_zpass_max_partials(const Brick &g);
+// FAST formulation of a single 1-D compact operator along dir (pbx_fast_lineop.cu)
+int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
+                 const double *in, double *out, long long *launches);
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
 bool fast_tma_available();
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
@@ -220,9 +223,10 @@ int lapl_reference(pbx_handle_s *h, const double *f, double *out);
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
               double *out1, const double *p, double *partials, const ZOpen *zo = nullptr);
-int grad_reference(pbx_handle_s *h, const double *f, double *df);
-int div_reference(pbx_handle_s *h, const double *f, double *out);
-int interp_reference(pbx_handle_s *h, const double *f, double *fi, int stagger);
+// grad / div / interp in the reference's stage order; fast = true uses the FAST line operators
+int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast);
+int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast);
+int interp_stages_run(pbx_handle_s *h, const double *f, double *fi, int stagger, bool fast);
 int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol, int maxit,
              int *its, double *rnorm, int *reason, double *hist, int nhist);
 int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);

@@ -189,6 +189,34 @@ def test_fast_long_x_lines():
         assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), orc.lapl(f, dx))
 
 
+@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 64), (128, 32, 64), (16, 512, 16), (2048, 16, 32)])
+def test_grad_div_interp_fast_vs_oracle(shape):
+    """FAST line operators (chunked first-order recursion) in the reference's stage order"""
+    rng = np.random.default_rng(4321)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    v = np.asfortranarray(rng.uniform(-1, 1, shape + (3,)))
+    dx = tuple(1.0 / n for n in shape)
+    orc.set_threads(8)
+    try:
+        want = (orc.grad(f, dx), orc.div(v, dx), orc.interp(f), orc.interp_div(f))
+    finally:
+        orc.set_threads(1)
+    cs.set_host_mode(pbx.MODE_FAST)
+    try:
+        got = (cs.grad(f, dx), cs.div(v, dx), cs.interp(f), cs.interp_div(f))
+    finally:
+        cs.set_host_mode(pbx.MODE_REFERENCE)
+    for g, w in zip(got, want):
+        assert np.max(np.abs(g - w)) <= 1e-13 * np.max(np.abs(w))
+    # constants are in the null space of every derivative, exactly
+    cs.set_host_mode(pbx.MODE_FAST)
+    try:
+        gc = cs.grad(np.full(shape, 2.8170923), dx)
+    finally:
+        cs.set_host_mode(pbx.MODE_REFERENCE)
+    assert np.max(np.abs(gc)) <= 100 * EPS * max(shape)
+
+
 def test_fields_golden():
     for tag in "ab":
         f, v, dx = G[f"f3{tag}_f"], G[f"f3{tag}_v"], G[f"f3{tag}_dx"]
