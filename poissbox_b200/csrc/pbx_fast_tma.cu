@@ -134,6 +134,7 @@ struct YZT {
     int nbox, RB;             // boxes per field per tile, line points per box
     int ntx, ntx8, ntiles;    // tiles along x (16 wide), 8-wide sub-tiles along x, total tiles
     int zdir;                 // 0: y pass (box = (16, RB, G)), 1: z pass (box = (16, G, RB))
+    int rev;                  // 1: walk the tiles from the last to the first (L2 reuse, see lapl_fast)
 };
 
 struct YZShared {
@@ -155,6 +156,7 @@ struct BarGroup {
 __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const CUtensorMap *map0,
                                               const CUtensorMap *map1, int tile)
 {
+    if (p.rev) tile = p.ntiles - 1 - tile;
     const int x0 = (tile % p.ntx) * XWT, g0 = (tile / p.ntx) * p.G;
     mbar_expect_tx(&S.full, 2 * YZ_TILE_BYTES);
     for (int b = 0; b < p.nbox; ++b) {
@@ -196,7 +198,8 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
+        const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
         const int xt8 = (tile % p.ntx) * NGRP + grp;         // 8-wide sub-tile index along x
         const int gt = tile / p.ntx;
         const int x = xt8 * XW + tx;
@@ -229,9 +232,9 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             }
         }
         mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
-        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
+        if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty, (uint32_t)(it & 1));       // ... and neither does anybody else
-            yz_issue_tile(S, p, &map0, &map1, tile + gridDim.x);
+            yz_issue_tile(S, p, &map0, &map1, tile0 + gridDim.x);
         }
 
         if (!ZPASS) {
@@ -281,6 +284,7 @@ struct XT {
     CompositeCoef M, D;
     int T;                    // chunks per line (power of two, <= 32)
     int ntiles;               // tiles of 256 chunks
+    int rev;                  // 1: walk the tiles from the last to the first
 };
 
 struct XShared {
@@ -343,7 +347,7 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         fence_mbar_init();
         if ((int)blockIdx.x < p.ntiles) {
             mbar_expect_tx(&S.full, TILE_BYTES);
-            tma_load_2d(S.tin, &mapF, &S.full, 0, blockIdx.x * NT);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * NT);
         }
     }
     __syncthreads();
@@ -354,7 +358,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
     const int ql = (tid & ~31) | seg | ((t - 1) & (T - 1));   // row of the previous chunk of the line
     const int qr = (tid & ~31) | seg | ((t + 1) & (T - 1));
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
+        const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
         mbar_wait(&S.full, (uint32_t)(it & 1));
         double ef[LC + 6];
 #pragma unroll
@@ -376,10 +381,11 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             ef[LC + 5] = r1.x;
         }
         mbar_arrive(&S.empty);
-        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
+        if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
+            const int nxt = tile0 + (int)gridDim.x;
             mbar_wait(&S.empty, (uint32_t)(it & 1));
             mbar_expect_tx(&S.full, TILE_BYTES);
-            tma_load_2d(S.tin, &mapF, &S.full, 0, (tile + gridDim.x) * NT);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - nxt : nxt) * NT);
         }
 
         double va[LC], vb[LC];
@@ -522,7 +528,7 @@ bool fast_tma_available() { return encode_fn() != nullptr; }
 
 // returns PBX_ERR_UNSUPPORTED when the shape does not fit the TMA kernels (caller falls back)
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
-                   double *B, long long *launches)
+                   double *B, int rev, long long *launches)
 {
     const int T = g.nx / LC;
     if (g.nx % LC || T > 32 || (T & (T - 1)) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
@@ -533,6 +539,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     p.D = fc.D[0];
     p.T = T;
     p.ntiles = (int)((nchunks + NT - 1) / NT);
+    p.rev = rev;
     CUtensorMap mf, ma, mb;
     if (!make_map_x(&mf, f, nchunks) || !make_map_x(&ma, A, nchunks) || !make_map_x(&mb, B, nchunks))
         return PBX_ERR_UNSUPPORTED;
@@ -555,10 +562,11 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
 
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, const ZOpen &zo, long long *launches)
+                    double *partials, const ZOpen &zo, int rev, long long *launches)
 {
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
+    p.rev = rev;
     p.M = fc.M;
     p.D = fc.D[dir];
     CUtensorMap m0, m1;

@@ -172,10 +172,10 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
 bool fast_tma_available();
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
-                   double *B, long long *launches);
+                   double *B, int rev, long long *launches);
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, const ZOpen &zo, long long *launches);
+                    double *partials, const ZOpen &zo, int rev, long long *launches);
 
 }  // namespace pbx
 
@@ -222,7 +222,8 @@ int ensure_scratch(pbx_handle_s *h, int count);
 int lapl_reference(pbx_handle_s *h, const double *f, double *out);
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
-              double *out1, const double *p, double *partials, const ZOpen *zo = nullptr);
+              double *out1, const double *p, double *partials, const ZOpen *zo = nullptr,
+              int rev = 0);
 // grad / div / interp in the reference's stage order; fast = true uses the FAST line operators
 int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast);
 int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast);
