@@ -91,22 +91,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// L2 prefetch of a tile that will be loaded one step later: shortens the latency of that load
-// (the z pass gathers 512 rows 2 MiB apart per tile and was seen waiting for its tiles)
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(c0), "r"(c1)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -184,19 +168,6 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
     }
 }
 
-__device__ __forceinline__ void yz_prefetch_tile(const YZT &p, const CUtensorMap *map0,
-                                                 const CUtensorMap *map1, int tile)
-{
-    if (p.rev) tile = p.ntiles - 1 - tile;
-    const int x0 = (tile % p.ntx) * XWT, g0 = (tile / p.ntx) * p.G;
-    for (int b = 0; b < p.nbox; ++b) {
-        const int i0 = b * p.RB;
-        const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
-        tma_prefetch_3d(map0, x0, c1, c2);
-        tma_prefetch_3d(map1, x0, c1, c2);
-    }
-}
-
 template <bool ZPASS, bool SLAB>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
@@ -214,7 +185,6 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         mbar_init(&S.empty, NTHR_YZ);
         fence_mbar_init();
         if ((int)blockIdx.x < p.ntiles) yz_issue_tile(S, p, &map0, &map1, blockIdx.x);
-        if ((int)(blockIdx.x + gridDim.x) < p.ntiles) yz_prefetch_tile(p, &map0, &map1, blockIdx.x + gridDim.x);
     }
     __syncthreads();
 
@@ -265,8 +235,6 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty, (uint32_t)(it & 1));       // ... and neither does anybody else
             yz_issue_tile(S, p, &map0, &map1, tile0 + gridDim.x);
-            if (tile0 + 2 * (int)gridDim.x < p.ntiles)
-                yz_prefetch_tile(p, &map0, &map1, tile0 + 2 * gridDim.x);
         }
 
         if (!ZPASS) {
@@ -418,8 +386,6 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             mbar_wait(&S.empty, (uint32_t)(it & 1));
             mbar_expect_tx(&S.full, TILE_BYTES);
             tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - nxt : nxt) * NT);
-            const int nx2 = nxt + (int)gridDim.x;
-            if (nx2 < p.ntiles) tma_prefetch_2d(&mapF, 0, (p.rev ? p.ntiles - 1 - nx2 : nx2) * NT);
         }
 
         double va[LC], vb[LC];
