@@ -22,6 +22,7 @@
 #pragma once
 
 #include "pbx_internal.h"
+#include "pbx_ptx.cuh"
 
 namespace pbx {
 namespace fast {
@@ -170,10 +171,7 @@ __device__ __forceinline__ void get_halo(const Xchg &x, int s0, const double (&v
 // CTA-wide barrier among the NT compute threads only (named barrier 1), so that a kernel may
 // carry extra producer warps that do not take part
 struct BarCompute {
-    __device__ __forceinline__ void operator()() const
-    {
-        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-    }
+    __device__ __forceinline__ void operator()() const { ptx::named_bar_sync_const<1, NT>(); }
 };
 struct BarAll {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
