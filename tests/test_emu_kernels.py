@@ -1,0 +1,145 @@
+"""CPU: the library's own kernel sources on the fiber model of tests/emu (TEST INFRASTRUCTURE, see
+tests/emu/include/pbx_emu.h), checked against the oracle.  These tests pin KERNEL LOGIC -- tile
+geometry, chunk look-back, barriers, TMA box coordinates, slab boundaries -- in a container
+without a GPU; the parity claims themselves are made by the `-m gpu` tests on the real kernels
+(tests/test_parity_gpu.py), which these mirror at sizes the model runs in seconds."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib as orc
+from test_parity_gpu import assert_fast_close, tdma_init
+
+EPS = np.finfo(np.float64).eps
+
+
+def handle(shape, dx, no_tma="0", **kw):
+    os.environ["PBX_NO_TMA"] = no_tma
+    try:
+        return emu_lib.EmuHandle(*shape, dx, **kw)
+    finally:
+        os.environ.pop("PBX_NO_TMA", None)
+
+
+def field(shape, seed=1234, ncomp=None):
+    rng = np.random.default_rng(seed)
+    return np.asfortranarray(rng.uniform(-1, 1, shape if ncomp is None else shape + (ncomp,)))
+
+
+@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 32, 16), (16, 48, 32), (128, 16, 16), (16, 16, 128)])
+@pytest.mark.parametrize("no_tma", ["0", "1"])
+def test_emu_lapl_fast_and_reference(shape, no_tma):
+    dx = tuple(1.0 / n for n in shape)
+    f = field(shape)
+    ref = orc.lapl(f, dx)
+    lib = emu_lib.load()
+    h = handle(shape, dx, no_tma)
+    maps0 = lib.pbx_emu_tensor_maps_total()
+    out = h.lapl(f)
+    if no_tma == "1":
+        assert lib.pbx_emu_tensor_maps_total() == maps0   # generic kernels only
+    elif shape[1] in (16, 32) and shape[2] in (16, 32, 128):
+        assert lib.pbx_emu_tensor_maps_total() - maps0 == 7   # all three TMA kernels ran
+    assert_fast_close(out, ref)
+    h.set_mode(1)
+    assert np.array_equal(h.lapl(f), ref)
+    h.close()
+
+
+def test_emu_tma_and_generic_bit_identical():
+    shape = (64, 32, 64)
+    dx = tuple(1.0 / n for n in shape)
+    f = field(shape, 7)
+    outs = []
+    for no_tma in ("0", "1"):
+        h = handle(shape, dx, no_tma)
+        outs.append(h.lapl_dot(f))
+        h.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+    ref = np.vdot(f, outs[0][0])
+    assert abs(outs[0][1] - ref) <= 1e-13 * abs(ref)
+
+
+@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 16)])
+def test_emu_grad_div_interp(shape):
+    dx = tuple(0.7 / n for n in shape)
+    f, v = field(shape, 4321), field(shape, 4322, 3)
+    want = (orc.grad(f, dx), orc.div(v, dx), orc.interp(f), orc.interp_div(f))
+    h = handle(shape, dx)
+    h.set_mode(1)
+    got = (h.grad(f), h.div(v), h.interp(f), h.interp(f, +1))
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    h.set_mode(0)
+    got = (h.grad(f), h.div(v), h.interp(f), h.interp(f, +1))
+    for g, w in zip(got, want):
+        assert np.max(np.abs(g - w)) <= 1e-13 * np.max(np.abs(w))
+    h.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 33, 128])
+def test_emu_tridsol_bit_exact(n):
+    lib = emu_lib.load()
+    rng = np.random.default_rng(n)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    for per in (False, True):
+        a, b, c, x, d = tdma_init(n, rng, per)
+        bb, dd = b.copy(), d.copy()
+        emu_lib.check(lib, lib.pbx_tdma_host(n, dp(a), dp(bb), dp(c), dp(dd)))
+        bo, _ = orc.fwd_sweep(a, b, c, d)
+        assert np.array_equal(dd, orc.tdma(a, b, c, d)) and np.array_equal(bb, bo)
+        dd = d.copy()
+        emu_lib.check(lib, lib.pbx_tdma_periodic_host(n, dp(a), dp(b), dp(c), dp(dd)))
+        assert np.array_equal(dd, orc.tdma_periodic(a, b, c, d))
+
+
+def test_emu_cg_matches_oracle():
+    n = 16
+    dx = (2 * np.pi / n,) * 3
+    c = (np.arange(n) + 0.5) * dx[0]
+    u = np.exp(np.sin(c)[:, None, None] + np.sin(c)[None, :, None] + np.sin(c)[None, None, :])
+    b = orc.lapl(np.asfortranarray(u), dx)
+    xo, its_o, rn_o, why_o, hist_o = orc.cg_solve(b, dx, rtol=1e-8)
+    h = handle((n, n, n), dx)
+    x, its, rn, why, hist = h.cg_solve(b, rtol=1e-8)
+    h.close()
+    assert why == why_o == 2 and abs(its - its_o) <= 1
+    m = min(len(hist), len(hist_o))
+    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-6)
+    assert np.max(np.abs(x - xo)) <= 1e-6 * np.max(np.abs(xo))
+
+
+@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 16, 256), 4)])
+@pytest.mark.parametrize("no_tma", ["0", "1"])
+def test_emu_slabs_match_single_brick(shape, P, no_tma):
+    nx, ny, nz = shape
+    nzl = nz // P
+    dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+    f = field(shape, 5)
+    whole = handle(shape, dx, no_tma)
+    ref = whole.lapl(f)
+    slabs = [handle((nx, ny, nzl), dx, no_tma, slab=(r, P)) for r in range(P)]
+    for r, h in enumerate(slabs):
+        h.slab_phase1(np.asfortranarray(f[:, :, r * nzl:(r + 1) * nzl]))
+    emu_lib.EmuHandle.slab_exchange_local(slabs)
+    out = np.concatenate([h.slab_phase2() for h in slabs], axis=2)
+    assert np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(ref))
+    for h in slabs + [whole]:
+        h.close()
+
+
+def test_emu_no_device_is_an_error():
+    """the harness honours the product's rule: no device, no result (PBX_ERR_CUDA)"""
+    lib = emu_lib.load()
+    os.environ["PBX_EMU_NO_DEVICE"] = "1"
+    try:
+        h = ctypes.c_void_p()
+        from poissbox_b200 import _lib
+        rc = lib.pbx_create(16, 16, 16, _lib._d3(1.0, 1.0, 1.0), 0, None, ctypes.byref(h))
+        assert rc == _lib.PBX_ERR_CUDA
+    finally:
+        os.environ.pop("PBX_EMU_NO_DEVICE", None)
