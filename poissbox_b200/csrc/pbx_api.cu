@@ -168,15 +168,19 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)
 {
     if (!h->fast_ok) {
-        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; ny, nz <= 512)");
+        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; nx <= 4096)");
         return PBX_ERR_UNSUPPORTED;
     }
     if ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) & 15) {
         set_last_error("FAST schedule needs 16-byte aligned fields");
         return PBX_ERR_ARG;
     }
-    PBX_TRY(ensure_scratch(h, 2));
+    // a y line longer than one CTA holds is cut into overlapping segments whose halos other CTAs
+    // read: that y pass cannot run in place and writes to a second pair of scratch fields
+    const bool yseg = seg_geometry(h->ny / LC).nseg > 1;
+    PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
+    double *C = yseg ? S[2] : S[0], *D = yseg ? S[3] : S[1];
     // Tile order and the 126 MB L2: a pass that starts where its producer has just finished finds
     // the last ~50 MB of each input still resident.  Inside the CG the input p was written front to
     // back by the p-update, so the x pass walks back to front and the y pass front to back; for a
@@ -184,8 +188,8 @@ int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, do
     const int xrev = p ? 1 : 0;
     PBX_TRY(fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr, nullptr, xrev));
     // the y pass runs in place: a tile is read completely before any of it is written
-    PBX_TRY(fast_pass(h, 1, S[0], S[1], S[0], S[1], nullptr, nullptr, nullptr, 1 - xrev));
-    PBX_TRY(fast_pass(h, 2, S[0], S[1], out, nullptr, p, partials));
+    PBX_TRY(fast_pass(h, 1, S[0], S[1], C, D, nullptr, nullptr, nullptr, 1 - xrev));
+    PBX_TRY(fast_pass(h, 2, C, D, out, nullptr, p, partials));
     return PBX_OK;
 }
 
@@ -296,7 +300,7 @@ int pbx_set_mode(pbx_handle h, int mode)
 {
     if (!h || (mode != PBX_MODE_FAST && mode != PBX_MODE_REFERENCE)) return PBX_ERR_ARG;
     if (mode == PBX_MODE_FAST && !h->fast_ok) {
-        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; ny, nz <= 512)");
+        set_last_error("FAST schedule needs nx, ny, nz multiples of 16 (>= 16; nx <= 4096)");
         return PBX_ERR_UNSUPPORTED;
     }
     if (mode == PBX_MODE_REFERENCE && h->nranks > 1) {
@@ -361,8 +365,10 @@ int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps
     if (!h || !f || !d2f || !ms || reps < 1 || f == d2f) return PBX_ERR_ARG;
     if (!h->fast_ok || h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
-    PBX_TRY(ensure_scratch(h, 2));
+    const bool yseg = seg_geometry(h->ny / LC).nseg > 1;
+    PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
+    double *C = yseg ? S[2] : S[0], *D = yseg ? S[3] : S[1];
     cudaEvent_t ev[4];
     for (auto &e : ev) PBX_CUDA(cudaEventCreate(&e));
     ms[0] = ms[1] = ms[2] = 0.0;
@@ -371,9 +377,9 @@ int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps
         cudaEventRecord(ev[0], h->stream);
         rc = fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr);
         cudaEventRecord(ev[1], h->stream);
-        if (rc == PBX_OK) rc = fast_pass(h, 1, S[0], S[1], S[0], S[1], nullptr, nullptr, nullptr, 1);
+        if (rc == PBX_OK) rc = fast_pass(h, 1, S[0], S[1], C, D, nullptr, nullptr, nullptr, 1);
         cudaEventRecord(ev[2], h->stream);
-        if (rc == PBX_OK) rc = fast_pass(h, 2, S[0], S[1], d2f, nullptr, nullptr, nullptr);
+        if (rc == PBX_OK) rc = fast_pass(h, 2, C, D, d2f, nullptr, nullptr, nullptr);
         cudaEventRecord(ev[3], h->stream);
         if (cudaEventSynchronize(ev[3]) != cudaSuccess) rc = PBX_ERR_CUDA;
         for (int k = 0; k < 3 && rc == PBX_OK; ++k) {

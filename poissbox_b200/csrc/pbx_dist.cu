@@ -209,8 +209,8 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
         set_last_error("the z-slab decomposition needs the FAST schedule (sizes multiples of 16)");
         return PBX_ERR_UNSUPPORTED;
     }
-    if (h->nz < 64) {
-        set_last_error("z-slab decomposition needs at least 64 planes per rank");
+    if (h->nz < 64 || h->nz > SEG_T * LC) {
+        set_last_error("z-slab decomposition needs between 64 and 512 planes per rank");
         return PBX_ERR_UNSUPPORTED;
     }
     DistState *d = new DistState();
@@ -344,10 +344,13 @@ int dist_phase1(pbx_handle_s *h, const double *f)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return PBX_ERR_ARG;
-    PBX_TRY(ensure_scratch(h, 2));
+    // a segmented y pass (ny > 512) cannot run in place: x pass -> S[2], S[3]; y pass -> S[0], S[1]
+    const bool yseg = seg_geometry(h->ny / LC).nseg > 1;
+    PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
-    PBX_TRY(fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr));
-    PBX_TRY(fast_pass(h, 1, S[0], S[1], S[0], S[1], nullptr, nullptr));
+    double *A = yseg ? S[2] : S[0], *B = yseg ? S[3] : S[1];
+    PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr));
+    PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr));
     ++d->epoch;
     const int par = (int)(d->epoch & 1);
     // with peer mappings the messages are stored straight into the neighbours' receive arrays

@@ -122,6 +122,22 @@ struct Xchg {
     }
 };
 
+// which chunk of the line thread-chunk t of segment `seg` is, and whether it is stored
+struct SegChunk {
+    int chunk;       // chunk index on the periodic line
+    bool interior;
+};
+__device__ __forceinline__ SegChunk seg_chunk(const SegGeom &sg, int seg, int t)
+{
+    if (sg.nseg == 1) return {t, true};
+    const int first = seg * sg.iseg;                       // first interior chunk of the segment
+    int c = first - sg.hlo + t;
+    const bool interior = t >= sg.hlo && t < sg.hlo + sg.iseg && c < sg.NC;
+    c %= sg.NC;
+    if (c < 0) c += sg.NC;
+    return {c, interior};
+}
+
 // true incoming state from the local end states published in slots (sy, sz); dir = -1 looks at
 // chunks t-1, t-2, ... (causal), dir = +1 at t+1, t+2, ... (anti-causal)
 __device__ __forceinline__ void lookback(const CompositeCoef &c, const Xchg &x, int sy, int sz,

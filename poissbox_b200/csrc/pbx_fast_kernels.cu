@@ -44,8 +44,9 @@ constexpr int CPAD = LC + 2;      // x pass: doubles per chunk in the padded sta
 // ---------------------------------------------------------------------------------------------
 struct YZParams {
     CompositeCoef M, D;
-    int nx, T, ng;          // x extent, chunks per line, number of lines in the "group" direction
+    int nx, T, ng;          // x extent, chunks per CTA, number of lines in the "group" direction
     long long sl, sg;       // strides (in doubles) along the line / between lines of a group
+    SegGeom seg;            // long lines: blockIdx.z numbers the segment (pbx_internal.h)
 };
 
 // y pass:  C = M a + D b ;  Dd = M b
@@ -58,8 +59,9 @@ ypass_kernel(const __grid_constant__ YZParams p, const double *__restrict__ A,
     const int x = blockIdx.x * XW + tx;
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
-    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW};
-    const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+    const SegChunk sc = seg_chunk(p.seg, blockIdx.z, t);
+    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, p.seg.nseg > 1 ? 1 : 0};
+    const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
     double a[LC], b[LC];
 #pragma unroll
@@ -72,7 +74,7 @@ ypass_kernel(const __grid_constant__ YZParams p, const double *__restrict__ A,
     double eb[LC + 6], c[LC], d[LC];
     get_halo(xc, Y_SLOTS, b, eb);
     ypass_body(p.M, p.D, xc, a, eb, c, d, BarAll());
-    if (live) {
+    if (live && sc.interior) {
 #pragma unroll
         for (int k = 0; k < LC; ++k) {
             C[base + k * p.sl] = c[k];
@@ -93,8 +95,9 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
     const int x = blockIdx.x * XW + tx;
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
-    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, zo.open};
-    const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+    const SegChunk sc = seg_chunk(p.seg, blockIdx.z, t);
+    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, (zo.open || p.seg.nseg > 1) ? 1 : 0};
+    const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
     double c[LC], d[LC];
 #pragma unroll
@@ -116,7 +119,7 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
     }
 
     double dot = 0.0;
-    if (live) {
+    if (live && sc.interior) {
         if (pv != nullptr) {
 #pragma unroll
             for (int k = 0; k < LC; ++k) {
@@ -133,7 +136,7 @@ zpass_kernel(const __grid_constant__ YZParams p, const __grid_constant__ ZOpen z
         // same association as the TMA kernel whenever the CTA consists of full warps
         double tot = (nthr & 31) == 0 ? block_sum_warps(dot, sm + (Y_SLOTS + 5) * NT, xc.q, nthr, BarAll())
                                       : block_sum_fixed(dot, sm, xc.q, nthr, BarAll());
-        if (xc.q == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+        if (xc.q == 0) partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
     }
 }
 
@@ -223,10 +226,10 @@ constexpr size_t YZ_SMEM = sizeof(double) * (Y_SLOTS + 6) * NT;
 
 bool fast_supported(int nx, int ny, int nz)
 {
-    // chunks of 16 points; one CTA must hold a whole line of chunks (T <= 32 at XW = 8 for y/z,
-    // T <= 256 for x)
+    // chunks of 16 points; an x line must fit one CTA (T <= 256 chunks); y and z lines of more
+    // than 32 chunks are cut into overlapping segments (SegGeom)
     auto ok = [](int n, int tmax) { return n >= LC && n % LC == 0 && n / LC <= tmax; };
-    return ok(nx, NT) && ok(ny, NT / XW) && ok(nz, NT / XW);
+    return ok(nx, NT) && ok(ny, 1 << 20) && ok(nz, 1 << 20);
 }
 
 int fast_xpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
@@ -261,7 +264,8 @@ static void yz_geometry(const Brick &g, int dir, YZParams *p, dim3 *grid, dim3 *
 {
     const int n = dir == 1 ? g.ny : g.nz;
     p->nx = g.nx;
-    p->T = n / LC;
+    p->seg = seg_geometry(n / LC);
+    p->T = p->seg.T;
     p->ng = dir == 1 ? g.nz : g.ny;
     p->sl = dir == 1 ? (long long)g.nx : (long long)g.nx * g.ny;
     p->sg = dir == 1 ? (long long)g.nx * g.ny : (long long)g.nx;
@@ -269,7 +273,7 @@ static void yz_geometry(const Brick &g, int dir, YZParams *p, dim3 *grid, dim3 *
     if (G < 1) G = 1;
     if (G > p->ng) G = p->ng;
     *block = dim3(XW, p->T, G);
-    *grid = dim3((g.nx + XW - 1) / XW, (p->ng + G - 1) / G);
+    *grid = dim3((g.nx + XW - 1) / XW, (p->ng + G - 1) / G, p->seg.nseg);
 }
 
 int fast_ypass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *A,
@@ -299,7 +303,7 @@ int fast_zpass_max_partials(const Brick &g)
     YZParams p;
     dim3 grid, block;
     yz_geometry(g, 2, &p, &grid, &block);
-    return (int)(grid.x * grid.y);
+    return (int)(grid.x * grid.y * grid.z);
 }
 
 int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *C,
@@ -319,8 +323,12 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
                                       (int)YZ_SMEM));
         attr_set[dev_ & 63] = true;
     }
+    if (zo.open && p.seg.nseg > 1) {
+        set_last_error("a z slab of more than 512 planes per rank is not supported");
+        return PBX_ERR_UNSUPPORTED;
+    }
     zpass_kernel<<<grid, block, YZ_SMEM, s>>>(p, zo, C, D, out, pvec, dot_partials);
-    if (n_partials) *n_partials = (int)(grid.x * grid.y);
+    if (n_partials) *n_partials = (int)(grid.x * grid.y * grid.z);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -83,6 +83,7 @@ struct LYZ {
     LineOp op;
     int nx, T, ng;
     long long sl, sg;
+    SegGeom seg;          // lines of more than 512 points: blockIdx.z numbers the segment
 };
 
 __global__ void __launch_bounds__(NT, 3)
@@ -93,8 +94,9 @@ lineop_yz_kernel(const __grid_constant__ LYZ p, const double *__restrict__ in, d
     const int x = blockIdx.x * XW + tx;
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
-    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW};
-    const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+    const SegChunk sc = seg_chunk(p.seg, blockIdx.z, t);
+    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, p.seg.nseg > 1 ? 1 : 0};
+    const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
     double f[LC];
 #pragma unroll
     for (int k = 0; k < LC; ++k) f[k] = live ? __ldg(in + base + k * p.sl) : 0.0;
@@ -104,7 +106,7 @@ lineop_yz_kernel(const __grid_constant__ LYZ p, const double *__restrict__ in, d
     get_halo(xc, 2, f, e);
     stencil4(p.op, e, v);
     solve1_chunk(p.op.cc, xc, 0, v, BarAll());
-    if (live) {
+    if (live && sc.interior) {
 #pragma unroll
         for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
     }
@@ -211,14 +213,15 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
         p.op = op;
         const int n = dir == 1 ? g.ny : g.nz;
         p.nx = g.nx;
-        p.T = n / LC;
+        p.seg = seg_geometry(n / LC);
+        p.T = p.seg.T;
         p.ng = dir == 1 ? g.nz : g.ny;
         p.sl = dir == 1 ? (long long)g.nx : (long long)g.nx * g.ny;
         p.sg = dir == 1 ? (long long)g.nx * g.ny : (long long)g.nx;
         int G = NT / (XW * p.T);
         if (G < 1) G = 1;
         if (G > p.ng) G = p.ng;
-        dim3 block(XW, p.T, G), grid((g.nx + XW - 1) / XW, (p.ng + G - 1) / G);
+        dim3 block(XW, p.T, G), grid((g.nx + XW - 1) / XW, (p.ng + G - 1) / G, p.seg.nseg);
         lineop_yz_kernel<<<grid, block, 0, s>>>(p, in, out);
     }
     if (launches) ++*launches;

@@ -57,7 +57,18 @@ struct YZT {
     int ntx, ntx8, ntiles;    // tiles along x (16 wide), 8-wide sub-tiles along x, total tiles
     int zdir;                 // 0: y pass (box = (16, RB, G)), 1: z pass (box = (16, G, RB))
     int rev;                  // 1: walk the tiles from the last to the first (L2 reuse, see lapl_fast)
+    SegGeom seg;              // long lines: tile = (segment, x tile, line group), segment fastest
+    int ngt;                  // line groups (tiles in the remaining direction)
 };
+
+struct TileId {
+    int s, xt, gt;            // segment, 16-wide x tile, line group
+};
+__device__ __forceinline__ TileId tile_id(const YZT &p, int tile)
+{
+    const int s = tile % p.seg.nseg, rest = tile / p.seg.nseg;
+    return {s, rest % p.ntx, rest / p.ntx};
+}
 
 struct YZShared {
     double tile[2][YZ_TILE_DOUBLES];
@@ -76,18 +87,23 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
                                               const CUtensorMap *map1, int tile)
 {
     if (p.rev) tile = p.ntiles - 1 - tile;
-    const int x0 = (tile % p.ntx) * XWT, g0 = (tile / p.ntx) * p.G;
+    const TileId id = tile_id(p, tile);
+    const int x0 = id.xt * XWT, g0 = id.gt * p.G;
+    // first line point of the tile: 0, or hlo chunks in front of the segment's interior; the boxes
+    // of a segment tile wrap around the periodic line one by one (n is a multiple of RB)
+    const int start = p.seg.nseg > 1 ? (id.s * p.seg.iseg - p.seg.hlo) * LC : 0;
     mbar_expect_tx(&S.full, 2 * YZ_TILE_BYTES);
     for (int b = 0; b < p.nbox; ++b) {
-        const int i0 = b * p.RB;
+        int i0 = (start + b * p.RB) % p.n;
+        if (i0 < 0) i0 += p.n;
         const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
-        const int off = i0 * p.se;
+        const int off = b * p.RB * p.se;
         tma_load_3d(&S.tile[0][off], map0, &S.full, x0, c1, c2);
         tma_load_3d(&S.tile[1][off], map1, &S.full, x0, c1, c2);
     }
 }
 
-template <bool ZPASS, bool SLAB>
+template <bool ZPASS, bool SLAB, bool SEG>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -113,18 +129,26 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     const int t = (lt >> 3) % p.T;
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
-    Xchg xc{S.xchg[grp], lt, t, p.T, XW, SLAB ? 1 : 0};
+    constexpr bool segd = SEG;                               // tiles are segments of longer lines
+    const int npts = SEG ? SEG_T * LC : p.n;                 // line points in a tile
+    Xchg xc{S.xchg[grp], lt, t, p.T, XW, (SLAB || segd) ? 1 : 0};
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
     for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
         const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
-        const int xt8 = (tile % p.ntx) * NGRP + grp;         // 8-wide sub-tile index along x
-        const int gt = tile / p.ntx;
+        TileId id{0, tile % p.ntx, tile / p.ntx};
+        SegChunk sc{t, true};
+        if (SEG) {
+            id = tile_id(p, tile);
+            sc = seg_chunk(p.seg, id.s, t);
+        }
+        const int xt8 = id.xt * NGRP + grp;                  // 8-wide sub-tile index along x
+        const int gt = id.gt;
         const int x = xt8 * XW + tx;
         const int g = gt * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng);
-        const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+        const bool live = (x < p.nx) && (g < p.ng) && sc.interior;
+        const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
         double lo9[DIST_MSG], up9[DIST_MSG];
         if (SLAB)
@@ -141,11 +165,11 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 int il = i0 - 3 + k, ir = i0 + LC + k;
-                const bool lo = il < 0, hi = ir >= p.n;
-                if (lo) il += p.n;
-                if (hi) ir -= p.n;
+                const bool lo = il < 0, hi = ir >= npts;
+                if (lo) il += npts;
+                if (hi) ir -= npts;
                 const double vl = tb[il * p.se], vr = tb[ir * p.se];
-                const bool cut = SLAB;    // open line: nothing beyond the slab
+                const bool cut = SLAB || segd;    // open line: nothing beyond the slab / segment
                 eb[k] = (cut && lo) ? 0.0 : vl;
                 eb[LC + 3 + k] = (cut && hi) ? 0.0 : vr;
             }
@@ -190,7 +214,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                 // one partial per 8-wide sub-tile, numbered as the generic kernel numbers its CTAs;
                 // the warp sums go through the last exchange slot, which the z pass never uses
                 double tot = block_sum_warps(dot, S.xchg[grp] + (Y_SLOTS - 1) * NT, lt, NT, bar);
-                if (lt == 0 && xt8 < p.ntx8) partials[gt * p.ntx8 + xt8] = tot;
+                if (lt == 0 && xt8 < p.ntx8) partials[(id.s * p.ngt + gt) * p.ntx8 + xt8] = tot;
             }
         }
     }
@@ -415,29 +439,41 @@ int sm_count()
 bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
 {
     const int n = dir == 1 ? g.ny : g.nz;
-    if (n % LC || n < LC || n > 512 || (g.nx & 1)) return false;
+    if (n % LC || n < LC || (g.nx & 1)) return false;
     p->nx = g.nx;
     p->n = n;
-    p->T = n / LC;
+    p->seg = seg_geometry(n / LC);
+    p->T = p->seg.T;
     if (NT % (XW * p->T)) return false;          // T must divide 32
     p->G = NT / (XW * p->T);
     p->ng = dir == 1 ? g.nz : g.ny;
     p->sl = dir == 1 ? (long long)g.nx : (long long)g.nx * g.ny;
     p->sg = dir == 1 ? (long long)g.nx * g.ny : (long long)g.nx;
     p->zdir = dir == 2;
-    p->nbox = n > 256 ? 2 : 1;
-    p->RB = n / p->nbox;
+    const int npts = p->T * LC;                  // line points in a tile
+    if (p->seg.nseg > 1) {
+        // segment tiles start at multiples of 4 chunks: 64-point boxes never straddle the line end
+        if (n % 64) return false;
+        p->RB = 64;
+        p->nbox = npts / p->RB;
+    } else {
+        p->nbox = n > 256 ? 2 : 1;
+        p->RB = n / p->nbox;
+    }
     if (p->nbox > 1 && p->G != 1) return false;
     if (p->zdir) {          // smem layout [i][g][16]
         p->se = p->G * XWT;
         p->sgm = XWT;
     } else {                // smem layout [g][i][16]
         p->se = XWT;
-        p->sgm = n * XWT;
+        p->sgm = npts * XWT;
     }
     p->ntx = (g.nx + XWT - 1) / XWT;
     p->ntx8 = (g.nx + XW - 1) / XW;
-    p->ntiles = p->ntx * ((p->ng + p->G - 1) / p->G);
+    p->ngt = (p->ng + p->G - 1) / p->G;
+    const long long nt = (long long)p->ntx * p->ngt * p->seg.nseg;
+    if (nt > 0x7fffffffLL) return false;
+    p->ntiles = (int)nt;
     return true;
 }
 
@@ -485,6 +521,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
 {
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
+    if (zo.open && p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;   // the generic launcher reports it
     p.rev = rev;
     p.M = fc.M;
     p.D = fc.D[dir];
@@ -495,22 +532,27 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, true>, (cudaFuncAttribute)a, (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    if (dir == 1)
-        yz_tma_kernel<false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
-    else if (!zo.open)
-        yz_tma_kernel<true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+    const bool segd = p.seg.nseg > 1;
+    if (dir == 1 && !segd)
+        yz_tma_kernel<false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    else if (dir == 1)
+        yz_tma_kernel<false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    else if (zo.open)
+        yz_tma_kernel<true, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+    else if (!segd)
+        yz_tma_kernel<true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     else
-        yz_tma_kernel<true, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -149,6 +149,39 @@ struct ZOpen {
     double rinv = 0;                                // 1 / r of the interpolation recursion
 };
 
+// Long lines.  A CTA holds at most SEG_T chunks (512 points) of a y or z line.  A longer line is cut
+// into segments of `iseg` chunks that are computed independently as OPEN lines of SEG_T chunks:
+// `hlo` halo chunks below and the rest above the segment are loaded (wrapping around the periodic
+// line) and computed but not stored.  A chunk's recursion state depends on the nlook <= 3
+// preceding chunks only and its solved stencil halo on one chunk more, so SEG_HALO = 4 halo
+// chunks reproduce the whole-line result to the truncation the look-back already makes (< 1e-19).
+constexpr int SEG_T = 32;
+constexpr int SEG_HALO = 4;
+struct SegGeom {
+    int nseg;   // 1: the whole periodic line in one CTA (T = NC, hlo = 0, iseg = NC)
+    int iseg;   // interior chunks per segment (a multiple of 4 when nseg > 1)
+    int hlo;    // halo chunks in front of the interior
+    int T;      // chunks per CTA
+    int NC;     // chunks per line
+};
+inline SegGeom seg_geometry(int nchunks)
+{
+    SegGeom s;
+    s.NC = nchunks;
+    if (nchunks <= SEG_T) {
+        s.nseg = 1;
+        s.iseg = s.T = nchunks;
+        s.hlo = 0;
+        return s;
+    }
+    const int imax = SEG_T - 2 * SEG_HALO;
+    s.nseg = (nchunks + imax - 1) / imax;
+    s.iseg = ((nchunks + s.nseg - 1) / s.nseg + 3) & ~3;
+    s.hlo = SEG_HALO;
+    s.T = SEG_T;
+    return s;
+}
+
 // FAST schedule passes
 struct FastCoefs {
     CompositeCoef D[3];   // derivative composite, per direction (depends on dx)

@@ -21,6 +21,7 @@ enum cudaMemcpyKind {
     cudaMemcpyDeviceToHost = 2,
     cudaMemcpyDeviceToDevice = 3
 };
+typedef int cudaFuncAttribute;
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaDevAttrMultiProcessorCount = 16 };
 enum { cudaEventDisableTiming = 2 };

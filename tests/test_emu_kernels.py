@@ -49,8 +49,9 @@ def test_emu_lapl_fast_and_reference(shape, no_tma):
     h.close()
 
 
-def test_emu_tma_and_generic_bit_identical():
-    shape = (64, 32, 64)
+@pytest.mark.parametrize("shape", [(64, 32, 64), (16, 1024, 16), (16, 16, 656)])
+def test_emu_tma_and_generic_bit_identical(shape):
+    """includes y / z lines of more than 512 points, which run as overlapping segments"""
     dx = tuple(1.0 / n for n in shape)
     f = field(shape, 7)
     outs = []
@@ -62,9 +63,14 @@ def test_emu_tma_and_generic_bit_identical():
     assert outs[0][1] == outs[1][1]
     ref = np.vdot(f, outs[0][0])
     assert abs(outs[0][1] - ref) <= 1e-13 * abs(ref)
+    orc.set_threads(8)
+    try:
+        assert_fast_close(outs[0][0], orc.lapl(f, dx))
+    finally:
+        orc.set_threads(1)
 
 
-@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 16)])
+@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 16), (16, 1024, 16), (16, 16, 656)])
 def test_emu_grad_div_interp(shape):
     dx = tuple(0.7 / n for n in shape)
     f, v = field(shape, 4321), field(shape, 4322, 3)
@@ -113,7 +119,7 @@ def test_emu_cg_matches_oracle():
     assert np.max(np.abs(x - xo)) <= 1e-6 * np.max(np.abs(xo))
 
 
-@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 16, 256), 4)])
+@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 16, 256), 4), ((16, 528, 128), 2)])
 @pytest.mark.parametrize("no_tma", ["0", "1"])
 def test_emu_slabs_match_single_brick(shape, P, no_tma):
     nx, ny, nz = shape

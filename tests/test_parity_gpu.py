@@ -167,8 +167,8 @@ def test_fields_reference_bit_exact(shape, dx):
 
 @pytest.mark.parametrize("shape", [(2048, 8, 8), (8, 2048, 8), (8, 8, 2048), (1000, 12, 10)])
 def test_long_lines_reference_bit_exact(shape):
-    """BASELINE configs[4]: line lengths up to 2048 in each direction (REFERENCE schedule; the FAST
-    one takes lines up to 4096 in x and 512 in y, z per brick and falls back otherwise)"""
+    """BASELINE configs[4]: line lengths up to 2048 in each direction, REFERENCE schedule (these
+    bricks have extents that are not multiples of 16, which the FAST schedule does not take)"""
     rng = np.random.default_rng(99)
     f = np.asfortranarray(rng.uniform(-1, 1, shape))
     v = np.asfortranarray(rng.uniform(-1, 1, shape + (3,)))
@@ -189,7 +189,8 @@ def test_fast_long_x_lines():
         assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), orc.lapl(f, dx))
 
 
-@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 64), (128, 32, 64), (16, 512, 16), (2048, 16, 32)])
+@pytest.mark.parametrize("shape", [(32, 16, 48), (64, 64, 64), (128, 32, 64), (16, 512, 16), (2048, 16, 32),
+                                   (16, 1024, 16), (32, 16, 2048), (16, 656, 528)])
 def test_grad_div_interp_fast_vs_oracle(shape):
     """FAST line operators (chunked first-order recursion) in the reference's stage order"""
     rng = np.random.default_rng(4321)
@@ -230,9 +231,12 @@ def test_fields_golden():
 
 
 @pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 48), (64, 64, 64), (128, 32, 64),
-                                   (48, 80, 112), (1024, 16, 16), (16, 512, 16), (16, 16, 512)])
+                                   (48, 80, 112), (1024, 16, 16), (16, 512, 16), (16, 16, 512),
+                                   (16, 1024, 16), (16, 16, 1024), (32, 2048, 16), (16, 32, 2048),
+                                   (16, 528, 656), (64, 1024, 32), (1024, 1024, 16)])
 def test_lapl_fast_vs_oracle(shape):
-    """S2 inputs: U[-1,1], default_rng(1234), dx = 1/n"""
+    """S2 inputs: U[-1,1], default_rng(1234), dx = 1/n.  y and z lines of more than
+    512 points (BASELINE configs[4]: up to 2048) run as overlapping segments."""
     rng = np.random.default_rng(1234)
     f = np.asfortranarray(rng.uniform(-1, 1, shape))
     dx = tuple(1.0 / n for n in shape)
@@ -319,7 +323,8 @@ def test_lapl_full_size_properties():
     h.close()
 
 
-@pytest.mark.parametrize("shape", [(512, 512, 32), (64, 64, 64), (256, 128, 32), (32, 512, 512), (48, 80, 112)])
+@pytest.mark.parametrize("shape", [(512, 512, 32), (64, 64, 64), (256, 128, 32), (32, 512, 512), (48, 80, 112),
+                                   (64, 1024, 32), (32, 16, 2048), (16, 640, 1088)])
 def test_tma_and_generic_kernels_bit_identical(shape):
     """the TMA-pipelined persistent kernels and the generic kernels share their arithmetic
     (pbx_fast_common.cuh): same bits, including the fused p.Ap partial sums"""

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("shape,P", [((64, 32, 128), 2), ((32, 32, 512), 8), ((48, 16, 256), 2),
-                                     ((512, 16, 192), 3), ((16, 512, 128), 2)])
+                                     ((512, 16, 192), 3), ((16, 512, 128), 2), ((32, 1024, 128), 2)])
 @pytest.mark.parametrize("no_tma", ["0", "1"])
 def test_slabs_match_single_brick(shape, P, no_tma):
     import torch
@@ -41,7 +41,8 @@ def test_slabs_match_single_brick(shape, P, no_tma):
         h.close()
 
 
-def test_slab_needs_64_planes():
-    with pytest.raises(pbx.PbxError) as e:
-        pbx.Handle(32, 32, 48, (1, 1, 1), slab=(0, 2))
-    assert e.value.code == 4
+def test_slab_needs_64_to_512_planes():
+    for nzl in (48, 528):
+        with pytest.raises(pbx.PbxError) as e:
+            pbx.Handle(32, 32, nzl, (1, 1, 1), slab=(0, 2))
+        assert e.value.code == 4
