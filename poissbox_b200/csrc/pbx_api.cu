@@ -147,20 +147,10 @@ int interp_stages_run(pbx_handle_s *h, const double *f, double *fi, int stagger,
 // FAST schedule driver
 // ------------------------------------------------------------------------------------------------
 // one pass (0 = x, 1 = y, 2 = z): the TMA-pipelined kernel when the shape fits, else the generic one
-// z0, nzb: restrict an x or y pass to the planes [z0, z0 + nzb) of the brick (nzb = 0: all)
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
-              double *out1, const double *p, double *partials, const ZOpen *zop, int rev, int z0,
-              int nzb)
+              double *out1, const double *p, double *partials, const ZOpen *zop, int rev)
 {
     Brick g{h->nx, h->ny, h->nz};
-    if (nzb > 0 && dir != 2) {
-        const size_t off = (size_t)z0 * h->nx * h->ny;
-        g.nz = nzb;
-        in0 += off;
-        if (in1) in1 += off;
-        out0 += off;
-        if (out1) out1 += off;
-    }
     const ZOpen zo = zop ? *zop : ZOpen();
     // measured on B200 at 512^3 (profiles/README.md): TMA-pipelined x / y / z passes run at
     // 90 / 85 / 76 % of the measured HBM peak against 45 / 74 / 66 % for the generic kernels.
@@ -173,27 +163,6 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
     if (dir == 0) return fast_xpass(h->stream, g, h->fc, in0, out0, out1, &h->launches);
     if (dir == 1) return fast_ypass(h->stream, g, h->fc, in0, in1, out0, out1, &h->launches);
     return fast_zpass(h->stream, g, h->fc, in0, in1, out0, p, partials, nullptr, zo, &h->launches);
-}
-
-int fast_xy(pbx_handle_s *h, const double *f, double *A, double *B, double *C, double *D, int xrev)
-{
-    const int zb = h->xy_block;
-    if (zb <= 0 || zb >= h->nz) {
-        PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr, nullptr, xrev));
-        return fast_pass(h, 1, A, B, C, D, nullptr, nullptr, nullptr, 1 - xrev);
-    }
-    // Blocked: the x pass of a block of zb planes writes 16 B/DoF that the y pass of the same block
-    // reads back at once -- out of the 126 MB L2 when the block fits (zb * nx * ny * 16 B) -- and, when
-    // the y pass runs in place, overwrites before the dirty lines are evicted: 24 + 32 B/DoF of HBM
-    // traffic become 8 + 16.
-    const int nb = (h->nz + zb - 1) / zb;
-    for (int i = 0; i < nb; ++i) {
-        const int b = xrev ? nb - 1 - i : i;
-        const int z0 = b * zb, nzb = h->nz - z0 < zb ? h->nz - z0 : zb;
-        PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr, nullptr, xrev, z0, nzb));
-        PBX_TRY(fast_pass(h, 1, A, B, C, D, nullptr, nullptr, nullptr, 1 - xrev, z0, nzb));
-    }
-    return PBX_OK;
 }
 
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)
@@ -217,8 +186,9 @@ int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, do
     // back by the p-update, so the x pass walks back to front and the y pass front to back; for a
     // stand-alone apply the x pass walks forward and the y pass backward.
     const int xrev = p ? 1 : 0;
-    // the y pass runs in place (unless segmented): a tile is read completely before any of it is written
-    PBX_TRY(fast_xy(h, f, S[0], S[1], C, D, xrev));
+    PBX_TRY(fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr, nullptr, xrev));
+    // the y pass runs in place: a tile is read completely before any of it is written
+    PBX_TRY(fast_pass(h, 1, S[0], S[1], C, D, nullptr, nullptr, nullptr, 1 - xrev));
     PBX_TRY(fast_pass(h, 2, C, D, out, nullptr, p, partials));
     return PBX_OK;
 }
@@ -299,8 +269,6 @@ int pbx_create(int nx, int ny, int nz, const double dx[3], int device, void *ncc
         h->use_tma = !(e && e[0] == '1');
         e = getenv("PBX_TMA_YZ");
         h->use_tma_yz = !(e && e[0] == '0');
-        e = getenv("PBX_XY_BLOCK");
-        if (e) h->xy_block = atoi(e);
     }
     h->mode = h->fast_ok ? PBX_MODE_FAST : PBX_MODE_REFERENCE;
     if (nccl_comm) {
@@ -401,30 +369,23 @@ int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps
     PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
     double *C = yseg ? S[2] : S[0], *D = yseg ? S[3] : S[1];
-    // the launches of one apply in order: (x, y) per block of planes (one block unless the x and y
-    // passes are blocked, fast_xy), then z; an event between any two
-    const int zb = (h->xy_block > 0 && h->xy_block < h->nz) ? h->xy_block : h->nz;
-    const int nb = (h->nz + zb - 1) / zb;
-    std::vector<cudaEvent_t> ev(2 * nb + 2);
+    cudaEvent_t ev[4];
     for (auto &e : ev) PBX_CUDA(cudaEventCreate(&e));
     ms[0] = ms[1] = ms[2] = 0.0;
     int rc = PBX_OK;
     for (int r = 0; r < reps && rc == PBX_OK; ++r) {
         cudaEventRecord(ev[0], h->stream);
-        for (int b = 0; b < nb && rc == PBX_OK; ++b) {
-            const int z0 = b * zb, nzb = h->nz - z0 < zb ? h->nz - z0 : zb;
-            rc = fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr, nullptr, 0, z0, nzb);
-            cudaEventRecord(ev[2 * b + 1], h->stream);
-            if (rc == PBX_OK) rc = fast_pass(h, 1, S[0], S[1], C, D, nullptr, nullptr, nullptr, 1, z0, nzb);
-            cudaEventRecord(ev[2 * b + 2], h->stream);
-        }
+        rc = fast_pass(h, 0, f, nullptr, S[0], S[1], nullptr, nullptr);
+        cudaEventRecord(ev[1], h->stream);
+        if (rc == PBX_OK) rc = fast_pass(h, 1, S[0], S[1], C, D, nullptr, nullptr, nullptr, 1);
+        cudaEventRecord(ev[2], h->stream);
         if (rc == PBX_OK) rc = fast_pass(h, 2, C, D, d2f, nullptr, nullptr, nullptr);
-        cudaEventRecord(ev[2 * nb + 1], h->stream);
-        if (cudaEventSynchronize(ev[2 * nb + 1]) != cudaSuccess) rc = PBX_ERR_CUDA;
-        for (int k = 0; k < 2 * nb + 1 && rc == PBX_OK; ++k) {
+        cudaEventRecord(ev[3], h->stream);
+        if (cudaEventSynchronize(ev[3]) != cudaSuccess) rc = PBX_ERR_CUDA;
+        for (int k = 0; k < 3 && rc == PBX_OK; ++k) {
             float t = 0;
             cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
-            ms[k == 2 * nb ? 2 : (k & 1)] += t;
+            ms[k] += t;
         }
     }
     for (auto &e : ev) cudaEventDestroy(e);

@@ -349,7 +349,8 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
     double *A = yseg ? S[2] : S[0], *B = yseg ? S[3] : S[1];
-    PBX_TRY(fast_xy(h, f, A, B, S[0], S[1], 0));
+    PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr));
+    PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr));
     ++d->epoch;
     const int par = (int)(d->epoch & 1);
     // with peer mappings the messages are stored straight into the neighbours' receive arrays

@@ -229,9 +229,6 @@ struct pbx_handle_s {
     bool fast_ok = false;
     bool use_tma = true;     // PBX_NO_TMA=1 in the environment selects the generic kernels
     bool use_tma_yz = true;  // PBX_TMA_YZ=0: generic y/z passes, TMA x pass
-    int xy_block = 0;        // > 0: x and y passes alternate over blocks of this many z planes, so that
-                             // the x pass's two outputs are still in L2 when the y pass reads them
-                             // and are overwritten there before they reach HBM (PBX_XY_BLOCK)
 
     // REFERENCE-schedule tables: [dir][kind]
     pbx::RefLineTables ref[3][2];
@@ -259,9 +256,7 @@ int lapl_reference(pbx_handle_s *h, const double *f, double *out);
 int lapl_fast(pbx_handle_s *h, const double *f, double *out, const double *p, double *dot_dev);
 int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, double *out0,
               double *out1, const double *p, double *partials, const ZOpen *zo = nullptr,
-              int rev = 0, int z0 = 0, int nzb = 0);
-// x pass then y pass of the FAST Laplacian: f -> (C, D); A, B are the x pass's outputs (scratch)
-int fast_xy(pbx_handle_s *h, const double *f, double *A, double *B, double *C, double *D, int xrev);
+              int rev = 0);
 // grad / div / interp in the reference's stage order; fast = true uses the FAST line operators
 int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast);
 int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast);
