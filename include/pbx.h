@@ -116,6 +116,17 @@ int pbx_create_slab(int nx, int ny, int nz_local, const double dx[3], int device
 int pbx_slab_phase1(pbx_handle h, const double *f);
 int pbx_slab_phase2(pbx_handle h, double *d2f);
 int pbx_slab_exchange_local(pbx_handle *hs, int n);
+/* grad / div / interp on slabs, phase-driven in the same way: phase 1 = the stages before the z
+ * operators plus the boundary sweeps of their inputs (three numbers per z line, operator and
+ * neighbour); exchange; phase 2 = the z operators and the remaining stages.  `in` must be the same
+ * array in both phases.  With an ncclComm_t, pbx_grad_device / pbx_div_device / pbx_interp_device
+ * run the three steps themselves. */
+#define PBX_OP_GRAD 1
+#define PBX_OP_DIV 2
+#define PBX_OP_INTERP 3      /* stagger -1 */
+#define PBX_OP_INTERP_DIV 4  /* stagger +1 */
+int pbx_slab_op_phase1(pbx_handle h, int op, const double *in);
+int pbx_slab_op_phase2(pbx_handle h, int op, const double *in, double *out);
 /* the same exchange over the handle's NCCL communicator, and the CG's scalar all-reduce (exposed
  * for profiling the communication steps on their own) */
 int pbx_slab_exchange(pbx_handle h);

@@ -18,6 +18,7 @@ _d3 = c_double * 3
 PBX_OK, PBX_ERR_ARG, PBX_ERR_CUDA, PBX_ERR_NCCL, PBX_ERR_UNSUPPORTED, PBX_ERR_NOMEM = 0, 1, 2, 3, 4, 5
 PBX_ERR_SIZE = 7
 MODE_FAST, MODE_REFERENCE = 0, 1
+OP_GRAD, OP_DIV, OP_INTERP, OP_INTERP_DIV = 1, 2, 3, 4
 
 # every symbol include/pbx.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -40,6 +41,8 @@ SIGNATURES = {
     "pbx_slab_phase1": (c_int, [c_void_p, c_void_p]),
     "pbx_slab_phase2": (c_int, [c_void_p, c_void_p]),
     "pbx_slab_exchange_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
+    "pbx_slab_op_phase1": (c_int, [c_void_p, c_int, c_void_p]),
+    "pbx_slab_op_phase2": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "pbx_slab_exchange": (c_int, [c_void_p]),
     "pbx_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int]),
     "pbx_dist_tables_host": (c_int, [c_int, c_double, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),

@@ -56,9 +56,17 @@ Lines lines_of(const pbx_handle_s *h, int dir)
     }
 }
 
+// zslot: on a slab of a z-decomposed box a z operator takes the neighbours' messages that
+// line_boundary() put in slot `zslot` of the exchange buffers before the exchange
 int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in, double *out,
-            bool fast = false)
+            bool fast = false, int zslot = 0)
 {
+    if (h->nranks > 1 && dir == 2) {
+        const double *lo = nullptr, *up = nullptr;
+        PBX_TRY(dist_line_msgs(h, zslot, &lo, &up));
+        return fast_line_op(h->stream, Brick{h->nx, h->ny, h->nz}, dir, kind, stagger, h->dx[dir], in,
+                            out, &h->launches, lo, up);
+    }
     if (fast)
         return fast_line_op(h->stream, Brick{h->nx, h->ny, h->nz}, dir, kind, stagger, h->dx[dir], in,
                             out, &h->launches);
@@ -76,8 +84,8 @@ static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2,
     PBX_TRY(ensure_scratch(h, 5));
     double **S = h->scratch;
     const int B = PBX_STAGGER_BACKWARD;
-    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0], fast));      // dff1 (= dff2, :63)
-    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1], fast));       // dff3
+    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0], fast, 0));   // dff1 (= dff2, :63)
+    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1], fast, 1));    // dff3
     PBX_TRY(line_op(h, 1, OP_INTERP, B, S[0], S[2], fast));   // dfe1
     PBX_TRY(line_op(h, 1, OP_DERIV, B, S[0], S[3], fast));    // dfe2
     PBX_TRY(line_op(h, 1, OP_INTERP, B, S[1], S[4], fast));   // dfe3
@@ -88,8 +96,10 @@ static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2,
 }
 
 // src/compact_schemes.f90:207-257 (X -> Y -> Z, forward stagger).  i1..i3 may be scratch 0..2.
-static int div_stages(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
-                      double *out, bool fast = false)
+// div_stages_xy: the X and Y stages, leaving the inputs of the two Z operators in S[4]
+// (interpolation) and S[3] (derivative); div_stages_z: the Z stage.
+static int div_stages_xy(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
+                         bool fast = false)
 {
     PBX_TRY(ensure_scratch(h, 5));
     double **S = h->scratch;
@@ -103,12 +113,25 @@ static int div_stages(pbx_handle_s *h, const double *i1, const double *i2, const
     PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));   // dff1
     PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast));    // dff2
     PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3], fast));     // dff3
-    PBX_TRY(ref_add(h->stream, N, S[1], S[2], S[4], &h->launches));   // :249
-    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0], fast));   // dfc
+    return ref_add(h->stream, N, S[1], S[2], S[4], &h->launches);   // :249
+}
+
+static int div_stages_z(pbx_handle_s *h, double *out, bool fast = false)
+{
+    double **S = h->scratch;
+    const int F = PBX_STAGGER_FORWARD;
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0], fast, 0));   // dfc
     // the z derivative goes to a scratch field first: FAST line operators cannot run in place
-    PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], S[1], fast));    // df
-    PBX_TRY(ref_add(h->stream, N, S[1], S[0], out, &h->launches));    // :251
-    return PBX_OK;
+    PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], S[1], fast, 1));    // df
+    return ref_add(h->stream, N, S[1], S[0], out, &h->launches);    // :251
+}
+
+static int div_stages(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
+                      double *out, bool fast = false)
+{
+    PBX_TRY(div_stages_xy(h, i1, i2, i3, fast));
+    return div_stages_z(h, out, fast);
 }
 
 int lapl_reference(pbx_handle_s *h, const double *f, double *out)
@@ -129,6 +152,57 @@ int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     return div_stages(h, f, f + N, f + 2 * N, out, fast && h->fast_ok);
+}
+
+// ---- grad / div / interp on one slab of a z-decomposed box: two phases around ONE exchange ---------
+// phase 1 runs whatever precedes the Z stage and the boundary sweeps of the Z operators' inputs
+// (three planes of nx*ny numbers per operator and neighbour); phase 2 the Z operators, which take
+// the neighbours' messages as true stencil halos and recursion states, and whatever follows.
+static int line_boundary(pbx_handle_s *h, int zslot, OpKind kind, int stagger, const double *in)
+{
+    double *dn = nullptr, *up = nullptr;
+    PBX_TRY(dist_line_dst(h, zslot, &dn, &up));
+    return fast_line_boundary(h->stream, Brick{h->nx, h->ny, h->nz}, kind, stagger, h->dx[2], in, dn, up,
+                              &h->launches);
+}
+
+int slab_op_phase1(pbx_handle_s *h, int op, const double *in)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    PBX_TRY(ensure_scratch(h, 5));
+    PBX_TRY(dist_begin_epoch(h));
+    switch (op) {
+    case PBX_OP_GRAD:
+        PBX_TRY(line_boundary(h, 0, OP_INTERP, PBX_STAGGER_BACKWARD, in));
+        return line_boundary(h, 1, OP_DERIV, PBX_STAGGER_BACKWARD, in);
+    case PBX_OP_DIV:
+        PBX_TRY(div_stages_xy(h, in, in + N, in + 2 * N, true));
+        PBX_TRY(line_boundary(h, 0, OP_INTERP, PBX_STAGGER_FORWARD, h->scratch[4]));
+        return line_boundary(h, 1, OP_DERIV, PBX_STAGGER_FORWARD, h->scratch[3]);
+    case PBX_OP_INTERP:
+        return line_boundary(h, 0, OP_INTERP, PBX_STAGGER_BACKWARD, in);
+    case PBX_OP_INTERP_DIV:
+        return line_boundary(h, 0, OP_INTERP, PBX_STAGGER_FORWARD, in);
+    default:
+        return PBX_ERR_ARG;
+    }
+}
+
+int slab_op_phase2(pbx_handle_s *h, int op, const double *in, double *out)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    switch (op) {
+    case PBX_OP_GRAD:
+        return grad_stages(h, in, out, out + N, out + 2 * N, true);
+    case PBX_OP_DIV:
+        return div_stages_z(h, out, true);
+    case PBX_OP_INTERP:
+        return interp_stages_run(h, in, out, PBX_STAGGER_BACKWARD, true);
+    case PBX_OP_INTERP_DIV:
+        return interp_stages_run(h, in, out, PBX_STAGGER_FORWARD, true);
+    default:
+        return PBX_ERR_ARG;
+    }
 }
 
 // src/compact_schemes.f90:93-142
@@ -395,28 +469,59 @@ int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps
     return PBX_OK;
 }
 
+// on a z-decomposed box: phase 1, the exchange over the communicator, phase 2
+static int slab_op(pbx_handle h, int op, const double *in, double *out)
+{
+    if (!h->comm) {
+        set_last_error("slab handle without a communicator: drive it with pbx_slab_op_phase1/2");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) {
+        set_last_error("FAST schedule needs 16-byte aligned fields");
+        return PBX_ERR_ARG;
+    }
+    PBX_TRY(slab_op_phase1(h, op, in));
+    PBX_TRY(dist_exchange(h));
+    return slab_op_phase2(h, op, in, out);
+}
+
 int pbx_grad_device(pbx_handle h, const double *f, double *df)
 {
     if (!h || !f || !df) return PBX_ERR_ARG;
-    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
+    if (h->nranks > 1) return slab_op(h, PBX_OP_GRAD, f, df);
     return grad_stages_run(h, f, df, h->mode == PBX_MODE_FAST);
 }
 
 int pbx_div_device(pbx_handle h, const double *f, double *df)
 {
     if (!h || !f || !df) return PBX_ERR_ARG;
-    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
+    if (h->nranks > 1) return slab_op(h, PBX_OP_DIV, f, df);
     return div_stages_run(h, f, df, h->mode == PBX_MODE_FAST);
 }
 
 int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger)
 {
     if (!h || !f || !fi || (stagger != -1 && stagger != 1)) return PBX_ERR_ARG;
-    if (h->nranks > 1) return PBX_ERR_UNSUPPORTED;
     PBX_CUDA(cudaSetDevice(h->device));
+    if (h->nranks > 1)
+        return slab_op(h, stagger == PBX_STAGGER_BACKWARD ? PBX_OP_INTERP : PBX_OP_INTERP_DIV, f, fi);
     return interp_stages_run(h, f, fi, stagger, h->mode == PBX_MODE_FAST);
+}
+
+int pbx_slab_op_phase1(pbx_handle h, int op, const double *in)
+{
+    if (!h || !in || !h->dist) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return slab_op_phase1(h, op, in);
+}
+
+int pbx_slab_op_phase2(pbx_handle h, int op, const double *in, double *out)
+{
+    if (!h || !in || !out || !h->dist) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return slab_op_phase2(h, op, in, out);
 }
 
 // ---- batched 1-D operators ---------------------------------------------------------------------

@@ -364,6 +364,37 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     return PBX_OK;
 }
 
+// ---- message slots for the line operators of grad / div / interp (pbx_api.cu) --------------------
+int dist_begin_epoch(pbx_handle_s *h)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d) return PBX_ERR_ARG;
+    ++d->epoch;
+    return PBX_OK;
+}
+
+int dist_line_dst(pbx_handle_s *h, int slot, double **msg_dn, double **msg_up)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || slot < 0 || 3 * slot + 3 > DIST_MSG) return PBX_ERR_ARG;
+    const int par = (int)(d->epoch & 1);
+    const size_t off = (size_t)(3 * slot) * d->nlines;
+    *msg_dn = (d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn) + off;
+    *msg_up = (d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up) + off;
+    return PBX_OK;
+}
+
+int dist_line_msgs(pbx_handle_s *h, int slot, const double **from_lo, const double **from_up)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || slot < 0 || 3 * slot + 3 > DIST_MSG) return PBX_ERR_ARG;
+    const int par = (int)(d->epoch & 1);
+    const size_t off = (size_t)(3 * slot) * d->nlines;
+    *from_lo = d->recv_lo[par] + off;
+    *from_up = d->recv_up[par] + off;
+    return PBX_OK;
+}
+
 // z sweep on the slab, the neighbours' messages of this parity in place
 int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 {
@@ -396,6 +427,12 @@ static int dist_exchange_nccl(pbx_handle_s *h)
     PBX_NCCL(g_nccl.Recv(d->recv_up[par], cnt, ncclFloat64, d->upper, c, h->stream));
     PBX_NCCL(g_nccl.GroupEnd());
     return PBX_OK;
+}
+
+int dist_exchange(pbx_handle_s *h)
+{
+    if (!h->dist || !h->comm) return PBX_ERR_ARG;
+    return dist_exchange_nccl(h);
 }
 
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)

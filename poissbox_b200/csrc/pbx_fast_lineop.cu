@@ -79,6 +79,90 @@ __device__ __forceinline__ void solve1_chunk(const CompositeCoef &c, const Xchg 
     for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[LC - 1 - k], W, v[k]);
 }
 
+// ---- one slab of a z-decomposed box (pbx_dist.cu) ------------------------------------------------
+// The slab is an open line.  Per z line each neighbour sends three numbers (LINE_MSG):
+//   from the lower rank:  0  Y0 = sum_j r^j rhs(-1-j) over its top planes, evaluated with nothing
+//                            above its slab,   1  f(-1),   2  f(-2)      (its top two input planes)
+//   from the upper rank:  0  P0 = sum_j r^j y0(n+j) / (1 - r^2)-weighted moment of its bottom planes
+//                            (zero incoming state, nothing below its slab),   1  f(n),   2  f(n+1).
+// Chunk 0 / chunk T-1 of a line complete them with what their own planes contribute to the
+// neighbour's truncated right-hand sides and publish the TRUE recursion state just outside the slab
+// as the end state of a virtual chunk -1 / T, which the look-back then propagates exactly.
+constexpr int LINE_MSG = 3;
+struct SlabMsg {
+    int open = 0;
+    const double *from_lo = nullptr, *from_up = nullptr;   // [LINE_MSG][nlines]
+    long long nlines = 0;
+};
+
+__device__ __forceinline__ double lookback1_nat(const CompositeCoef &c, const Xchg &x, int slot,
+                                                int vslot, int dir)
+{
+    double S = 0.0;
+    const int qv = x.q + ((dir < 0 ? 0 : x.T - 1) - x.t) * x.tstride;   // owner of the virtual state
+#pragma unroll
+    for (int m = 1; m <= MAXLOOK; ++m) {
+        if (m <= c.nlook) {
+            const int tt = x.t + dir * m;
+            double e = 0.0;
+            if (tt >= 0 && tt < x.T)
+                e = x.sm[slot * NT + x.q + (tt - x.t) * x.tstride];
+            else if (tt == -1 || tt == x.T)
+                e = x.sm[vslot * NT + qv];
+            S = m == 1 ? e : fma(c.look[m - 1], e, S);
+        }
+    }
+    return S;
+}
+
+// solve1_chunk on a slab: slots s0, s0+1 (chunk states) and vs, vs+1 (virtual boundary states).
+// f0, f1: the line's first two input values (chunk 0), fm1, fm2: its last two (chunk T-1).
+template <class Bar>
+__device__ __forceinline__ void solve1_chunk_slab(const LineOp &op, const Xchg &x, int s0, int vs,
+                                                  const double (&lo)[LINE_MSG],
+                                                  const double (&up)[LINE_MSG], double f0, double f1,
+                                                  double fm1, double fm2, double (&v)[LC], Bar bar)
+{
+    const CompositeCoef &c = op.cc;
+    const bool first = x.t == 0, last = x.t == x.T - 1;
+    const double sg = op.deriv ? -1.0 : 1.0;
+    double y = 0.0;
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+        y = fma(c.r, y, v[k]);
+        v[k] = y;
+    }
+    x.put(s0, y);
+    if (first) {
+        // what my first planes add to the lower rank's last right-hand sides
+        const double dY = op.shift ? fma(c.r, op.b * f0, fma(op.b, f1, op.a * f0)) : op.b * f0;
+        x.put(vs, lo[0] + dY);
+    }
+    bar();
+    const double S = lookback1_nat(c, x, s0, vs, -1);
+    double w = 0.0, yout = 0.0;
+#pragma unroll
+    for (int k = LC - 1; k >= 0; --k) {
+        const double yk = fma(c.pw[k], S, v[k]);   // corrected causal value
+        if (k == LC - 1) yout = yk;
+        w = fma(c.r, w, yk);
+        v[k] = w;
+    }
+    x.put(s0 + 1, w);
+    if (last) {
+        // true anti-causal state at the first plane above: the neighbour's moment, plus what my last
+        // planes add to its first two right-hand sides, plus the echo of my outgoing causal state
+        const double d0 = op.shift ? sg * op.b * fm1 : sg * fma(op.b, fm2, op.a * fm1);
+        const double d1 = op.shift ? 0.0 : sg * op.b * fm1;
+        const double i1 = 1.0 / (1.0 - c.r * c.r);
+        x.put(vs + 1, fma(i1, fma(c.r, d1 + yout, d0), up[0]));
+    }
+    bar();
+    const double W = lookback1_nat(c, x, s0 + 1, vs + 1, +1);
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[LC - 1 - k], W, v[k]);
+}
+
 struct LYZ {
     LineOp op;
     int nx, T, ng;
@@ -86,16 +170,18 @@ struct LYZ {
     SegGeom seg;          // lines of more than 512 points: blockIdx.z numbers the segment
 };
 
+template <bool SLAB>
 __global__ void __launch_bounds__(NT, 3)
-lineop_yz_kernel(const __grid_constant__ LYZ p, const double *__restrict__ in, double *__restrict__ out)
+lineop_yz_kernel(const __grid_constant__ LYZ p, const __grid_constant__ SlabMsg zo,
+                 const double *__restrict__ in, double *__restrict__ out)
 {
-    __shared__ double sm[8 * NT];
+    __shared__ double sm[10 * NT];
     const int tx = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
     const int x = blockIdx.x * XW + tx;
     const int g = blockIdx.y * blockDim.z + tz;
     const bool live = (x < p.nx) && (g < p.ng);
     const SegChunk sc = seg_chunk(p.seg, blockIdx.z, t);
-    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, p.seg.nseg > 1 ? 1 : 0};
+    Xchg xc{sm, (tz * p.T + t) * XW + tx, t, p.T, XW, (SLAB || p.seg.nseg > 1) ? 1 : 0};
     const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
     double f[LC];
 #pragma unroll
@@ -104,8 +190,29 @@ lineop_yz_kernel(const __grid_constant__ LYZ p, const double *__restrict__ in, d
     __syncthreads();
     double e[LC + 6], v[LC];
     get_halo(xc, 2, f, e);
-    stencil4(p.op, e, v);
-    solve1_chunk(p.op.cc, xc, 0, v, BarAll());
+    if (SLAB) {
+        const bool first = t == 0, last = t == p.T - 1;
+        const long long line = live ? (long long)x + (long long)p.nx * g : 0;
+        double lo[LINE_MSG], up[LINE_MSG];
+#pragma unroll
+        for (int a = 0; a < LINE_MSG; ++a) {
+            lo[a] = first ? __ldg(zo.from_lo + a * zo.nlines + line) : 0.0;
+            up[a] = last ? __ldg(zo.from_up + a * zo.nlines + line) : 0.0;
+        }
+        if (first) {
+            e[2] = lo[1];
+            e[1] = lo[2];
+        }
+        if (last) {
+            e[LC + 3] = up[1];
+            e[LC + 4] = up[2];
+        }
+        stencil4(p.op, e, v);
+        solve1_chunk_slab(p.op, xc, 0, 8, lo, up, f[0], f[1], f[LC - 1], f[LC - 2], v, BarAll());
+    } else {
+        stencil4(p.op, e, v);
+        solve1_chunk(p.op.cc, xc, 0, v, BarAll());
+    }
     if (live && sc.interior) {
 #pragma unroll
         for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
@@ -171,16 +278,47 @@ lineop_x_kernel(const __grid_constant__ LX p, const double *__restrict__ in, dou
     }
 }
 
-}  // namespace
-
-// one 1-D compact operator along dir on a brick the FAST schedule supports (fast_supported())
-int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
-                 const double *in, double *out, long long *launches)
+// right-hand side at plane k of a z line whose values outside [lo, hi) count as zero
+__device__ __forceinline__ double rhs_at(const LineOp &op, const double *__restrict__ in,
+                                         long long nlines, long long l, int k, int lo, int hi)
 {
-    if (in == out || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
-        set_last_error("FAST line operators need distinct, 16-byte aligned input and output");
-        return PBX_ERR_ARG;
+    auto at = [&](int i) { return (i < lo || i >= hi) ? 0.0 : __ldg(in + (long long)i * nlines + l); };
+    const int sh = op.shift;
+    const double f0 = at(k + sh), f1 = at(k - 1 + sh), f2 = at(k + 1 + sh), f3 = at(k - 2 + sh);
+    const double t1 = op.deriv ? f0 - f1 : f0 + f1;
+    const double t2 = op.deriv ? f2 - f3 : f2 + f3;
+    return fma(op.b, t2, op.a * t1);
+}
+
+// Boundary sweep of a z line operator's input on one slab (see SlabMsg): blockIdx.y = 0 sweeps
+// the bottom `bm` planes (message to the lower rank), 1 the top `bm` planes (to the upper rank).
+// One thread per z line, coalesced in x; neighbouring planes are re-read through L1.
+__global__ void __launch_bounds__(128)
+lineop_boundary_kernel(long long nlines, int nzl, int bm, const __grid_constant__ LineOp op,
+                       const double *__restrict__ in, double *__restrict__ msg_dn,
+                       double *__restrict__ msg_up)
+{
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines) return;
+    const double r = op.cc.r;
+    if (blockIdx.y == 0) {
+        // sum_j r^j y0_j with y0 the causal recursion from zero state = sum_i r^i rhs_i / (1 - r^2)
+        double P = 0.0;
+        for (int i = bm - 1; i >= 0; --i) P = fma(r, P, rhs_at(op, in, nlines, l, i, 0, nzl));
+        msg_dn[0 * nlines + l] = P / (1.0 - r * r);
+        msg_dn[1 * nlines + l] = __ldg(in + l);
+        msg_dn[2 * nlines + l] = __ldg(in + nlines + l);
+    } else {
+        double y = 0.0;
+        for (int i = nzl - bm; i < nzl; ++i) y = fma(r, y, rhs_at(op, in, nlines, l, i, 0, nzl));
+        msg_up[0 * nlines + l] = y;
+        msg_up[1 * nlines + l] = __ldg(in + (long long)(nzl - 1) * nlines + l);
+        msg_up[2 * nlines + l] = __ldg(in + (long long)(nzl - 2) * nlines + l);
     }
+}
+
+LineOp make_line_op(OpKind kind, int stagger, double dx)
+{
     LineOp op;
     make_composite_coef(kind, dx, &op.cc);
     double a, b;
@@ -190,6 +328,38 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
     op.b = b * sc;
     op.deriv = kind == OP_DERIV;
     op.shift = stagger == PBX_STAGGER_BACKWARD ? 0 : 1;
+    return op;
+}
+
+}  // namespace
+
+// boundary sweep of a z line operator on a slab: three planes of nx*ny numbers for either neighbour
+int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger, double dx,
+                       const double *in, double *msg_dn, double *msg_up, long long *launches)
+{
+    const LineOp op = make_line_op(kind, stagger, dx);
+    const long long nlines = (long long)g.nx * g.ny;
+    // planes that matter: r^bm * bm below 1e-19 (r = -1/3: 48, r = -0.148: 24)
+    const int bm = kind == OP_DERIV ? 24 : 48;
+    if (g.nz < bm + 2) return PBX_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((nlines + 127) / 128), 2);
+    lineop_boundary_kernel<<<grid, 128, 0, s>>>(nlines, g.nz, bm, op, in, msg_dn, msg_up);
+    if (launches) ++*launches;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+// one 1-D compact operator along dir on a brick the FAST schedule supports (fast_supported())
+int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
+                 const double *in, double *out, long long *launches, const double *from_lo,
+                 const double *from_up)
+{
+    if (in == out || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+        set_last_error("FAST line operators need distinct, 16-byte aligned input and output");
+        return PBX_ERR_ARG;
+    }
+    const LineOp op = make_line_op(kind, stagger, dx);
+    if (from_lo && (dir != 2 || !from_up)) return PBX_ERR_ARG;
     if (dir == 0) {
         LX p;
         p.op = op;
@@ -222,7 +392,17 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
         if (G < 1) G = 1;
         if (G > p.ng) G = p.ng;
         dim3 block(XW, p.T, G), grid((g.nx + XW - 1) / XW, (p.ng + G - 1) / G, p.seg.nseg);
-        lineop_yz_kernel<<<grid, block, 0, s>>>(p, in, out);
+        if (from_lo) {
+            if (p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;   // slabs hold at most 512 planes
+            SlabMsg zo;
+            zo.open = 1;
+            zo.from_lo = from_lo;
+            zo.from_up = from_up;
+            zo.nlines = (long long)g.nx * g.ny;
+            lineop_yz_kernel<true><<<grid, block, 0, s>>>(p, zo, in, out);
+        } else {
+            lineop_yz_kernel<false><<<grid, block, 0, s>>>(p, SlabMsg(), in, out);
+        }
     }
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());

@@ -200,8 +200,13 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
                int *n_partials, const ZOpen &zo, long long *launches);
 int fast_zpass_max_partials(const Brick &g);
 // FAST formulation of a single 1-D compact operator along dir (pbx_fast_lineop.cu)
+// from_lo / from_up (dir == 2 only): the brick is one slab of a z-decomposed box and these are the
+// neighbours' messages produced by fast_line_boundary ([3][nx*ny] each)
 int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
-                 const double *in, double *out, long long *launches);
+                 const double *in, double *out, long long *launches, const double *from_lo = nullptr,
+                 const double *from_up = nullptr);
+int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger, double dx,
+                       const double *in, double *msg_dn, double *msg_up, long long *launches);
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
 bool fast_tma_available();
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
@@ -272,6 +277,12 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 int dist_attach(pbx_handle_s *h);
 void dist_free(pbx_handle_s *h);
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials);
+// grad / div / interp on slabs (pbx_api.cu): message slots of the exchange buffers.  A slot holds
+// the three planes a z line operator needs from each neighbour; DIST_MSG / 3 slots per exchange.
+int dist_begin_epoch(pbx_handle_s *h);                                         // next exchange round
+int dist_line_dst(pbx_handle_s *h, int slot, double **msg_dn, double **msg_up);   // where phase 1 writes
+int dist_line_msgs(pbx_handle_s *h, int slot, const double **from_lo, const double **from_up);
+int dist_exchange(pbx_handle_s *h);                                            // over the communicator
 // sum `count` doubles in place over the handle's communicator (no-op for a single rank)
 int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count);
 }  // namespace pbx

@@ -55,6 +55,17 @@ class Handle:
         check(LIB.pbx_slab_phase2(self._h, self._field(out)))
         return out
 
+    def slab_op_phase1(self, op, f):
+        """grad / div / interp on a slab (op = _lib.OP_*): stages before the z operators + boundary sweeps"""
+        check(LIB.pbx_slab_op_phase1(self._h, int(op), self._field(f, 3 if op == _lib.OP_DIV else 1)))
+
+    def slab_op_phase2(self, op, f, out=None):
+        if out is None:
+            out = self.empty(3 if op == _lib.OP_GRAD else 1)
+        check(LIB.pbx_slab_op_phase2(self._h, int(op), self._field(f, 3 if op == _lib.OP_DIV else 1),
+                                     self._field(out, 3 if op == _lib.OP_GRAD else 1)))
+        return out
+
     @staticmethod
     def slab_exchange_local(handles):
         arr = (ctypes.c_void_p * len(handles))(*[h._h for h in handles])

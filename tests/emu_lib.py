@@ -134,6 +134,15 @@ class EmuHandle:
         check(self.lib, self.lib.pbx_slab_phase2(self._h, ptr(out)))
         return out
 
+    def slab_op_phase1(self, op, f):
+        self._f = aligned(f)
+        check(self.lib, self.lib.pbx_slab_op_phase1(self._h, op, ptr(self._f)))
+
+    def slab_op_phase2(self, op):
+        out = new_field(self.shape + (3,) if op == _lib.OP_GRAD else self.shape)
+        check(self.lib, self.lib.pbx_slab_op_phase2(self._h, op, ptr(self._f), ptr(out)))
+        return out
+
     @staticmethod
     def slab_exchange_local(handles):
         lib = handles[0].lib

@@ -138,6 +138,33 @@ def test_emu_slabs_match_single_brick(shape, P, no_tma):
         h.close()
 
 
+@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 32, 192), 3)])
+def test_emu_slab_grad_div_interp(shape, P):
+    """grad / div / interp on P slabs (phase 1, exchange, phase 2) against the whole brick"""
+    from poissbox_b200 import _lib
+
+    nx, ny, nz = shape
+    nzl = nz // P
+    dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+    f, v = field(shape, 11), field(shape, 12, 3)
+    orc.set_threads(8)
+    try:
+        want = {_lib.OP_GRAD: orc.grad(f, dx), _lib.OP_DIV: orc.div(v, dx),
+                _lib.OP_INTERP: orc.interp(f), _lib.OP_INTERP_DIV: orc.interp_div(f)}
+    finally:
+        orc.set_threads(1)
+    slabs = [handle((nx, ny, nzl), dx, slab=(r, P)) for r in range(P)]
+    for op, w in want.items():
+        src = v if op == _lib.OP_DIV else f
+        for r, h in enumerate(slabs):
+            h.slab_op_phase1(op, np.asfortranarray(src[:, :, r * nzl:(r + 1) * nzl]))
+        emu_lib.EmuHandle.slab_exchange_local(slabs)
+        out = np.concatenate([h.slab_op_phase2(op) for h in slabs], axis=2)
+        assert np.max(np.abs(out - w)) <= 1e-13 * np.max(np.abs(w)), op
+    for h in slabs:
+        h.close()
+
+
 def test_emu_no_device_is_an_error():
     """the harness honours the product's rule: no device, no result (PBX_ERR_CUDA)"""
     lib = emu_lib.load()

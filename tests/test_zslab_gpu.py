@@ -41,6 +41,39 @@ def test_slabs_match_single_brick(shape, P, no_tma):
         h.close()
 
 
+@pytest.mark.parametrize("shape,P", [((64, 32, 128), 2), ((32, 48, 256), 4), ((16, 1024, 128), 2)])
+def test_slab_grad_div_interp_match_single_brick(shape, P):
+    """grad / div / interp on P slabs (phase 1, exchange of three numbers per z line, operator and
+    neighbour, phase 2) against the whole periodic brick"""
+    import torch
+
+    from poissbox_b200 import _lib
+
+    nx, ny, nz = shape
+    nzl = nz // P
+    dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    v = torch.rand((3, nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    whole = pbx.Handle(nx, ny, nz, dx)
+    slabs = [pbx.Handle(nx, ny, nzl, dx, slab=(r, P)) for r in range(P)]
+    want = {_lib.OP_GRAD: whole.grad(f), _lib.OP_DIV: whole.div(v), _lib.OP_INTERP: whole.interp(f),
+            _lib.OP_INTERP_DIV: whole.interp(f, +1)}
+    for op, w in want.items():
+        zdim = 1 if op in (_lib.OP_GRAD,) else 0
+        parts = [(v[:, r * nzl:(r + 1) * nzl] if op == _lib.OP_DIV else f[r * nzl:(r + 1) * nzl]).contiguous()
+                 for r in range(P)]
+        for h, part in zip(slabs, parts):
+            h.slab_op_phase1(op, part)
+        pbx.Handle.slab_exchange_local(slabs)
+        out = torch.cat([h.slab_op_phase2(op, part) for h, part in zip(slabs, parts)], dim=zdim)
+        torch.cuda.synchronize()
+        err = (out - w).abs().max().item() / w.abs().max().item()
+        assert err <= 1e-13, (op, err)
+    for h in slabs + [whole]:
+        h.close()
+
+
 def test_slab_needs_64_to_512_planes():
     for nzl in (48, 528):
         with pytest.raises(pbx.PbxError) as e:

@@ -1,5 +1,5 @@
 """torchrun worker: checks the NCCL z-slab path (pbx_create with an ncclComm_t) on N GPUs against a
-single-GPU evaluation of the same global problem, for the Laplacian and for the CG.
+single-GPU evaluation of the same global problem, for the Laplacian, grad / div / interp and the CG.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port 29555 tools/dist_check.py [n]
@@ -47,6 +47,17 @@ w, dot = h.lapl_dot(mine)
 dref = torch.dot(f.flatten(), ref.flatten()).item()
 derr = abs(dot.item() - dref) / abs(dref)
 
+# grad / div / interp over the communicator against the whole brick (FAST line operators)
+v = torch.rand((3, n, n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+sl = slice(rank * nzl, (rank + 1) * nzl)
+gerr = 0.0
+for name, got, want in (("grad", h.grad(mine), whole.grad(f)[:, sl]),
+                        ("div", h.div(v[:, sl].contiguous()), whole.div(v)[sl]),
+                        ("interp", h.interp(mine), whole.interp(f)[sl]),
+                        ("interp_div", h.interp(mine, +1), whole.interp(f, +1)[sl])):
+    torch.cuda.synchronize()
+    gerr = max(gerr, (got - want).abs().max().item() / want.abs().max().item())
+
 # CG: b = A x_true on the global grid; the slab solve must take the same iterations (+-1)
 b = ref
 x1, its1, rn1, why1, hist1 = whole.cg_solve(b, rtol=1e-8)
@@ -56,10 +67,10 @@ torch.cuda.synchronize()
 xerr = (xs - x1[rank * nzl:(rank + 1) * nzl]).norm().item() / x1.norm().item()
 m = min(len(hist1), len(hist2)) // 2
 herr = float(np.max(np.abs(hist1[:m] - hist2[:m]) / hist1[:m]))
-ok = err <= 1e-13 and derr <= 1e-12 and why1 == why2 == 2 and abs(its1 - its2) <= 1 and xerr <= 1e-5 and herr <= 1e-6
+ok = err <= 1e-13 and gerr <= 1e-13 and derr <= 1e-12 and why1 == why2 == 2 and abs(its1 - its2) <= 1 and xerr <= 1e-5 and herr <= 1e-6
 res = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
-print(f"rank {rank}/{world}: lapl err {err:.2e} dot err {derr:.2e} cg its {its1} vs {its2} reasons {why1},{why2} "
+print(f"rank {rank}/{world}: lapl err {err:.2e} grad/div/interp err {gerr:.2e} dot err {derr:.2e} cg its {its1} vs {its2} reasons {why1},{why2} "
       f"xerr {xerr:.2e} hist err {herr:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
 h.close()
 whole.close()
