@@ -232,10 +232,11 @@ struct XT {
 
 struct XShared {
     double tin[TILE_DOUBLES];
-    double sta[TILE_DOUBLES];
-    double stb[TILE_DOUBLES];
+    double sta[TILE_DOUBLES];   // WIDE: the chunk-state exchange area (X_SLOTS * NT doubles) lives in
+    double stb[TILE_DOUBLES];   // sta..stb while a tile is computed, before the results are staged
     uint64_t full, empty;
 };
+static_assert(X_SLOTS * NT <= 2 * TILE_DOUBLES, "exchange area must fit the two staging tiles");
 
 // swizzled address of 16-byte piece j of row q (128-byte rows, TMA SWIZZLE_128B)
 __device__ __forceinline__ int swz(int q, int j) { return q * 16 + ((j ^ (q & 7)) << 1); }
@@ -276,6 +277,11 @@ __device__ __forceinline__ void solve_shfl(const CompositeCoef &c, double (&v)[L
     bwd_fix(c, v, Y, Z);
 }
 
+// WIDE = false: a line is at most one warp (T <= 32 chunks); states and halos by shuffle.
+// WIDE = true:  T = 64, 128 or 256 chunks (lines of 1024 - 4096 points): a line spans several warps
+//               of the CTA, and the chunk states and solved halos go through shared memory
+//               (xpass_body, the arithmetic of the generic x kernel) -- same TMA data movement.
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 2)
 x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap mapF,
              const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB)
@@ -298,8 +304,9 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
     const int lane = tid & 31;
     const int T = p.T;
     const int seg = lane & ~(T - 1), t = lane & (T - 1);
-    const int ql = (tid & ~31) | seg | ((t - 1) & (T - 1));   // row of the previous chunk of the line
-    const int qr = (tid & ~31) | seg | ((t + 1) & (T - 1));
+    // rows of the previous / next chunk of the same line
+    const int ql = WIDE ? ((tid & ~(T - 1)) | ((tid - 1) & (T - 1))) : ((tid & ~31) | seg | ((t - 1) & (T - 1)));
+    const int qr = WIDE ? ((tid & ~(T - 1)) | ((tid + 1) & (T - 1))) : ((tid & ~31) | seg | ((t + 1) & (T - 1)));
     int it = 0;
     for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
         const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
@@ -332,6 +339,14 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         }
 
         double va[LC], vb[LC];
+        if (WIDE) {
+            // the exchange area aliases the staging tiles: the previous tile's TMA stores must have
+            // read them
+            if (tid == 0) tma_wait_read0();
+            BarCompute()();
+            const Xchg xc{S.sta, tid, tid & (T - 1), T, 1};
+            xpass_body(p.M, p.D, xc, ef, va, vb, BarCompute());
+        } else {
         stencil<true>(p.D, ef, va);
 #pragma unroll
         for (int k = 0; k < LC; ++k) vb[k] = ef[k + 3];
@@ -351,9 +366,11 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             for (int k = 0; k < LC; ++k) e[k + 3] = vb[k];
             stencil<false>(p.M, e, vb);
         }
+        }
 
-        // staging tiles: wait until the previous tile's TMA stores have read them
-        if (tid == 0) tma_wait_read0();
+        // staging tiles: wait until the previous tile's TMA stores have read them (WIDE: until
+        // everybody has read the exchange area)
+        if (!WIDE && tid == 0) tma_wait_read0();
         BarCompute()();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -486,7 +503,8 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
                    double *B, int rev, long long *launches)
 {
     const int T = g.nx / LC;
-    if (g.nx % LC || T > 32 || (T & (T - 1)) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    if (g.nx % LC || T > NT || (T & (T - 1)) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    const bool wide = T > 32;
     const size_t nchunks = g.N() / LC;
     if (nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
     XT p;
@@ -503,13 +521,18 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
-        PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = 2 * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    x_tma_kernel<<<grid, NT, smem, s>>>(p, mf, ma, mb);
+    if (wide)
+        x_tma_kernel<true><<<grid, NT, smem, s>>>(p, mf, ma, mb);
+    else
+        x_tma_kernel<false><<<grid, NT, smem, s>>>(p, mf, ma, mb);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -49,9 +49,10 @@ def test_emu_lapl_fast_and_reference(shape, no_tma):
     h.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 32, 64), (16, 1024, 16), (16, 16, 656)])
+@pytest.mark.parametrize("shape", [(64, 32, 64), (16, 1024, 16), (16, 16, 656), (1024, 16, 16)])
 def test_emu_tma_and_generic_bit_identical(shape):
-    """includes y / z lines of more than 512 points, which run as overlapping segments"""
+    """includes y / z lines of more than 512 points, which run as overlapping segments, and x lines
+    of 1024 points (several warps per line in the TMA x kernel)"""
     dx = tuple(1.0 / n for n in shape)
     f = field(shape, 7)
     outs = []

@@ -181,7 +181,8 @@ def test_long_lines_reference_bit_exact(shape):
 
 
 def test_fast_long_x_lines():
-    """x lines of 2048 and 4096 points on the FAST schedule (generic x kernel, cross-warp exchange)"""
+    """x lines of 2048 and 4096 points on the FAST schedule (several warps per line: chunk states
+    through shared memory in both the TMA and the generic x kernel)"""
     for shape in ((2048, 16, 16), (4096, 16, 16)):
         rng = np.random.default_rng(5)
         f = np.asfortranarray(rng.uniform(-1, 1, shape))
@@ -324,7 +325,8 @@ def test_lapl_full_size_properties():
 
 
 @pytest.mark.parametrize("shape", [(512, 512, 32), (64, 64, 64), (256, 128, 32), (32, 512, 512), (48, 80, 112),
-                                   (64, 1024, 32), (32, 16, 2048), (16, 640, 1088)])
+                                   (64, 1024, 32), (32, 16, 2048), (16, 640, 1088), (1024, 64, 32),
+                                   (4096, 16, 16), (2048, 1024, 16)])
 def test_tma_and_generic_kernels_bit_identical(shape):
     """the TMA-pipelined persistent kernels and the generic kernels share their arithmetic
     (pbx_fast_common.cuh): same bits, including the fused p.Ap partial sums"""
