@@ -9,6 +9,12 @@ namespace pbx {
 
 namespace {
 
+// The sweeps are serial recurrences with a division per point, so a thread can only hide the
+// latency of its global loads by issuing them ahead: every sweep walks its line in blocks of PF
+// points and loads block k+1 into registers before it computes block k (same operations in the
+// same order as the plain loop -- the results carry the same bits).
+constexpr int PF = 8;
+
 // fwd_sweep, src/tridsol.f90:76-96 (a sub-diagonal, b DIAGONAL <- pivots, c super-diagonal)
 __global__ void __launch_bounds__(128)
 fwd_kernel(int n, long long nl, long long es, long long ls, const double *__restrict__ a,
@@ -18,14 +24,45 @@ fwd_kernel(int n, long long nl, long long es, long long ls, const double *__rest
     if (l >= nl) return;
     const long long o = l * ls;
     double bp = b[o], dp = d[o], cp = c[o];
-    for (int i = 1; i < n; ++i) {
-        const long long q = o + i * es;
-        double w = __ddiv_rn(a[q], bp);
-        bp = __dsub_rn(b[q], __dmul_rn(w, cp));
-        dp = __dsub_rn(d[q], __dmul_rn(w, dp));
-        cp = c[q];
-        b[q] = bp;
-        d[q] = dp;
+    double an[PF], bn[PF], cn[PF], dn[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const long long q = o + (long long)(1 + u) * es;
+        const bool in = 1 + u < n;
+        an[u] = in ? a[q] : 0.0;
+        bn[u] = in ? b[q] : 1.0;
+        cn[u] = in ? c[q] : 0.0;
+        dn[u] = in ? d[q] : 0.0;
+    }
+    for (int i0 = 1; i0 < n; i0 += PF) {
+        double ac[PF], bc[PF], cc[PF], dc[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            ac[u] = an[u];
+            bc[u] = bn[u];
+            cc[u] = cn[u];
+            dc[u] = dn[u];
+            const int i = i0 + PF + u;
+            const long long q = o + (long long)i * es;
+            const bool in = i < n;
+            an[u] = in ? a[q] : 0.0;
+            bn[u] = in ? b[q] : 1.0;
+            cn[u] = in ? c[q] : 0.0;
+            dn[u] = in ? d[q] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int i = i0 + u;
+            if (i < n) {
+                const long long q = o + (long long)i * es;
+                double w = __ddiv_rn(ac[u], bp);
+                bp = __dsub_rn(bc[u], __dmul_rn(w, cp));
+                dp = __dsub_rn(dc[u], __dmul_rn(w, dp));
+                cp = cc[u];
+                b[q] = bp;
+                d[q] = dp;
+            }
+        }
     }
 }
 
@@ -40,10 +77,38 @@ bwd_kernel(int n, long long nl, long long es, long long ls, const double *__rest
     long long q = o + (long long)(n - 1) * es;
     double x = __ddiv_rn(d[q], b[q]);
     d[q] = x;
-    for (int i = n - 2; i >= 0; --i) {
-        q = o + i * es;
-        x = __ddiv_rn(__dsub_rn(d[q], __dmul_rn(c[q], x)), b[q]);
-        d[q] = x;
+    double bn[PF], cn[PF], dn[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int i = n - 2 - u;
+        const long long qq = o + (long long)i * es;
+        const bool in = i >= 0;
+        bn[u] = in ? b[qq] : 1.0;
+        cn[u] = in ? c[qq] : 0.0;
+        dn[u] = in ? d[qq] : 0.0;
+    }
+    for (int i0 = n - 2; i0 >= 0; i0 -= PF) {
+        double bc[PF], cc[PF], dc[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            bc[u] = bn[u];
+            cc[u] = cn[u];
+            dc[u] = dn[u];
+            const int i = i0 - PF - u;
+            const long long qq = o + (long long)i * es;
+            const bool in = i >= 0;
+            bn[u] = in ? b[qq] : 1.0;
+            cn[u] = in ? c[qq] : 0.0;
+            dn[u] = in ? d[qq] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int i = i0 - u;
+            if (i >= 0) {
+                x = __ddiv_rn(__dsub_rn(dc[u], __dmul_rn(cc[u], x)), bc[u]);
+                d[o + (long long)i * es] = x;
+            }
+        }
     }
 }
 
@@ -59,44 +124,109 @@ periodic_kernel(int n, long long nl, long long es, long long ls, const double *_
     const long long o = l * ls;
     const long long qn = o + (long long)(n - 1) * es;
     const double gamma = -b[o];                                      // :51
-    const double a1 = a[o], cn = c[qn];
+    const double a1 = a[o], cn_ = c[qn];
     const double b1m = __dsub_rn(b[o], gamma);                       // :55
-    const double bnm = __dsub_rn(b[qn], __ddiv_rn(__dmul_rn(cn, a1), gamma));   // :56
+    const double bnm = __dsub_rn(b[qn], __ddiv_rn(__dmul_rn(cn_, a1), gamma));   // :56
 
     // two forward sweeps (:57 on d, :66 on u) share the pivots; pivots are stored for the
     // backward sweeps
     double bp = b1m, dp = d[o], up = gamma, cp = c[o];
     bmod[l] = bp;
     u[l] = up;
-    for (int i = 1; i < n; ++i) {
-        const long long q = o + i * es;
-        double bi = (i == n - 1) ? bnm : b[q];
-        double ui = (i == n - 1) ? cn : 0.0;                         // :63-65
-        double w = __ddiv_rn(a[q], bp);
-        bp = __dsub_rn(bi, __dmul_rn(w, cp));
-        dp = __dsub_rn(d[q], __dmul_rn(w, dp));
-        up = __dsub_rn(ui, __dmul_rn(w, up));
-        cp = c[q];
-        bmod[i * nl + l] = bp;
-        u[i * nl + l] = up;
-        d[q] = dp;
+    {
+        double an[PF], bn[PF], cn[PF], dn[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const long long q = o + (long long)(1 + k) * es;
+            const bool in = 1 + k < n;
+            an[k] = in ? a[q] : 0.0;
+            bn[k] = in ? b[q] : 1.0;
+            cn[k] = in ? c[q] : 0.0;
+            dn[k] = in ? d[q] : 0.0;
+        }
+        for (int i0 = 1; i0 < n; i0 += PF) {
+            double ac[PF], bc[PF], cc[PF], dc[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                ac[k] = an[k];
+                bc[k] = bn[k];
+                cc[k] = cn[k];
+                dc[k] = dn[k];
+                const int i = i0 + PF + k;
+                const long long q = o + (long long)i * es;
+                const bool in = i < n;
+                an[k] = in ? a[q] : 0.0;
+                bn[k] = in ? b[q] : 1.0;
+                cn[k] = in ? c[q] : 0.0;
+                dn[k] = in ? d[q] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int i = i0 + k;
+                if (i < n) {
+                    const long long q = o + (long long)i * es;
+                    double bi = (i == n - 1) ? bnm : bc[k];
+                    double ui = (i == n - 1) ? cn_ : 0.0;                // :63-65
+                    double w = __ddiv_rn(ac[k], bp);
+                    bp = __dsub_rn(bi, __dmul_rn(w, cp));
+                    dp = __dsub_rn(dc[k], __dmul_rn(w, dp));
+                    up = __dsub_rn(ui, __dmul_rn(w, up));
+                    cp = cc[k];
+                    bmod[i * nl + l] = bp;
+                    u[i * nl + l] = up;
+                    d[q] = dp;
+                }
+            }
+        }
     }
     // backward sweeps
     double xd = __ddiv_rn(dp, bp), xu = __ddiv_rn(up, bp);
     d[qn] = xd;
     u[(long long)(n - 1) * nl + l] = xu;
-    const double dn = xd, un = xu;
-    for (int i = n - 2; i >= 0; --i) {
-        const long long q = o + i * es;
-        const double ci = c[q], bi = bmod[i * nl + l];
-        xd = __ddiv_rn(__dsub_rn(d[q], __dmul_rn(ci, xd)), bi);
-        xu = __ddiv_rn(__dsub_rn(u[i * nl + l], __dmul_rn(ci, xu)), bi);
-        d[q] = xd;
-        u[i * nl + l] = xu;
+    const double dn_ = xd, un = xu;
+    {
+        double cn[PF], bn[PF], dn[PF], vn[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = n - 2 - k;
+            const long long q = o + (long long)i * es;
+            const bool in = i >= 0;
+            cn[k] = in ? c[q] : 0.0;
+            bn[k] = in ? bmod[i * nl + l] : 1.0;
+            dn[k] = in ? d[q] : 0.0;
+            vn[k] = in ? u[i * nl + l] : 0.0;
+        }
+        for (int i0 = n - 2; i0 >= 0; i0 -= PF) {
+            double cc[PF], bc[PF], dc[PF], vc[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                cc[k] = cn[k];
+                bc[k] = bn[k];
+                dc[k] = dn[k];
+                vc[k] = vn[k];
+                const int i = i0 - PF - k;
+                const long long q = o + (long long)i * es;
+                const bool in = i >= 0;
+                cn[k] = in ? c[q] : 0.0;
+                bn[k] = in ? bmod[i * nl + l] : 1.0;
+                dn[k] = in ? d[q] : 0.0;
+                vn[k] = in ? u[i * nl + l] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int i = i0 - k;
+                if (i >= 0) {
+                    xd = __ddiv_rn(__dsub_rn(dc[k], __dmul_rn(cc[k], xd)), bc[k]);
+                    xu = __ddiv_rn(__dsub_rn(vc[k], __dmul_rn(cc[k], xu)), bc[k]);
+                    d[o + (long long)i * es] = xd;
+                    u[i * nl + l] = xu;
+                }
+            }
+        }
     }
     // :69-70
     const double a1g = __ddiv_rn(a1, gamma);
-    const double fac = __dadd_rn(xd, __dmul_rn(a1g, dn));
+    const double fac = __dadd_rn(xd, __dmul_rn(a1g, dn_));
     const double den = __dadd_rn(1.0, __dadd_rn(xu, __dmul_rn(a1g, un)));
     for (int i = 0; i < n; ++i) {
         const long long q = o + i * es;

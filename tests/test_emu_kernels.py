@@ -104,6 +104,32 @@ def test_emu_tridsol_bit_exact(n):
         assert np.array_equal(dd, orc.tdma_periodic(a, b, c, d))
 
 
+@pytest.mark.parametrize("n", [5, 64, 203])
+def test_emu_tridsol_batch_layouts(n):
+    """many lines per launch, line-major and element-major layouts, all four routines"""
+    lib = emu_lib.load()
+    rng = np.random.default_rng(3 + n)
+    nl = 37
+    for per in (False, True):
+        sys_ = [tdma_init(n, rng, per) for _ in range(nl)]
+        A, B, C, D = (np.stack([s_[i] for s_ in sys_]) for i in (0, 1, 2, 4))   # [line][i]
+        want_t = np.stack([orc.tdma(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_])
+        want_p = np.stack([orc.tdma_periodic(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_])
+        want_b = np.stack([orc.fwd_sweep(s_[0], s_[1], s_[2], s_[4])[0] for s_ in sys_])
+        for layout in ("line_major", "elem_major"):
+            tr = (lambda v: v.copy()) if layout == "line_major" else (lambda v: np.ascontiguousarray(v.T))
+            es, ls = (1, n) if layout == "line_major" else (nl, 1)
+            back = (lambda v: v) if layout == "line_major" else (lambda v: v.T)
+            a, b, c, d = (tr(v) for v in (A, B, C, D))
+            emu_lib.check(lib, lib.pbx_tdma_batch_device(n, nl, es, ls, emu_lib.ptr(a), emu_lib.ptr(b),
+                                                         emu_lib.ptr(c), emu_lib.ptr(d), None))
+            assert np.array_equal(back(d), want_t) and np.array_equal(back(b), want_b)
+            a, b, c, d = (tr(v) for v in (A, B, C, D))
+            emu_lib.check(lib, lib.pbx_tdma_periodic_batch_device(n, nl, es, ls, emu_lib.ptr(a), emu_lib.ptr(b),
+                                                                  emu_lib.ptr(c), emu_lib.ptr(d), None))
+            assert np.array_equal(back(d), want_p) and np.array_equal(back(b), B)
+
+
 def test_emu_cg_matches_oracle():
     n = 16
     dx = (2 * np.pi / n,) * 3
