@@ -125,6 +125,7 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n);
 #define PBX_OP_DIV 2
 #define PBX_OP_INTERP 3      /* stagger -1 */
 #define PBX_OP_INTERP_DIV 4  /* stagger +1 */
+#define PBX_OP_STAR 5        /* the 2nd-order star: one plane travels each way */
 int pbx_slab_op_phase1(pbx_handle h, int op, const double *in);
 int pbx_slab_op_phase2(pbx_handle h, int op, const double *in, double *out);
 /* the same exchange over the handle's NCCL communicator, and the CG's scalar all-reduce (exposed
@@ -154,6 +155,24 @@ int pbx_grad_device(pbx_handle h, const double *f, double *df);
 int pbx_div_device(pbx_handle h, const double *f, double *df);
 /* compact_schemes::interp / interp_div  src/compact_schemes.f90:93-152 */
 int pbx_interp_device(pbx_handle h, const double *f, double *fi, int stagger);
+
+/* ---------------------------------------------------------------------------------------------
+ * The 2nd-order 7-point star on the periodic box: what the reference's MatMult callback applies
+ * today (mfmult -> compute_lapl_pointwise, src/poissbox.f90:84-148 and :300-322, coefficients
+ * src/coefficients.f90:22-48) and the matrix P it preconditions with (:294).  Bit-identical to the
+ * reference's dot_product over the 3x3x3 box.
+ *   pbx_set_operator   which operator the shell matrix is: PBX_OPERATOR_COMPACT (default, the
+ *                      compact Laplacian the drop-in re-points mfmult at) or PBX_OPERATOR_STAR
+ *   pbx_matmult_device y = A x for the handle's operator: the body of the MATSHELL callback; the
+ *                      CG (pbx_cg_solve_*) runs on the same operator
+ * ------------------------------------------------------------------------------------------- */
+#define PBX_OPERATOR_COMPACT 0
+#define PBX_OPERATOR_STAR 1
+int pbx_set_operator(pbx_handle h, int op);
+int pbx_get_operator(pbx_handle h, int *op);
+int pbx_matmult_device(pbx_handle h, const double *x, double *y);
+int pbx_star_device(pbx_handle h, const double *x, double *y);
+int pbx_star_host(int nx, int ny, int nz, const double *x, const double dx[3], double *y);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched 1-D compact operators: one call applies grad_1d / interp_1d to `nlines` periodic lines

@@ -319,6 +319,70 @@ void orc_lapl(int nx, int ny, int nz, const double *f, const double dx[3], doubl
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* The 2nd-order star (the operator mfmult applies today, src/poissbox.f90:300-322).            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* src/coefficients.f90:22-37 */
+void orc_lapl_1d_coeffs(double dx, double coeffs[3])
+{
+    const double invdx2 = 1.0 / (dx * dx); /* :29  1 / dx**2 */
+    coeffs[0] = invdx2;                    /* :31 */
+    coeffs[1] = -2.0 * invdx2;             /* :32 */
+    coeffs[2] = invdx2;                    /* :33 */
+}
+
+/* src/coefficients.f90:40-50; coeffs(ii,jj,kk) <-> coeffs[ii + 3*(jj + 3*kk)], 0-based */
+void orc_lapl_star_coeffs(double dx, double dy, double dz, double coeffs[27])
+{
+    double c[3];
+    for (int i = 0; i < 27; ++i) coeffs[i] = 0.0; /* :45 */
+    orc_lapl_1d_coeffs(dx, c);
+    for (int i = 0; i < 3; ++i) coeffs[i + 3 * (1 + 3 * 1)] = coeffs[i + 3 * (1 + 3 * 1)] + c[i]; /* :46 */
+    orc_lapl_1d_coeffs(dy, c);
+    for (int j = 0; j < 3; ++j) coeffs[1 + 3 * (j + 3 * 1)] = coeffs[1 + 3 * (j + 3 * 1)] + c[j]; /* :47 */
+    orc_lapl_1d_coeffs(dz, c);
+    for (int k = 0; k < 3; ++k) coeffs[1 + 3 * (1 + 3 * k)] = coeffs[1 + 3 * (1 + 3 * k)] + c[k]; /* :48 */
+}
+
+/* src/poissbox.f90:128-148: dot_product over the flattened 3x3x3 boxes, in array element order */
+double orc_evaluate_laplacian_pointwise(const double f[27], const double grid_deltas[3])
+{
+    double coeffs[27], s = 0.0;
+    orc_lapl_star_coeffs(grid_deltas[0], grid_deltas[1], grid_deltas[2], coeffs);
+    for (int i = 0; i < 27; ++i) s = s + f[i] * coeffs[i];
+    return s;
+}
+
+typedef struct { int nx, ny, nz; const double *x; const double *dx; double *b; } star_ctx;
+
+static void star_range(long lo, long hi, int tid, void *p)
+{
+    star_ctx *c = (star_ctx *)p;
+    (void)tid;
+    const int nx = c->nx, ny = c->ny, nz = c->nz;
+    for (long k = lo; k < hi; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                double f[27]; /* xdof(i-1:i+1, j-1:j+1, k-1:k+1), :107, periodic ghosts */
+                for (int kk = 0; kk < 3; ++kk)
+                    for (int jj = 0; jj < 3; ++jj)
+                        for (int ii = 0; ii < 3; ++ii) {
+                            const int gi = (i + ii - 1 + nx) % nx, gj = (j + jj - 1 + ny) % ny;
+                            const int gk = (int)((k + kk - 1 + nz) % nz);
+                            f[ii + 3 * (jj + 3 * kk)] = c->x[gi + (size_t)nx * (gj + (size_t)ny * gk)];
+                        }
+                c->b[i + (size_t)nx * (j + (size_t)ny * k)] = orc_evaluate_laplacian_pointwise(f, c->dx);
+            }
+}
+
+/* src/poissbox.f90:84-126 */
+void orc_star(int nx, int ny, int nz, const double *x, const double dx[3], double *b)
+{
+    star_ctx c = {nx, ny, nz, x, dx, b};
+    par_for(nz, star_range, &c);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* CG.  Follows PETSc KSPCG (third-party; src/poissbox.f90:293-296 creates the KSP, :285-291     */
 /* attaches a constant MatNullSpace to A and P).  With -pc_type none the "preconditioner        */
 /* apply" is a copy followed by null-space removal (z = r - mean(r)), the default norm is the   */
@@ -414,6 +478,15 @@ int orc_cg_solve(int nx, int ny, int nz, const double dx[3], const double *b, do
                  double rtol, double abstol, int maxit, double *rnorm, int *reason, double *hist,
                  int nhist)
 {
+    return orc_cg_solve_op(0, nx, ny, nz, dx, b, x, rtol, abstol, maxit, rnorm, reason, hist, nhist);
+}
+
+/* op = 0: the compact Laplacian (orc_lapl); 1: the 2nd-order star (orc_star), the operator the
+ * reference's shell matrix applies today */
+int orc_cg_solve_op(int op, int nx, int ny, int nz, const double dx[3], const double *b, double *x,
+                    double rtol, double abstol, int maxit, double *rnorm, int *reason, double *hist,
+                    int nhist)
+{
     const size_t N = (size_t)nx * ny * nz;
     double *r = (double *)malloc(sizeof(double) * N);
     double *z = (double *)malloc(sizeof(double) * N);
@@ -445,7 +518,10 @@ int orc_cg_solve(int nx, int ny, int nz, const double dx[3], const double *b, do
                 vaypx(N, bb, z, p); /* VecAYPX: p <- z + b p */
             }
             dpiold = dpi;
-            orc_lapl(nx, ny, nz, p, dx, w);
+            if (op == 1)
+                orc_star(nx, ny, nz, p, dx, w);
+            else
+                orc_lapl(nx, ny, nz, p, dx, w);
             dpi = vdot(N, p, w);
             betaold = beta;
             if (dpi == 0.0 || (i > 0 && ((dpi > 0) - (dpi < 0)) * ((dpiold > 0) - (dpiold < 0)) < 0)) {

@@ -53,6 +53,15 @@ void orc_interp(int nx, int ny, int nz, const double *f, double *fi, int stagger
 void orc_interp_div(int nx, int ny, int nz, const double *f, double *fi);
 void orc_lapl(int nx, int ny, int nz, const double *f, const double dx[3], double *d2f);
 
+/* ---- the 2nd-order 7-point star: what the reference's MatMult callback computes TODAY ----
+ * src/coefficients.f90:22-48 (lapl_1d_coeffs, lapl_star_coeffs) and src/poissbox.f90:84-148
+ * (compute_lapl_pointwise, evaluate_laplacian_pointwise), called by mfmult :300-322; periodic
+ * ghosts as the DMDA provides them (DM_BOUNDARY_PERIODIC). */
+void orc_lapl_1d_coeffs(double dx, double coeffs[3]);
+void orc_lapl_star_coeffs(double dx, double dy, double dz, double coeffs[27]);
+double orc_evaluate_laplacian_pointwise(const double f[27], const double grid_deltas[3]);
+void orc_star(int nx, int ny, int nz, const double *x, const double dx[3], double *b);
+
 /* thread count used by the 3-D routines' loops over lines (1 = the reference's serial behaviour;
  * >1 is the "all host cores" courtesy baseline, results are bit-identical either way). */
 void orc_set_threads(int nthreads);
@@ -65,6 +74,10 @@ int orc_get_threads(void);
 int orc_cg_solve(int nx, int ny, int nz, const double dx[3], const double *b, double *x,
                  double rtol, double abstol, int maxit, double *rnorm, int *reason, double *hist,
                  int nhist);
+
+int orc_cg_solve_op(int op, int nx, int ny, int nz, const double dx[3], const double *b, double *x,
+                    double rtol, double abstol, int maxit, double *rnorm, int *reason, double *hist,
+                    int nhist);
 
 #ifdef __cplusplus
 }

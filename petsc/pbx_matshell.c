@@ -35,8 +35,10 @@ static PetscErrorCode PbxMatMult(Mat M, Vec x, Vec f)
     PetscCall(MatShellGetContext(M, &ctx));
     PetscCall(VecCUDAGetArrayRead(x, &px));
     PetscCall(VecCUDAGetArrayWrite(f, &pf));
-    PetscCheck(pbx_lapl_device(ctx->h, (const double *)px, (double *)pf) == PBX_OK, PETSC_COMM_SELF,
-               PETSC_ERR_LIB, "pbx_lapl_device: %s", pbx_last_error());
+    /* the handle's operator: the compact Laplacian (default) or, after
+     * pbx_set_operator(h, PBX_OPERATOR_STAR), the 2nd-order star mfmult applies today */
+    PetscCheck(pbx_matmult_device(ctx->h, (const double *)px, (double *)pf) == PBX_OK, PETSC_COMM_SELF,
+               PETSC_ERR_LIB, "pbx_matmult_device: %s", pbx_last_error());
     PetscCall(VecCUDARestoreArrayWrite(f, &pf));
     PetscCall(VecCUDARestoreArrayRead(x, &px));
     PetscFunctionReturn(PETSC_SUCCESS);

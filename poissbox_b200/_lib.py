@@ -18,7 +18,8 @@ _d3 = c_double * 3
 PBX_OK, PBX_ERR_ARG, PBX_ERR_CUDA, PBX_ERR_NCCL, PBX_ERR_UNSUPPORTED, PBX_ERR_NOMEM = 0, 1, 2, 3, 4, 5
 PBX_ERR_SIZE = 7
 MODE_FAST, MODE_REFERENCE = 0, 1
-OP_GRAD, OP_DIV, OP_INTERP, OP_INTERP_DIV = 1, 2, 3, 4
+OP_GRAD, OP_DIV, OP_INTERP, OP_INTERP_DIV, OP_STAR = 1, 2, 3, 4, 5
+OPERATOR_COMPACT, OPERATOR_STAR = 0, 1
 
 # every symbol include/pbx.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -52,6 +53,11 @@ SIGNATURES = {
     "pbx_grad_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_div_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_interp_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "pbx_set_operator": (c_int, [c_void_p, c_int]),
+    "pbx_get_operator": (c_int, [c_void_p, _ip]),
+    "pbx_matmult_device": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pbx_star_device": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pbx_star_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp]),
     "pbx_grad_1d_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_double, c_void_p, c_int, c_void_p]),
     "pbx_interp_1d_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_int, c_void_p]),
     "pbx_tdma_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

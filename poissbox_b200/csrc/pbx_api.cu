@@ -183,6 +183,17 @@ int slab_op_phase1(pbx_handle_s *h, int op, const double *in)
         return line_boundary(h, 0, OP_INTERP, PBX_STAGGER_BACKWARD, in);
     case PBX_OP_INTERP_DIV:
         return line_boundary(h, 0, OP_INTERP, PBX_STAGGER_FORWARD, in);
+    case PBX_OP_STAR: {
+        // my bottom plane is the lower rank's plane above its top, my top plane the upper rank's
+        // plane below its bottom
+        double *dn = nullptr, *up = nullptr;
+        PBX_TRY(dist_line_dst(h, 0, &dn, &up));
+        const size_t plane = (size_t)h->nx * h->ny;
+        PBX_CUDA(cudaMemcpyAsync(dn, in, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        PBX_CUDA(cudaMemcpyAsync(up, in + plane * (h->nz - 1), plane * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, h->stream));
+        return PBX_OK;
+    }
     default:
         return PBX_ERR_ARG;
     }
@@ -200,6 +211,11 @@ int slab_op_phase2(pbx_handle_s *h, int op, const double *in, double *out)
         return interp_stages_run(h, in, out, PBX_STAGGER_BACKWARD, true);
     case PBX_OP_INTERP_DIV:
         return interp_stages_run(h, in, out, PBX_STAGGER_FORWARD, true);
+    case PBX_OP_STAR: {
+        const double *lo = nullptr, *up = nullptr;
+        PBX_TRY(dist_line_msgs(h, 0, &lo, &up));
+        return star_apply(h, in, out, lo, up);
+    }
     default:
         return PBX_ERR_ARG;
     }
@@ -485,6 +501,51 @@ static int slab_op(pbx_handle h, int op, const double *in, double *out)
     return slab_op_phase2(h, op, in, out);
 }
 
+}  // extern "C"
+
+namespace pbx {
+int matmult(pbx_handle_s *h, const double *x, double *y)
+{
+    if (h->op == PBX_OPERATOR_STAR) {
+        if (h->nranks > 1) return slab_op(h, PBX_OP_STAR, x, y);
+        return star_apply(h, x, y, nullptr, nullptr);
+    }
+    if (h->nranks > 1) return dist_lapl(h, x, y, nullptr, nullptr);
+    return h->mode == PBX_MODE_FAST ? lapl_fast(h, x, y, nullptr, nullptr) : lapl_reference(h, x, y);
+}
+}  // namespace pbx
+
+extern "C" {
+
+int pbx_set_operator(pbx_handle h, int op)
+{
+    if (!h || (op != PBX_OPERATOR_COMPACT && op != PBX_OPERATOR_STAR)) return PBX_ERR_ARG;
+    h->op = op;
+    return PBX_OK;
+}
+
+int pbx_get_operator(pbx_handle h, int *op)
+{
+    if (!h || !op) return PBX_ERR_ARG;
+    *op = h->op;
+    return PBX_OK;
+}
+
+int pbx_matmult_device(pbx_handle h, const double *x, double *y)
+{
+    if (!h || !x || !y || x == y) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return matmult(h, x, y);
+}
+
+int pbx_star_device(pbx_handle h, const double *x, double *y)
+{
+    if (!h || !x || !y || x == y) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    if (h->nranks > 1) return slab_op(h, PBX_OP_STAR, x, y);
+    return star_apply(h, x, y, nullptr, nullptr);
+}
+
 int pbx_grad_device(pbx_handle h, const double *f, double *df)
 {
     if (!h || !f || !df) return PBX_ERR_ARG;
@@ -728,6 +789,12 @@ int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], d
         PBX_TRY(pbx_set_mode(e->h, m));
         return pbx_lapl_device(e->h, e->din, e->dout);
     });
+}
+
+int pbx_star_host(int nx, int ny, int nz, const double *x, const double dx[3], double *y)
+{
+    return host_run(nx, ny, nz, dx, x, 1, y, 1,
+                    [&](HostEntry *e) { return pbx_star_device(e->h, e->din, e->dout); });
 }
 
 static int host_mode_for(HostEntry *e)

@@ -305,7 +305,12 @@ int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int gu
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     cudaStream_t s = h->stream;
     int np;
-    if (h->nranks > 1) {
+    if (h->op == PBX_OPERATOR_STAR) {
+        PBX_TRY(matmult(h, p, w));
+        np = vec_grid(N);
+        k_dot_generic<<<np, VT, 0, s>>>(N, p, w, h->cg_partials);
+        ++h->launches;
+    } else if (h->nranks > 1) {
         PBX_TRY(dist_lapl(h, p, w, p, h->cg_partials));
         np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
     } else if (h->mode == PBX_MODE_FAST) {

@@ -225,6 +225,7 @@ struct pbx_handle_s {
     double dx[3] = {0, 0, 0};
     int device = 0;
     int mode = PBX_MODE_FAST;
+    int op = PBX_OPERATOR_COMPACT;   // what pbx_matmult_device and the CG apply
     cudaStream_t stream = nullptr;
     void *comm = nullptr;   // ncclComm_t
     int rank = 0, nranks = 1;
@@ -266,6 +267,10 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
 int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast);
 int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast);
 int interp_stages_run(pbx_handle_s *h, const double *f, double *fi, int stagger, bool fast);
+// 2nd-order star (pbx_star.cu); lo / up: neighbour planes of a slab (nullptr: periodic in z)
+int star_apply(pbx_handle_s *h, const double *x, double *y, const double *lo, const double *up);
+// y = A x for the handle's operator, whatever the decomposition (pbx_api.cu)
+int matmult(pbx_handle_s *h, const double *x, double *y);
 int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol, int maxit,
              int *its, double *rnorm, int *reason, double *hist, int nhist);
 int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);

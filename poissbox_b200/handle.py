@@ -130,9 +130,28 @@ class Handle:
         check(LIB.pbx_lapl_device(self._h, self._field(f), self._field(out)))
         return out
 
-    def mult(self, x, y):
-        """MatMult of the shell matrix: y = A x (mfmult, src/poissbox.f90:300-322)"""
-        return self.lapl(x, y)
+    def mult(self, x, y=None):
+        """MatMult of the shell matrix: y = A x (mfmult, src/poissbox.f90:300-322) for the handle's
+        operator (`operator` property: the compact Laplacian, or the 2nd-order star mfmult applies today)"""
+        y = self.empty() if y is None else y
+        check(LIB.pbx_matmult_device(self._h, self._field(x), self._field(y)))
+        return y
+
+    def star(self, x, out=None):
+        """the 2nd-order 7-point star (compute_lapl_pointwise, src/poissbox.f90:84-126)"""
+        out = self.empty() if out is None else out
+        check(LIB.pbx_star_device(self._h, self._field(x), self._field(out)))
+        return out
+
+    @property
+    def operator(self):
+        op = ctypes.c_int()
+        check(LIB.pbx_get_operator(self._h, ctypes.byref(op)))
+        return op.value
+
+    @operator.setter
+    def operator(self, op):
+        check(LIB.pbx_set_operator(self._h, int(op)))
 
     def lapl_dot(self, f, out=None):
         out = self.empty() if out is None else out

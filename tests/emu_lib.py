@@ -89,6 +89,21 @@ class EmuHandle:
         check(self.lib, self.lib.pbx_lapl_device(self._h, ptr(f), ptr(out)))
         return out
 
+    def star(self, f):
+        f = aligned(f)
+        out = new_field(self.shape)
+        check(self.lib, self.lib.pbx_star_device(self._h, ptr(f), ptr(out)))
+        return out
+
+    def set_operator(self, op):
+        check(self.lib, self.lib.pbx_set_operator(self._h, op))
+
+    def mult(self, f):
+        f = aligned(f)
+        out = new_field(self.shape)
+        check(self.lib, self.lib.pbx_matmult_device(self._h, ptr(f), ptr(out)))
+        return out
+
     def lapl_dot(self, f):
         f = aligned(f)
         out = new_field(self.shape)

@@ -42,9 +42,14 @@ def _load():
         "orc_interp": (None, [i, i, i, _dp, _dp, i]),
         "orc_interp_div": (None, [i, i, i, _dp, _dp]),
         "orc_lapl": (None, [i, i, i, _dp, _dp, _dp]),
+        "orc_lapl_1d_coeffs": (None, [d, _dp]),
+        "orc_lapl_star_coeffs": (None, [d, d, d, _dp]),
+        "orc_evaluate_laplacian_pointwise": (d, [_dp, _dp]),
+        "orc_star": (None, [i, i, i, _dp, _dp, _dp]),
         "orc_set_threads": (None, [i]),
         "orc_get_threads": (i, []),
         "orc_cg_solve": (i, [i, i, i, _dp, _dp, _dp, d, d, i, _dp, _ip, _dp, i]),
+        "orc_cg_solve_op": (i, [i, i, i, i, _dp, _dp, _dp, d, d, i, _dp, _ip, _dp, i]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -165,13 +170,42 @@ def lapl(f, dx):
     return out
 
 
-def cg_solve(b, dx, rtol=1e-5, abstol=1e-50, maxit=10000):
+# ---- the 2nd-order star (coefficients.f90, compute_lapl) ----
+def lapl_1d_coeffs(dx):
+    c = np.zeros(3)
+    LIB.orc_lapl_1d_coeffs(float(dx), _p(c))
+    return c
+
+
+def lapl_star_coeffs(dx, dy, dz):
+    c = np.zeros((3, 3, 3), order="F")
+    LIB.orc_lapl_star_coeffs(float(dx), float(dy), float(dz), _p(c))
+    return c
+
+
+def evaluate_laplacian_pointwise(f, grid_deltas):
+    f = _f(f)
+    assert f.shape == (3, 3, 3)
+    return LIB.orc_evaluate_laplacian_pointwise(_p(f), _dx(grid_deltas))
+
+
+def star(x, dx):
+    """compute_lapl_pointwise on a periodic box (what mfmult applies today)"""
+    x = _f(x)
+    nx, ny, nz = x.shape
+    out = np.full((nx, ny, nz), 73.29, order="F")
+    LIB.orc_star(nx, ny, nz, _p(x), _dx(dx), _p(out))
+    return out
+
+
+def cg_solve(b, dx, rtol=1e-5, abstol=1e-50, maxit=10000, op=0):
+    """op = 0: compact Laplacian, 1: the 2nd-order star"""
     b = _f(b)
     nx, ny, nz = b.shape
     x = np.zeros_like(b, order="F")
     hist = np.zeros(maxit + 1)
     rnorm = ctypes.c_double(0)
     reason = ctypes.c_int(0)
-    its = LIB.orc_cg_solve(nx, ny, nz, _dx(dx), _p(b), _p(x), rtol, abstol, maxit,
+    its = LIB.orc_cg_solve_op(op, nx, ny, nz, _dx(dx), _p(b), _p(x), rtol, abstol, maxit,
                            ctypes.byref(rnorm), ctypes.byref(reason), _p(hist), len(hist))
     return x, its, rnorm.value, reason.value, hist[: its + 1]

@@ -75,6 +75,32 @@ def test_cg_matches_oracle(n, kind, rtol):
         assert np.linalg.norm(xg - xo) <= 1e3 * rtol * np.linalg.norm(xo)
 
 
+@pytest.mark.parametrize("n,kind", [(32, "S3"), (64, "S4")])
+def test_cg_on_star_operator_matches_oracle(n, kind):
+    """the reference's solve() as it stands today: KSPCG on the shell matrix whose MatMult is the
+    2nd-order star (src/poissbox.f90:269-322)"""
+    import torch
+
+    xt, dx = manufactured(n, kind)
+    orc.set_threads(8)
+    try:
+        b = orc.star(xt, dx)
+        xo, ito, rno, reo, ho = orc.cg_solve(b, dx, rtol=1e-8, op=1)
+    finally:
+        orc.set_threads(1)
+    h = pbx.Handle(n, n, n, dx)
+    h.operator = 1
+    x, its, rn, why, hist = h.cg_solve(pbx.fortran_to_torch(b), rtol=1e-8)
+    torch.cuda.synchronize()
+    xg = pbx.torch_to_fortran(x)
+    h.close()
+    assert why == reo == 2 and abs(its - ito) <= 1, (its, ito)
+    m = min(len(hist), len(ho))
+    assert np.allclose(hist[: max(2, m // 2)], ho[: max(2, m // 2)], rtol=1e-6)
+    assert np.linalg.norm(orc.star(xg, dx) - b) <= 20e-8 * np.linalg.norm(b)
+    assert np.linalg.norm(xg - xo) <= 1e-5 * np.linalg.norm(xo)
+
+
 def test_cg_golden():
     import os
 

@@ -142,6 +142,80 @@ def test_compact_coefficients():
 
 
 # ---------------------------------------------------------------- tests/grad/test_grad_1d.f90, tests/div/test_div_1d.f90
+# ---------------------------------------------------------------- tests/coefficients/test_d2dx2.f90, test_star.f90
+F32 = lambda v: float(np.float32(v))   # the tests' parameters are default-real literals
+
+
+def _feq(val, ref, tol):
+    d = abs(val - ref)
+    return d <= tol * abs(ref) or d <= tol
+
+
+def test_d2dx2():
+    """tests/coefficients/test_d2dx2.f90: lapl_1d_coeffs on constant / linear / quadratic triples,
+    scaled, shifted and on 2 dx and dx / 2 grids, tolerance 100 eps (:183-200)"""
+    a, b, c, x, dx, shift = (F32(v) for v in (2.718, 1.414, 1.848, 1.618, 0.155, 17.29))
+    pts = np.array([x - dx, x, x + dx])
+    tol = 100 * EPS
+
+    def ev(f, h):   # :163-175
+        co = orc.lapl_1d_coeffs(h)
+        return (co[0] * f[0] + co[2] * f[2]) + co[1] * f[1]
+
+    for f, want, spacing in ((np.full(3, c), 0.0, True), (b * pts, 0.0, True), (a * pts**2, 2 * a, False)):
+        assert _feq(ev(f, dx) * dx**2, want * dx**2, tol)
+        assert _feq(ev(2 * f, dx), 2 * want, tol)
+        assert _feq(ev(f / 2, dx) * dx**2, want * dx**2 / 2, tol)
+        assert _feq(ev(f + shift, dx) * dx**2, want * dx**2, tol)
+        assert _feq(ev(f - shift, dx) * dx**2, want * dx**2, tol)
+        if spacing:
+            assert _feq(ev(f, 2 * dx) * (2 * dx) ** 2, want * (2 * dx) ** 2, tol)
+            assert _feq(ev(f, dx / 2) * (dx / 2) ** 2, want * (dx / 2) ** 2, tol)
+
+
+def test_star():
+    """tests/coefficients/test_star.f90: lapl_star_coeffs + dot_product on 3x3x3 boxes holding a
+    constant, a constant-gradient and a quadratic field; tolerance 100 * 1.1 eps (:160-169).  The
+    same boxes go through evaluate_laplacian_pointwise (src/poissbox.f90:128-148)."""
+    a, b, c, x, dx = (F32(v) for v in (2.718, 1.414, 1.848, 1.618, 0.155))
+    pts = np.array([x - dx, x, x + dx])
+    tol = 100 * (1.1 * EPS)
+
+    def box(line):   # :45-79
+        return line[:, None, None] + line[None, :, None] + line[None, None, :]
+
+    fc = np.full((3, 3, 3), c)
+    for f, want in ((fc, 0.0), (box(b * pts), 0.0), (box(a * pts**2), 3 * (2 * a))):
+        co = orc.lapl_star_coeffs(dx, dx, dx)
+        val = float(np.dot(f.reshape(-1, order="F"), co.reshape(-1, order="F")))
+        assert _feq(val * dx**2, want * dx**2, tol)
+        val = orc.evaluate_laplacian_pointwise(np.asfortranarray(f), (dx, dx, dx))
+        assert _feq(val * dx**2, want * dx**2, tol)
+    co = orc.lapl_star_coeffs(0.1, 0.2, 0.4)
+    assert np.count_nonzero(co) == 7 and co[1, 1, 1] == ((0 - 2.0 * (1 / 0.1**2)) - 2.0 * (1 / 0.2**2)) - 2.0 * (1 / 0.4**2)
+
+
+def test_star_periodic_field():
+    """compute_lapl_pointwise (src/poissbox.f90:84-126) on a periodic box: constants are in the null
+    space, a sine is an eigenfunction with eigenvalue -(4/h^2) sin^2(k h / 2) per direction, and the
+    dense 27-term dot product equals the 7-term sum"""
+    n = (12, 9, 16)
+    h = tuple(2 * np.pi / m for m in n)
+    assert np.max(np.abs(orc.star(np.full(n, 2.8170923), h))) <= 1e-10
+    xs = [(np.arange(m) + 0.5) * d for m, d in zip(n, h)]
+    f = np.sin(xs[0])[:, None, None] + np.sin(2 * xs[1])[None, :, None] + np.cos(3 * xs[2])[None, None, :]
+    lam = [-(4 / d**2) * np.sin(k * d / 2) ** 2 for k, d in zip((1, 2, 3), h)]
+    want = lam[0] * np.sin(xs[0])[:, None, None] + lam[1] * np.sin(2 * xs[1])[None, :, None] + lam[2] * np.cos(3 * xs[2])[None, None, :]
+    got = orc.star(np.asfortranarray(f), h)
+    assert np.max(np.abs(got - want)) <= 1e-11 * np.max(np.abs(want))
+    rng = np.random.default_rng(2)
+    g = np.asfortranarray(rng.uniform(-1, 1, n))
+    cx, cy, cz = (1 / d**2 for d in h)
+    seven = (cx * (np.roll(g, 1, 0) + np.roll(g, -1, 0)) + cy * (np.roll(g, 1, 1) + np.roll(g, -1, 1))
+             + cz * (np.roll(g, 1, 2) + np.roll(g, -1, 2)) - 2 * (cx + cy + cz) * g)
+    assert np.max(np.abs(orc.star(g, h) - seven)) <= 1e-12 * np.max(np.abs(seven))
+
+
 def test_grad_1d_interp_1d():
     """tests/grad/test_grad_1d.f90:53-134 (n = 128, L = 2 pi)"""
     n = 128

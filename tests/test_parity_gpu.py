@@ -293,6 +293,42 @@ def test_grad_div_3d_kat():
     assert np.sqrt(np.mean((cs.div(F, [dx] * 3) - expect) ** 2)) <= 1e-9
 
 
+# ------------------------------------------------------------------------------------ 2nd-order star
+@pytest.mark.parametrize("shape", [(64, 64, 64), (12, 9, 7), (3, 3, 3), (100, 37, 65), (256, 16, 48)])
+def test_star_bit_exact(shape):
+    """compute_lapl_pointwise (src/poissbox.f90:84-148), the operator mfmult applies today:
+    bit-identical to the oracle through the compute_lapl mirror"""
+    from poissbox_b200 import compute_lapl
+
+    rng = np.random.default_rng(77)
+    x = np.asfortranarray(rng.uniform(-1, 1, shape))
+    dx = (0.13, 0.29 / shape[1], 1.7)
+    assert np.array_equal(compute_lapl.compute_lapl_pointwise(x, dx), orc.star(x, dx))
+
+
+def test_star_kat_and_matmult_operator():
+    """test_star.f90's fields on a periodic grid (constant -> 0, eigenfunctions), and the shell
+    matrix switching between the two operators"""
+    import torch
+
+    n = 64
+    h_ = 2 * np.pi / n
+    c = (np.arange(n) + 0.5) * h_
+    from poissbox_b200 import compute_lapl
+
+    assert np.max(np.abs(compute_lapl.compute_lapl_pointwise(np.full((n, n, n), 1.848), [h_] * 3))) <= 1e-9
+    f = np.sin(c)[:, None, None] + np.sin(c)[None, :, None] + np.sin(c)[None, None, :]
+    lam = -(4 / h_**2) * np.sin(h_ / 2) ** 2
+    assert np.max(np.abs(compute_lapl.compute_lapl_pointwise(f, [h_] * 3) - lam * f)) <= 1e-10
+    h = pbx.Handle(n, n, n, (h_,) * 3)
+    t = pbx.fortran_to_torch(f)
+    assert torch.equal(h.mult(t), h.lapl(t))
+    h.operator = 1
+    assert torch.equal(h.mult(t), h.star(t))
+    assert np.array_equal(pbx.torch_to_fortran(h.star(t)), orc.star(np.asfortranarray(f), [h_] * 3))
+    h.close()
+
+
 # ------------------------------------------------------------------------------------ full-size properties
 def test_lapl_full_size_properties():
     """256^3 (BASELINE configs[2]) device-resident: agreement of the two schedules, constants in
