@@ -220,6 +220,21 @@ int pbx_bwd_sweep_batch_device(int n, long long nlines, long long elem_stride,
 int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, double abstol,
                         int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist);
 
+/* Preconditioner of the CG.  The reference gives KSP the assembled 2nd-order star
+ * as the preconditioning matrix (KSPSetOperators(ksp, A, P), src/poissbox.f90:294) and its README
+ * runs `-pc_type gamg`: a multigrid preconditioner built on P.  PBX_PC_MG fills that role with a
+ * geometric V(nu, nu) cycle on the same star (damped Jacobi, cell-centred trilinear transfer,
+ * symmetric positive definite; pbx_mg.cu).  It is not PETSc's GAMG: iteration counts are its own.
+ * KSPCG semantics with a preconditioner: z = M^-1 r with the constant removed, preconditioned norm
+ * ||z||, beta = z.r, KSP_DIVERGED_INDEFINITE_PC (-8) if beta < 0.  Single rank only.
+ *   pbx_set_pc(h, PBX_PC_NONE, 0)  (default)   |   pbx_set_pc(h, PBX_PC_MG, nu)  nu = 0 -> 2
+ *   pbx_pc_apply_device            z = M^-1 (r - mean r), mean-free: one application, for tests */
+#define PBX_PC_NONE 0
+#define PBX_PC_MG 1
+#define PBX_DIVERGED_INDEFINITE_PC (-8)
+int pbx_set_pc(pbx_handle h, int pc, int nu);
+int pbx_pc_apply_device(pbx_handle h, const double *r, double *z);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-pointer convenience variants (what the Fortran module bodies call).
  * They use a cached handle for (nx,ny,nz,dx) on the current device, copy in, run, copy out.

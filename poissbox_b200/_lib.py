@@ -20,6 +20,7 @@ PBX_ERR_SIZE = 7
 MODE_FAST, MODE_REFERENCE = 0, 1
 OP_GRAD, OP_DIV, OP_INTERP, OP_INTERP_DIV, OP_STAR = 1, 2, 3, 4, 5
 OPERATOR_COMPACT, OPERATOR_STAR = 0, 1
+PC_NONE, PC_MG = 0, 1
 
 # every symbol include/pbx.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -65,6 +66,8 @@ SIGNATURES = {
     "pbx_fwd_sweep_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbx_bwd_sweep_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbx_cg_solve_device": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, _ip, _dp, _ip, _dp, c_int]),
+    "pbx_set_pc": (c_int, [c_void_p, c_int, c_int]),
+    "pbx_pc_apply_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp, c_int]),
     "pbx_grad_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp]),
     "pbx_div_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp]),

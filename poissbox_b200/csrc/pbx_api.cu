@@ -381,6 +381,7 @@ int pbx_destroy(pbx_handle h)
         for (int k = 0; k < 2; ++k) free_ref_tables(&h->ref[d][k]);
     for (int i = 0; i < h->nscratch; ++i) cudaFree(h->scratch[i]);
     cg_free(h);
+    mg_free(h);
     dist_free(h);
     delete h;
     return PBX_OK;
@@ -536,6 +537,28 @@ int pbx_matmult_device(pbx_handle h, const double *x, double *y)
     if (!h || !x || !y || x == y) return PBX_ERR_ARG;
     PBX_CUDA(cudaSetDevice(h->device));
     return matmult(h, x, y);
+}
+
+int pbx_set_pc(pbx_handle h, int pc, int nu)
+{
+    if (!h || (pc != PBX_PC_NONE && pc != PBX_PC_MG) || nu < 0) return PBX_ERR_ARG;
+    if (pc == PBX_PC_MG) {
+        if (h->nranks > 1) {
+            set_last_error("the multigrid preconditioner is single-rank");
+            return PBX_ERR_UNSUPPORTED;
+        }
+        PBX_CUDA(cudaSetDevice(h->device));
+        PBX_TRY(mg_setup(h, nu == 0 ? 2 : nu));
+    }
+    h->pc = pc;
+    return PBX_OK;
+}
+
+int pbx_pc_apply_device(pbx_handle h, const double *r, double *z)
+{
+    if (!h || !r || !z || r == z) return PBX_ERR_ARG;
+    PBX_CUDA(cudaSetDevice(h->device));
+    return pc_apply(h, r, z);
 }
 
 int pbx_star_device(pbx_handle h, const double *x, double *y)

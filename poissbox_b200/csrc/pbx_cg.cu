@@ -29,7 +29,9 @@ namespace {
 
 enum {
     SC_M0 = 0, SC_S1, SC_S2, SC_PW, SC_BETA, SC_BETAOLD, SC_A, SC_B, SC_DP, SC_DP0, SC_TTOL,
-    SC_PWOLD, SC_STATUS, SC_IT, SC_RTOL, SC_ABSTOL, SC_MEAN, SC_MAXIT, SC_NTOT, SC_COUNT
+    SC_PWOLD, SC_STATUS, SC_IT, SC_RTOL, SC_ABSTOL, SC_MEAN, SC_MAXIT, SC_NTOT,
+    // preconditioned CG: sums of z, z^2, z (r - m0), (r - m0) (contiguous: one reduction), mean of z
+    SC_SZ, SC_SZZ, SC_SZR, SC_SR, SC_MZ, SC_COUNT
 };
 
 constexpr int VT = 256;
@@ -182,20 +184,133 @@ k_reduce(const double *__restrict__ part, int cnt, int stride, int narr, double 
     }
 }
 
+// preconditioned CG: partial sums of z, z^2, z (r - m0), (r - m0) into four arrays `np` apart
+__global__ void __launch_bounds__(VT)
+k_pcdots(size_t N, const double *__restrict__ z, const double *__restrict__ r,
+         const double *__restrict__ sc, double *__restrict__ part, int np)
+{
+    __shared__ double sh[VT / 32];
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    const double m0 = sc[SC_M0];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += VT) {
+        const double zv = z[i], t = r[i] - m0;
+        a0 += zv;
+        a1 = fma(zv, zv, a1);
+        a2 = fma(zv, t, a2);
+        a3 += t;
+    }
+    a0 = block_sum(a0, sh);
+    a1 = block_sum(a1, sh);
+    a2 = block_sum(a2, sh);
+    a3 = block_sum(a3, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = a0;
+        part[np + blockIdx.x] = a1;
+        part[2 * np + blockIdx.x] = a2;
+        part[3 * np + blockIdx.x] = a3;
+    }
+}
+
+// p = (z - mean z) + b p   (b = 0 on the first iteration)
+__global__ void __launch_bounds__(VT)
+k_pupdate_pc(size_t N, const double *__restrict__ z, double *__restrict__ p,
+             const double *__restrict__ sc)
+{
+    if (sc[SC_STATUS] != 0.0) return;
+    const double m = sc[SC_MZ], b = sc[SC_B];
+    size_t i = (size_t)blockIdx.x * VT + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * VT;
+    for (; i < N; i += st) p[i] = b == 0.0 ? z[i] - m : fma(b, p[i], z[i] - m);
+}
+
+// v -= *m
+__global__ void __launch_bounds__(VT)
+k_center(size_t N, double *__restrict__ v, const double *__restrict__ m)
+{
+    const double mm = *m;
+    size_t i = (size_t)blockIdx.x * VT + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * VT;
+    for (; i < N; i += st) v[i] -= mm;
+}
+
+// r = b ; x = 0 (preconditioned CG: p comes from the first preconditioner application)
+__global__ void __launch_bounds__(VT)
+k_init_pc(size_t N, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r)
+{
+    size_t i = (size_t)blockIdx.x * VT + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * VT;
+    for (; i < N; i += st) {
+        x[i] = 0.0;
+        r[i] = b[i];
+    }
+}
+
 // the scalar logic of the KSPCG loop; one thread
 //   phase 0: m0 = S1 / N                     (S1 = sum b)
 //   phase 1: initial residual norm / test    (S1, S2 about m0)
 //   phase 2: a = beta / (p.w), indefiniteness test
 //   phase 3: new residual norm, test, b = beta/beta_old
+// with a preconditioner (z = M^-1 r, sums SC_SZ .. SC_SR of z, z^2, z (r - m0), r - m0):
+//   phase 4: first application: mean of z, ||z||, beta = z.r, test
+//   phase 5: mean of the updated residual (S1 about m0), the right-hand side's mean for the next PC
+//   phase 6: as phase 4 after an iteration: counts it, b = beta/beta_old, tests
+//   phase 7 / 8: SC_MEAN / SC_MZ = S1 / N (stand-alone preconditioner application)
 __global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double N = sc[SC_NTOT];
     if (phase == 0) {
         sc[SC_M0] = sc[SC_S1] / N;
+        sc[SC_MEAN] = sc[SC_M0];
+        return;
+    }
+    if (phase == 7 || phase == 8) {
+        sc[phase == 7 ? SC_MEAN : SC_MZ] = sc[SC_S1] / N;
         return;
     }
     if (sc[SC_STATUS] != 0.0) return;
+    if (phase == 5) {
+        sc[SC_MEAN] = sc[SC_M0] + sc[SC_S1] / N;
+        return;
+    }
+    if (phase == 4 || phase == 6) {
+        const double mz = sc[SC_SZ] / N;
+        double zz = sc[SC_SZZ] - sc[SC_SZ] * mz;
+        if (zz < 0.0) zz = 0.0;
+        const double dp = sqrt(zz);
+        const double beta = sc[SC_SZR] - mz * sc[SC_SR];   // (z - mz) . r
+        sc[SC_MZ] = mz;
+        sc[SC_DP] = dp;
+        int it = (int)sc[SC_IT];
+        if (phase == 4) {
+            sc[SC_DP0] = dp;
+            sc[SC_TTOL] = fmax(sc[SC_RTOL] * dp, sc[SC_ABSTOL]);
+            sc[SC_BETA] = beta;
+            sc[SC_B] = 0.0;
+            sc[SC_PWOLD] = 0.0;
+            if (hist && nhist > 0) hist[0] = dp;
+        } else {
+            it += 1;
+            sc[SC_IT] = it;
+            sc[SC_BETAOLD] = sc[SC_BETA];
+            sc[SC_BETA] = beta;
+            sc[SC_B] = beta / sc[SC_BETAOLD];
+            if (hist && it < nhist) hist[it] = dp;
+        }
+        if (dp != dp || beta != beta)
+            sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
+        else if (dp <= sc[SC_TTOL])
+            sc[SC_STATUS] = dp < sc[SC_ABSTOL] ? PBX_CONVERGED_ATOL : PBX_CONVERGED_RTOL;
+        else if (beta < 0.0)
+            sc[SC_STATUS] = PBX_DIVERGED_INDEFINITE_PC;
+        else if (phase == 6 && dp >= 1.0e4 * sc[SC_DP0])
+            sc[SC_STATUS] = PBX_DIVERGED_DTOL;
+        else if (phase == 6 && it >= (int)sc[SC_MAXIT])
+            sc[SC_STATUS] = PBX_DIVERGED_ITS;
+        return;
+    }
     if (phase == 2) {
         const double dpi = sc[SC_PW], dpiold = sc[SC_PWOLD];
         const int i = (int)sc[SC_IT];
@@ -274,10 +389,11 @@ int cg_alloc(pbx_handle_s *h, int maxit)
             if (nz > np) np = nz;
         }
         h->cg_npartials = np;
-        PBX_CUDA(cudaMalloc(&h->cg_partials, 2 * (size_t)np * sizeof(double)));
+        PBX_CUDA(cudaMalloc(&h->cg_partials, 4 * (size_t)np * sizeof(double)));
         PBX_CUDA(cudaMalloc(&h->cg_scal, SC_COUNT * sizeof(double)));
         PBX_CUDA(cudaMallocHost(&h->cg_host, 2 * SC_COUNT * sizeof(double)));
     }
+    if (h->pc != PBX_PC_NONE && !h->cg_z) PBX_CUDA(cudaMalloc(&h->cg_z, N * sizeof(double)));
     if (h->cg_hist_cap < maxit + 1) {
         if (h->cg_hist) cudaFree(h->cg_hist);
         h->cg_hist = nullptr;
@@ -339,7 +455,8 @@ void cg_free(pbx_handle_s *h)
     if (h->cg_scal) cudaFree(h->cg_scal);
     if (h->cg_host) cudaFreeHost(h->cg_host);
     if (h->cg_hist) cudaFree(h->cg_hist);
-    h->cg_r = h->cg_p = h->cg_w = h->cg_partials = h->cg_scal = h->cg_host = h->cg_hist = nullptr;
+    if (h->cg_z) cudaFree(h->cg_z);
+    h->cg_r = h->cg_p = h->cg_w = h->cg_partials = h->cg_scal = h->cg_host = h->cg_hist = h->cg_z = nullptr;
     h->cg_hist_cap = 0;
 }
 
@@ -351,9 +468,136 @@ int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev)
     return PBX_OK;
 }
 
+// z = M^-1 (r - *mean) for the handle's preconditioner (no mean removal of z)
+static int pc_raw(pbx_handle_s *h, const double *r, const double *mean_dev, double *z)
+{
+    if (h->pc == PBX_PC_MG) return mg_vcycle(h, r, mean_dev, z);
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    PBX_CUDA(cudaMemcpyAsync(z, r, N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    k_center<<<vec_grid(N), VT, 0, h->stream>>>(N, z, mean_dev);
+    ++h->launches;
+    return PBX_OK;
+}
+
+int pc_apply(pbx_handle_s *h, const double *r, double *z)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    PBX_TRY(cg_alloc(h, 1));
+    cudaStream_t s = h->stream;
+    double *sc = h->cg_scal, *part = h->cg_partials;
+    const int np = h->cg_npartials, nb = vec_grid(N);
+    const double ntot = (double)N;
+    PBX_CUDA(cudaMemcpyAsync(sc + SC_NTOT, &ntot, sizeof ntot, cudaMemcpyHostToDevice, s));
+    k_sum<<<nb, VT, 0, s>>>(N, r, part);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
+    k_scalar<<<1, 1, 0, s>>>(sc, 7, nullptr, 0);
+    h->launches += 3;
+    PBX_TRY(pc_raw(h, r, sc + SC_MEAN, z));
+    k_sum<<<nb, VT, 0, s>>>(N, z, part);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
+    k_scalar<<<1, 1, 0, s>>>(sc, 8, nullptr, 0);
+    k_center<<<nb, VT, 0, s>>>(N, z, sc + SC_MZ);
+    h->launches += 4;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+// KSPCG with a preconditioner: z = M^-1 r (constant removed), preconditioned norm, beta = z.r
+static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol,
+                       int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist)
+{
+    const size_t N = (size_t)h->nx * h->ny * h->nz;
+    if (h->nranks > 1) {
+        set_last_error("the preconditioned CG is single-rank");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    PBX_TRY(cg_alloc(h, maxit));
+    cudaStream_t s = h->stream;
+    double *sc = h->cg_scal, *part = h->cg_partials;
+    const int np = h->cg_npartials, nb = vec_grid(N);
+    double *r = h->cg_r, *p = h->cg_p, *w = h->cg_w, *z = h->cg_z;
+
+    double init[SC_COUNT];
+    for (int i = 0; i < SC_COUNT; ++i) init[i] = 0.0;
+    init[SC_RTOL] = rtol;
+    init[SC_ABSTOL] = abstol;
+    init[SC_MAXIT] = (double)maxit;
+    init[SC_NTOT] = (double)N;
+    PBX_CUDA(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, s));
+    k_sum<<<nb, VT, 0, s>>>(N, b, part);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
+    k_scalar<<<1, 1, 0, s>>>(sc, 0, nullptr, 0);        // m0 = mean(b) = mean(r) from here on
+    k_init_pc<<<nb, VT, 0, s>>>(N, b, x, r);
+    h->launches += 4;
+    PBX_TRY(pc_raw(h, r, sc + SC_MEAN, z));
+    k_pcdots<<<nb, VT, 0, s>>>(N, z, r, sc, part, np);
+    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 4, sc + SC_SZ, sc, 0);
+    k_scalar<<<1, 1, 0, s>>>(sc, 4, h->cg_hist, h->cg_hist_cap);
+    k_pupdate_pc<<<nb, VT, 0, s>>>(N, z, p, sc);
+    h->launches += 4;
+    PBX_CUDA(cudaGetLastError());
+
+    cudaEvent_t ev[2];
+    PBX_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    PBX_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    double *hs = h->cg_host;
+    PBX_CUDA(cudaMemcpyAsync(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PBX_CUDA(cudaStreamSynchronize(s));
+    int rc = PBX_OK;
+    bool done = hs[SC_STATUS] != 0.0;
+    int issued = 0;
+    while (!done && issued < maxit) {
+        const int slot = issued & 1;
+        if ((rc = matmult_dot(h, p, w, sc + SC_PW, 1)) != PBX_OK) break;
+        k_scalar<<<1, 1, 0, s>>>(sc, 2, nullptr, 0);
+        k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
+        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 1);
+        k_scalar<<<1, 1, 0, s>>>(sc, 5, nullptr, 0);
+        h->launches += 4;
+        if ((rc = pc_raw(h, r, sc + SC_MEAN, z)) != PBX_OK) break;
+        k_pcdots<<<nb, VT, 0, s>>>(N, z, r, sc, part, np);
+        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 4, sc + SC_SZ, sc, 1);
+        k_scalar<<<1, 1, 0, s>>>(sc, 6, h->cg_hist, h->cg_hist_cap);
+        k_pupdate_pc<<<nb, VT, 0, s>>>(N, z, p, sc);
+        h->launches += 4;
+        cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(ev[slot], s);
+        ++issued;
+        if (issued >= 2) {
+            cudaEventSynchronize(ev[slot ^ 1]);
+            if (hs[(slot ^ 1) * SC_COUNT + SC_STATUS] != 0.0) done = true;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc != PBX_OK) return rc;
+    PBX_CUDA(e);
+    PBX_CUDA(cudaMemcpy(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost));
+    int st = (int)hs[SC_STATUS];
+    const int nit = (int)hs[SC_IT];
+    if (st == 0) st = PBX_DIVERGED_ITS;
+    if (its) *its = nit;
+    if (rnorm) *rnorm = hs[SC_DP];
+    if (reason) *reason = st;
+    if (hist && nhist > 0) {
+        const int cnt = nit + 1 < nhist ? nit + 1 : nhist;
+        PBX_CUDA(cudaMemcpy(hist, h->cg_hist, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
 int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double abstol, int maxit,
              int *its, double *rnorm, int *reason, double *hist, int nhist)
 {
+    if (h->pc != PBX_PC_NONE) {
+        if (((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) != 0) {
+            set_last_error("pbx_cg_solve: b and x must be 16-byte aligned");
+            return PBX_ERR_ARG;
+        }
+        return cg_solve_pc(h, b, x, rtol, abstol, maxit, its, rnorm, reason, hist, nhist);
+    }
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     if (((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) != 0) {
         set_last_error("pbx_cg_solve: b and x must be 16-byte aligned");

@@ -254,6 +254,11 @@ struct pbx_handle_s {
 
     // z-slab decomposition (pbx_dist.cu)
     void *dist = nullptr;
+
+    // preconditioner of the CG (pbx_mg.cu): PBX_PC_NONE or PBX_PC_MG
+    int pc = PBX_PC_NONE;
+    void *mg = nullptr;
+    double *cg_z = nullptr;          // preconditioned residual (allocated when a PC is set)
 };
 
 namespace pbx {
@@ -267,6 +272,12 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
 int grad_stages_run(pbx_handle_s *h, const double *f, double *df, bool fast);
 int div_stages_run(pbx_handle_s *h, const double *f, double *out, bool fast);
 int interp_stages_run(pbx_handle_s *h, const double *f, double *fi, int stagger, bool fast);
+// multigrid V-cycle on the star (pbx_mg.cu): z = M^-1 (r - *mean)
+int mg_setup(pbx_handle_s *h, int nu);
+int mg_vcycle(pbx_handle_s *h, const double *r, const double *mean, double *z);
+void mg_free(pbx_handle_s *h);
+// z = M^-1 (r - mean(r)) for the handle's preconditioner, mean removed from z (pbx_cg.cu)
+int pc_apply(pbx_handle_s *h, const double *r, double *z);
 // 2nd-order star (pbx_star.cu); lo / up: neighbour planes of a slab (nullptr: periodic in z)
 int star_apply(pbx_handle_s *h, const double *x, double *y, const double *lo, const double *up);
 // y = A x for the handle's operator, whatever the decomposition (pbx_api.cu)

@@ -1,0 +1,297 @@
+// pbx_mg.cu -- geometric multigrid V-cycle on the 2nd-order 7-point star, as the preconditioner
+// of the conjugate-gradient solve.
+//
+// What it stands in for: the reference hands KSP two matrices, the shell operator A and the
+// assembled 2nd-order star P (KSPSetOperators(ksp, A, P), src/poissbox.f90:294; P from
+// assemble_laplacian, src/coefficients.f90:52-123), and its README runs the solve with
+// `-pc_type gamg`, i.e. a multigrid preconditioner built on P.  PETSc's GAMG is third-party
+// (algebraic, version unpinned, absent here): this is NOT a restatement of it -- parity is
+// unpinned by construction -- but the same role filled with a geometric V-cycle on the same P:
+//   S = -P (symmetric positive semi-definite, constant null space), periodic, cell-centred;
+//   smoother: nu damped-Jacobi sweeps before and after (omega = 6/7, the optimum for the 3-D star);
+//   transfer: cell-centred trilinear prolongation Pr (weights 3/4, 1/4 per direction) and
+//             restriction R = Pr^T / 8 (weights 1/8, 3/8, 3/8, 1/8), so the cycle is a symmetric
+//             positive definite operator on the zero-mean subspace, as CG requires;
+//   coarse operators by re-discretisation (spacing doubles); the coarsest grid (a side <= 4 or
+//   odd) gets a fixed number of Jacobi sweeps from a zero guess (again a symmetric polynomial in S).
+// The CG removes the constant from the result (MatNullSpace semantics); the mean of the right-hand
+// side is removed on entry (it is the invariant mean of b).
+//
+// Every kernel is a bandwidth-bound stencil / transfer sweep in the structure of pbx_star.cu
+// (a thread owns an (i,j) column of a block of planes, z neighbours in registers, in-plane
+// neighbours out of L1).  Per V(2,2) cycle the finest level moves about 110 B/DoF, all levels 8/7
+// of that.
+#include <vector>
+
+#include "pbx_internal.h"
+
+namespace pbx {
+
+namespace {
+
+constexpr int MBX = 32, MBY = 8, MKZ = 32;
+constexpr double MG_OMEGA = 6.0 / 7.0;
+constexpr int MG_COARSE_SWEEPS = 30;
+
+struct Lv {
+    int nx, ny, nz;
+    double cx, cy, cz;   // 1 / h^2 per direction
+    double wd;           // omega / diag(S)
+};
+
+// MODE 0: out = z + wd ((r - m) - S z)      damped Jacobi
+// MODE 1: out = (r - m) - S z               residual
+template <int MODE>
+__global__ void __launch_bounds__(MBX * MBY)
+mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
+                const double *__restrict__ r, const double *__restrict__ mean,
+                double *__restrict__ out)
+{
+    const int nx = lv.nx, ny = lv.ny, nz = lv.nz;
+    const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    const double m = mean ? *mean : 0.0;
+    const int k0 = blockIdx.z * MKZ, k1 = k0 + MKZ < nz ? k0 + MKZ : nz;
+    const size_t plane = (size_t)nx * ny;
+    const size_t col = i + (size_t)nx * j;
+    const size_t im = (i == 0 ? nx - 1 : i - 1) + (size_t)nx * j, ip = (i == nx - 1 ? 0 : i + 1) + (size_t)nx * j;
+    const size_t jm = i + (size_t)nx * (j == 0 ? ny - 1 : j - 1), jp = i + (size_t)nx * (j == ny - 1 ? 0 : j + 1);
+    double below = z[col + plane * (k0 > 0 ? k0 - 1 : nz - 1)];
+    double centre = z[col + plane * k0];
+    for (int k = k0; k < k1; ++k) {
+        const size_t pk = plane * k;
+        const double above = z[col + (k + 1 < nz ? pk + plane : 0)];
+        const double c2 = 2.0 * centre;
+        double sz = lv.cx * (c2 - __ldg(z + pk + im) - __ldg(z + pk + ip));
+        sz = fma(lv.cy, c2 - __ldg(z + pk + jm) - __ldg(z + pk + jp), sz);
+        sz = fma(lv.cz, c2 - below - above, sz);
+        const double res = (r[col + pk] - m) - sz;
+        out[col + pk] = MODE == 0 ? fma(lv.wd, res, centre) : res;
+        below = centre;
+        centre = above;
+    }
+}
+
+// out = wd (r - m): the first Jacobi sweep from a zero guess
+__global__ void __launch_bounds__(256)
+mg_scale_kernel(size_t n, double wd, const double *__restrict__ r, const double *__restrict__ mean,
+                double *__restrict__ out)
+{
+    const double m = mean ? *mean : 0.0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) out[i] = wd * (r[i] - m);
+}
+
+// coarse(I,J,K) = sum over the 4x4x4 fine cells 2I-1 .. 2I+2 (periodic) with weights
+// (1/8, 3/8, 3/8, 1/8) per direction.  lv = the FINE level; one thread per coarse cell.
+__global__ void __launch_bounds__(256)
+mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fine,
+                   double *__restrict__ coarse)
+{
+    const int cnx = lv.nx / 2, cny = lv.ny / 2, cnz = lv.nz / 2;
+    const size_t nc = (size_t)cnx * cny * cnz;
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nc) return;
+    const int I = (int)(q % cnx), J = (int)((q / cnx) % cny), K = (int)(q / ((size_t)cnx * cny));
+    const double w[4] = {0.125, 0.375, 0.375, 0.125};
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int k = 2 * K - 1 + c;
+        k = k < 0 ? k + lv.nz : (k >= lv.nz ? k - lv.nz : k);
+        double sk = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int j = 2 * J - 1 + b;
+            j = j < 0 ? j + lv.ny : (j >= lv.ny ? j - lv.ny : j);
+            const double *row = fine + (size_t)lv.nx * (j + (size_t)lv.ny * k);
+            const int i0 = 2 * I;
+            const double f0 = __ldg(row + (i0 == 0 ? lv.nx - 1 : i0 - 1)), f1 = __ldg(row + i0),
+                         f2 = __ldg(row + i0 + 1), f3 = __ldg(row + (i0 + 2 >= lv.nx ? 0 : i0 + 2));
+            sk = fma(w[b], fma(w[0], f0 + f3, w[1] * (f1 + f2)), sk);
+        }
+        s = fma(w[c], sk, s);
+    }
+    coarse[q] = s;
+}
+
+// fine += Pr coarse: fine cell 2I takes 3/4 c(I) + 1/4 c(I-1), cell 2I+1 takes 3/4 c(I) + 1/4 c(I+1),
+// per direction.  lv = the FINE level; one thread per fine cell.
+__global__ void __launch_bounds__(256)
+mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coarse,
+                  double *__restrict__ fine)
+{
+    const size_t n = (size_t)lv.nx * lv.ny * lv.nz;
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int cnx = lv.nx / 2, cny = lv.ny / 2, cnz = lv.nz / 2;
+    const int i = (int)(q % lv.nx), j = (int)((q / lv.nx) % lv.ny), k = (int)(q / ((size_t)lv.nx * lv.ny));
+    auto nb = [](int f, int cn, int &a, int &b) {   // a: the parent (3/4), b: the other one (1/4)
+        a = f >> 1;
+        b = (f & 1) ? (a + 1 == cn ? 0 : a + 1) : (a == 0 ? cn - 1 : a - 1);
+    };
+    int ia, ib, ja, jb, ka, kb;
+    nb(i, cnx, ia, ib);
+    nb(j, cny, ja, jb);
+    nb(k, cnz, ka, kb);
+    auto at = [&](int I, int J, int K) { return __ldg(coarse + I + (size_t)cnx * (J + (size_t)cny * K)); };
+    auto linex = [&](int J, int K) { return fma(0.25, at(ib, J, K), 0.75 * at(ia, J, K)); };
+    auto planey = [&](int K) { return fma(0.25, linex(jb, K), 0.75 * linex(ja, K)); };
+    fine[q] += fma(0.25, planey(kb), 0.75 * planey(ka));
+}
+
+}  // namespace
+
+struct MgLevel {
+    Lv lv;
+    double *r = nullptr, *z = nullptr, *t = nullptr;   // right-hand side, iterate, spare
+    size_t n = 0;
+};
+
+struct MgState {
+    std::vector<MgLevel> lev;   // lev[0] = the finest grid (r and z are the caller's arrays)
+    int nu = 2;
+};
+
+namespace {
+
+int sweep(pbx_handle_s *h, int mode, const Lv &lv, const double *z, const double *r, const double *mean,
+          double *out)
+{
+    dim3 block(MBX, MBY), grid((lv.nx + MBX - 1) / MBX, (lv.ny + MBY - 1) / MBY, (lv.nz + MKZ - 1) / MKZ);
+    if (mode == 0)
+        mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+    else
+        mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+    ++h->launches;
+    return PBX_OK;
+}
+
+unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
+
+// `count` Jacobi sweeps on S z = r - mean from a zero guess; the result ends in *cur (the spare in *alt)
+int smooth_from_zero(pbx_handle_s *h, const MgLevel &L, const double *r, const double *mean, int count,
+                     double **cur, double **alt)
+{
+    unsigned nb = blocks_for(L.n);
+    if (nb > 148 * 16) nb = 148 * 16;
+    mg_scale_kernel<<<nb, 256, 0, h->stream>>>(L.n, L.lv.wd, r, mean, *cur);
+    ++h->launches;
+    for (int s = 1; s < count; ++s) {
+        PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt));
+        std::swap(*cur, *alt);
+    }
+    return PBX_OK;
+}
+
+}  // namespace
+
+void mg_free(pbx_handle_s *h)
+{
+    MgState *m = (MgState *)h->mg;
+    if (!m) return;
+    for (size_t l = 0; l < m->lev.size(); ++l) {
+        if (l > 0) {
+            cudaFree(m->lev[l].r);
+            cudaFree(m->lev[l].z);
+        }
+        cudaFree(m->lev[l].t);
+    }
+    delete m;
+    h->mg = nullptr;
+}
+
+int mg_setup(pbx_handle_s *h, int nu)
+{
+    if (nu < 1 || nu > 8) return PBX_ERR_ARG;
+    if (h->mg) {
+        ((MgState *)h->mg)->nu = nu;
+        return PBX_OK;
+    }
+    MgState *m = new MgState();
+    m->nu = nu;
+    h->mg = m;
+    int n[3] = {h->nx, h->ny, h->nz};
+    double hh[3] = {h->dx[0], h->dx[1], h->dx[2]};
+    for (int l = 0;; ++l) {
+        MgLevel L;
+        L.lv.nx = n[0];
+        L.lv.ny = n[1];
+        L.lv.nz = n[2];
+        L.lv.cx = 1.0 / (hh[0] * hh[0]);
+        L.lv.cy = 1.0 / (hh[1] * hh[1]);
+        L.lv.cz = 1.0 / (hh[2] * hh[2]);
+        L.lv.wd = MG_OMEGA / (2.0 * (L.lv.cx + L.lv.cy + L.lv.cz));
+        L.n = (size_t)n[0] * n[1] * n[2];
+        m->lev.push_back(L);
+        MgLevel &R = m->lev.back();
+        if (cudaMalloc(&R.t, L.n * sizeof(double)) != cudaSuccess ||
+            (l > 0 && (cudaMalloc(&R.r, L.n * sizeof(double)) != cudaSuccess ||
+                       cudaMalloc(&R.z, L.n * sizeof(double)) != cudaSuccess))) {
+            cudaGetLastError();
+            mg_free(h);
+            set_last_error("multigrid hierarchy allocation failed");
+            return PBX_ERR_NOMEM;
+        }
+        const bool coarsest = n[0] <= 4 || n[1] <= 4 || n[2] <= 4 || (n[0] & 1) || (n[1] & 1) || (n[2] & 1);
+        if (coarsest) break;
+        for (int d = 0; d < 3; ++d) {
+            n[d] /= 2;
+            hh[d] *= 2.0;
+        }
+    }
+    return PBX_OK;
+}
+
+// z = M^-1 (r - mean): one V(nu, nu) cycle on S = -P.  mean: device scalar (may be nullptr = 0).
+int mg_vcycle(pbx_handle_s *h, const double *r, const double *mean, double *z)
+{
+    MgState *m = (MgState *)h->mg;
+    if (!m) return PBX_ERR_ARG;
+    const int nl = (int)m->lev.size(), nu = m->nu;
+    m->lev[0].r = const_cast<double *>(r);
+    m->lev[0].z = z;
+    std::vector<double *> cur(nl), alt(nl);
+    // downward leg
+    for (int l = 0; l < nl; ++l) {
+        MgLevel &L = m->lev[l];
+        const double *mp = l == 0 ? mean : nullptr;
+        if (l == nl - 1) {
+            // coarsest grid: a fixed number of sweeps, ending in L.z
+            cur[l] = (MG_COARSE_SWEEPS & 1) ? L.z : L.t;
+            alt[l] = (MG_COARSE_SWEEPS & 1) ? L.t : L.z;
+            PBX_TRY(smooth_from_zero(h, L, L.r, mp, MG_COARSE_SWEEPS, &cur[l], &alt[l]));
+            break;
+        }
+        // nu pre-sweeps (the first from the zero guess) + nu post-sweeps = 2 nu - 1 buffer swaps: start
+        // in the spare so that the result ends in L.z
+        cur[l] = L.t;
+        alt[l] = L.z;
+        PBX_TRY(smooth_from_zero(h, L, L.r, mp, nu, &cur[l], &alt[l]));
+        PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l]));          // residual into the spare
+        MgLevel &C = m->lev[l + 1];
+        mg_restrict_kernel<<<blocks_for(C.n), 256, 0, h->stream>>>(L.lv, alt[l], C.r);
+        ++h->launches;
+    }
+    // upward leg
+    for (int l = nl - 2; l >= 0; --l) {
+        MgLevel &L = m->lev[l];
+        const double *mp = l == 0 ? mean : nullptr;
+        mg_prolong_kernel<<<blocks_for(L.n), 256, 0, h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
+        ++h->launches;
+        for (int s = 0; s < nu; ++s) {
+            PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l]));
+            std::swap(cur[l], alt[l]);
+        }
+        if (cur[l] != L.z) {
+            set_last_error("multigrid buffer parity broken");
+            return PBX_ERR_ARG;
+        }
+    }
+    m->lev[0].r = m->lev[0].z = nullptr;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+}  // namespace pbx

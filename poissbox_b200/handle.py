@@ -180,6 +180,16 @@ class Handle:
         check(LIB.pbx_interp_device(self._h, self._field(f), self._field(out), int(stagger)))
         return out
 
+    def set_pc(self, pc, nu=0):
+        """preconditioner of cg_solve: _lib.PC_NONE (default) or _lib.PC_MG, a V(nu, nu) multigrid
+        cycle on the 2nd-order star (the role of `-pc_type gamg` on P, src/poissbox.f90:294)"""
+        check(LIB.pbx_set_pc(self._h, int(pc), int(nu)))
+
+    def pc_apply(self, r, z=None):
+        z = self.empty() if z is None else z
+        check(LIB.pbx_pc_apply_device(self._h, self._field(r), self._field(z)))
+        return z
+
     # -- solve ----------------------------------------------------------------------------------
     def cg_solve(self, b, x=None, rtol=1e-5, abstol=1e-50, maxit=10000):
         """KSPSolve with -ksp_type cg -pc_type none (src/poissbox.f90:293-296).

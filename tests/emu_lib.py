@@ -104,6 +104,15 @@ class EmuHandle:
         check(self.lib, self.lib.pbx_matmult_device(self._h, ptr(f), ptr(out)))
         return out
 
+    def set_pc(self, pc, nu=0):
+        check(self.lib, self.lib.pbx_set_pc(self._h, pc, nu))
+
+    def pc_apply(self, r):
+        r = aligned(r)
+        z = new_field(self.shape)
+        check(self.lib, self.lib.pbx_pc_apply_device(self._h, ptr(r), ptr(z)))
+        return z
+
     def lapl_dot(self, f):
         f = aligned(f)
         out = new_field(self.shape)

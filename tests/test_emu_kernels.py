@@ -235,6 +235,62 @@ def test_emu_star_slabs_and_cg():
     assert np.max(np.abs(x - xo)) <= 1e-8 * np.max(np.abs(xo))
 
 
+@pytest.mark.parametrize("shape,dx", [((16, 16, 16), (0.1, 0.1, 0.1)), ((32, 16, 48), (0.1, 0.15, 0.07)),
+                                      ((24, 16, 20), (0.3, 0.2, 0.25))])
+def test_emu_mg_vcycle_matches_model(shape, dx):
+    """the multigrid preconditioner (pbx_mg.cu) against its numpy model, and its symmetry and
+    positive definiteness on the zero-mean subspace (what CG needs of a preconditioner)"""
+    import mg_model as mg
+    from poissbox_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    r = np.asfortranarray(rng.standard_normal(shape)) + 0.3
+    q = np.asfortranarray(rng.standard_normal(shape))
+    for nu in (1, 2):
+        h = handle(shape, dx)
+        h.set_pc(_lib.PC_MG, nu)
+        z = h.pc_apply(r)
+        zm = mg.pc_apply(r, dx, nu)
+        assert np.max(np.abs(z - zm)) <= 1e-13 * np.max(np.abs(zm))
+        assert abs(z.mean()) <= 1e-13 * np.max(np.abs(z))
+        zq = h.pc_apply(q)
+        a, b = np.vdot(q - q.mean(), z), np.vdot(zq, r - r.mean())
+        assert abs(a - b) <= 1e-12 * max(abs(a), abs(b))
+        assert np.vdot(r - r.mean(), z) > 0
+        h.close()
+    h = handle(shape, dx)   # PC none: z = r - mean(r)
+    assert np.max(np.abs(h.pc_apply(r) - (r - r.mean()))) <= 1e-15 * np.max(np.abs(r))
+    h.close()
+
+
+@pytest.mark.parametrize("op", [0, 1])
+def test_emu_pcg_matches_model(op):
+    """KSPCG with the multigrid preconditioner: iteration count and history of the numpy model"""
+    import mg_model as mg
+    from poissbox_b200 import _lib
+
+    n = 16
+    hh = 2 * np.pi / n
+    dx = (hh,) * 3
+    c = (np.arange(n) + 0.5) * hh
+    u = np.exp(np.sin(c)[:, None, None] + np.sin(c)[None, :, None] + np.sin(c)[None, None, :])
+    apply_a = (lambda v: orc.lapl(np.asfortranarray(v), dx)) if op == 0 else (lambda v: orc.star(np.asfortranarray(v), dx))
+    b = apply_a(u)
+    xm, itm, histm = mg.pcg(apply_a, b, lambda r: mg.pc_apply(r, dx, 2))
+    h = handle((n, n, n), dx)
+    h.set_operator(op)
+    h.set_pc(_lib.PC_MG, 2)
+    x, its, rn, why, hist = h.cg_solve(b, rtol=1e-8)
+    assert why == 2 and its == itm
+    assert np.allclose(hist, histm[: its + 1], rtol=1e-9)
+    du = u - u.mean()
+    assert np.linalg.norm((x - x.mean()) - du) <= 1e-6 * np.linalg.norm(du)
+    h.set_pc(_lib.PC_NONE)
+    _, its0, _, why0, _ = h.cg_solve(b, rtol=1e-8)
+    assert why0 == 2 and its0 > 3 * its   # the unpreconditioned solve still works and is much longer
+    h.close()
+
+
 def test_emu_no_device_is_an_error():
     """the harness honours the product's rule: no device, no result (PBX_ERR_CUDA)"""
     lib = emu_lib.load()
