@@ -29,7 +29,7 @@ namespace pbx {
 
 namespace {
 
-constexpr int MBX = 32, MBY = 8, MKZ = 32;
+constexpr int MBX = 32, MBY = 8, MKZ = 4;
 constexpr double MG_OMEGA = 6.0 / 7.0;
 constexpr int MG_COARSE_SWEEPS = 30;
 
@@ -41,6 +41,9 @@ struct Lv {
 
 // MODE 0: out = z + wd ((r - m) - S z)      damped Jacobi
 // MODE 1: out = (r - m) - S z               residual
+// A thread owns MKZ consecutive planes of one (i,j) column; all its loads (MKZ + 2 values of its own
+// column, 4 MKZ in-plane neighbours, MKZ right-hand sides) are issued before the arithmetic, so
+// that a warp keeps ~30 requests in flight instead of walking a dependent chain of planes.
 template <int MODE>
 __global__ void __launch_bounds__(MBX * MBY)
 mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
@@ -51,24 +54,38 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
     const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
     if (i >= nx || j >= ny) return;
     const double m = mean ? *mean : 0.0;
-    const int k0 = blockIdx.z * MKZ, k1 = k0 + MKZ < nz ? k0 + MKZ : nz;
+    const int k0 = blockIdx.z * MKZ;
     const size_t plane = (size_t)nx * ny;
     const size_t col = i + (size_t)nx * j;
     const size_t im = (i == 0 ? nx - 1 : i - 1) + (size_t)nx * j, ip = (i == nx - 1 ? 0 : i + 1) + (size_t)nx * j;
     const size_t jm = i + (size_t)nx * (j == 0 ? ny - 1 : j - 1), jp = i + (size_t)nx * (j == ny - 1 ? 0 : j + 1);
-    double below = z[col + plane * (k0 > 0 ? k0 - 1 : nz - 1)];
-    double centre = z[col + plane * k0];
-    for (int k = k0; k < k1; ++k) {
-        const size_t pk = plane * k;
-        const double above = z[col + (k + 1 < nz ? pk + plane : 0)];
-        const double c2 = 2.0 * centre;
-        double sz = lv.cx * (c2 - __ldg(z + pk + im) - __ldg(z + pk + ip));
-        sz = fma(lv.cy, c2 - __ldg(z + pk + jm) - __ldg(z + pk + jp), sz);
-        sz = fma(lv.cz, c2 - below - above, sz);
-        const double res = (r[col + pk] - m) - sz;
-        out[col + pk] = MODE == 0 ? fma(lv.wd, res, centre) : res;
-        below = centre;
-        centre = above;
+    double zc[MKZ + 2], zim[MKZ], zip[MKZ], zjm[MKZ], zjp[MKZ], rr[MKZ];
+#pragma unroll
+    for (int u = 0; u < MKZ + 2; ++u) {
+        int k = k0 - 1 + u;
+        k = k < 0 ? nz - 1 : (k >= nz ? k - nz : k);
+        zc[u] = (k0 + u - 1 <= nz) ? z[col + plane * k] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < MKZ; ++u) {
+        const bool in = k0 + u < nz;
+        const size_t pk = plane * (in ? k0 + u : 0);
+        zim[u] = in ? __ldg(z + pk + im) : 0.0;
+        zip[u] = in ? __ldg(z + pk + ip) : 0.0;
+        zjm[u] = in ? __ldg(z + pk + jm) : 0.0;
+        zjp[u] = in ? __ldg(z + pk + jp) : 0.0;
+        rr[u] = in ? r[col + pk] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < MKZ; ++u) {
+        if (k0 + u < nz) {
+            const double centre = zc[u + 1], c2 = 2.0 * centre;
+            double sz = lv.cx * (c2 - zim[u] - zip[u]);
+            sz = fma(lv.cy, c2 - zjm[u] - zjp[u], sz);
+            sz = fma(lv.cz, c2 - zc[u] - zc[u + 2], sz);
+            const double res = (rr[u] - m) - sz;
+            out[col + plane * (k0 + u)] = MODE == 0 ? fma(lv.wd, res, centre) : res;
+        }
     }
 }
 

@@ -35,36 +35,56 @@ StarCoef star_coef(const double dx[3])
 }
 
 constexpr int SBX = 32, SBY = 8;   // CTA = 32 x 8 columns
-constexpr int SKZ = 32;            // planes per CTA
+constexpr int SKZ = 4;             // planes per thread
 
 // lo / up: the plane below k = 0 / above k = nz - 1 when the brick is one slab of a z-decomposed
-// box (nullptr: periodic in z within the brick)
+// box (nullptr: periodic in z within the brick).  All of a thread's loads (SKZ + 2 values of its own
+// column, 4 SKZ in-plane neighbours) are issued before the arithmetic.
 __global__ void __launch_bounds__(SBX * SBY)
 star_kernel(int nx, int ny, int nz, const __grid_constant__ StarCoef c, const double *__restrict__ x,
             const double *__restrict__ lo, const double *__restrict__ up, double *__restrict__ y)
 {
     const int i = blockIdx.x * SBX + threadIdx.x, j = blockIdx.y * SBY + threadIdx.y;
     if (i >= nx || j >= ny) return;
-    const int k0 = blockIdx.z * SKZ, k1 = k0 + SKZ < nz ? k0 + SKZ : nz;
+    const int k0 = blockIdx.z * SKZ;
     const size_t plane = (size_t)nx * ny;
     const size_t col = i + (size_t)nx * j;
     const size_t im = (i == 0 ? nx - 1 : i - 1) + (size_t)nx * j, ip = (i == nx - 1 ? 0 : i + 1) + (size_t)nx * j;
     const size_t jm = i + (size_t)nx * (j == 0 ? ny - 1 : j - 1), jp = i + (size_t)nx * (j == ny - 1 ? 0 : j + 1);
-    double below = k0 > 0 ? x[col + plane * (k0 - 1)] : (lo ? lo[col] : x[col + plane * (nz - 1)]);
-    double centre = x[col + plane * k0];
-    for (int k = k0; k < k1; ++k) {
-        const size_t pk = plane * k;
-        const double above = k + 1 < nz ? x[col + pk + plane] : (up ? up[col] : x[col]);
-        double s = __dadd_rn(0.0, __dmul_rn(below, c.cz));
-        s = __dadd_rn(s, __dmul_rn(__ldg(x + pk + jm), c.cy));
-        s = __dadd_rn(s, __dmul_rn(__ldg(x + pk + im), c.cx));
-        s = __dadd_rn(s, __dmul_rn(centre, c.c0));
-        s = __dadd_rn(s, __dmul_rn(__ldg(x + pk + ip), c.cx));
-        s = __dadd_rn(s, __dmul_rn(__ldg(x + pk + jp), c.cy));
-        s = __dadd_rn(s, __dmul_rn(above, c.cz));
-        y[col + pk] = s;
-        below = centre;
-        centre = above;
+    double xc[SKZ + 2], xim[SKZ], xip[SKZ], xjm[SKZ], xjp[SKZ];
+#pragma unroll
+    for (int u = 0; u < SKZ + 2; ++u) {
+        const int k = k0 - 1 + u;
+        if (k > nz)
+            xc[u] = 0.0;
+        else if (k < 0)
+            xc[u] = lo ? lo[col] : x[col + plane * (nz - 1)];
+        else if (k == nz)
+            xc[u] = up ? up[col] : x[col];
+        else
+            xc[u] = x[col + plane * k];
+    }
+#pragma unroll
+    for (int u = 0; u < SKZ; ++u) {
+        const bool in = k0 + u < nz;
+        const size_t pk = plane * (in ? k0 + u : 0);
+        xim[u] = in ? __ldg(x + pk + im) : 0.0;
+        xip[u] = in ? __ldg(x + pk + ip) : 0.0;
+        xjm[u] = in ? __ldg(x + pk + jm) : 0.0;
+        xjp[u] = in ? __ldg(x + pk + jp) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < SKZ; ++u) {
+        if (k0 + u < nz) {
+            double s = __dadd_rn(0.0, __dmul_rn(xc[u], c.cz));
+            s = __dadd_rn(s, __dmul_rn(xjm[u], c.cy));
+            s = __dadd_rn(s, __dmul_rn(xim[u], c.cx));
+            s = __dadd_rn(s, __dmul_rn(xc[u + 1], c.c0));
+            s = __dadd_rn(s, __dmul_rn(xip[u], c.cx));
+            s = __dadd_rn(s, __dmul_rn(xjp[u], c.cy));
+            s = __dadd_rn(s, __dmul_rn(xc[u + 2], c.cz));
+            y[col + plane * (k0 + u)] = s;
+        }
     }
 }
 

@@ -96,7 +96,10 @@ def test_cg_on_star_operator_matches_oracle(n, kind):
     h.close()
     assert why == reo == 2 and abs(its - ito) <= 1, (its, ito)
     m = min(len(hist), len(ho))
-    assert np.allclose(hist[: max(2, m // 2)], ho[: max(2, m // 2)], rtol=1e-6)
+    # as in test_cg_matches_oracle: for the smooth S4 right-hand side the later iterations are
+    # governed by rounding noise, which the two summation orders amplify differently
+    assert np.allclose(hist[:6], ho[:6], rtol=1e-8)
+    assert np.allclose(hist[: max(2, m // 2)], ho[: max(2, m // 2)], rtol=1e-6 if kind == "S3" else 1e-2)
     assert np.linalg.norm(orc.star(xg, dx) - b) <= 20e-8 * np.linalg.norm(b)
     assert np.linalg.norm(xg - xo) <= 1e-5 * np.linalg.norm(xo)
 
