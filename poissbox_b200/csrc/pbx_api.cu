@@ -557,6 +557,10 @@ int pbx_set_pc(pbx_handle h, int pc, int nu)
 int pbx_pc_apply_device(pbx_handle h, const double *r, double *z)
 {
     if (!h || !r || !z || r == z) return PBX_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(z)) & 15) {
+        set_last_error("pbx_pc_apply_device: r and z must be 16-byte aligned");
+        return PBX_ERR_ARG;
+    }
     PBX_CUDA(cudaSetDevice(h->device));
     return pc_apply(h, r, z);
 }

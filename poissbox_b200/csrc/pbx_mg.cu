@@ -101,17 +101,18 @@ mg_scale_kernel(size_t n, double wd, const double *__restrict__ r, const double 
 }
 
 // coarse(I,J,K) = sum over the 4x4x4 fine cells 2I-1 .. 2I+2 (periodic) with weights
-// (1/8, 3/8, 3/8, 1/8) per direction.  lv = the FINE level; one thread per coarse cell.
-__global__ void __launch_bounds__(256)
+// (1/8, 3/8, 3/8, 1/8) per direction.  lv = the FINE level; one thread per coarse cell, CTA = 32 x 8
+// coarse cells of plane blockIdx.z.
+__global__ void __launch_bounds__(MBX * MBY)
 mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fine,
                    double *__restrict__ coarse)
 {
-    const int cnx = lv.nx / 2, cny = lv.ny / 2, cnz = lv.nz / 2;
-    const size_t nc = (size_t)cnx * cny * cnz;
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nc) return;
-    const int I = (int)(q % cnx), J = (int)((q / cnx) % cny), K = (int)(q / ((size_t)cnx * cny));
+    const int cnx = lv.nx / 2, cny = lv.ny / 2;
+    const int I = blockIdx.x * MBX + threadIdx.x, J = blockIdx.y * MBY + threadIdx.y, K = blockIdx.z;
+    if (I >= cnx || J >= cny) return;
     const double w[4] = {0.125, 0.375, 0.375, 0.125};
+    const int i0 = 2 * I;
+    const int im = i0 == 0 ? lv.nx - 1 : i0 - 1, ip = i0 + 2 >= lv.nx ? 0 : i0 + 2;
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -123,27 +124,23 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
             int j = 2 * J - 1 + b;
             j = j < 0 ? j + lv.ny : (j >= lv.ny ? j - lv.ny : j);
             const double *row = fine + (size_t)lv.nx * (j + (size_t)lv.ny * k);
-            const int i0 = 2 * I;
-            const double f0 = __ldg(row + (i0 == 0 ? lv.nx - 1 : i0 - 1)), f1 = __ldg(row + i0),
-                         f2 = __ldg(row + i0 + 1), f3 = __ldg(row + (i0 + 2 >= lv.nx ? 0 : i0 + 2));
-            sk = fma(w[b], fma(w[0], f0 + f3, w[1] * (f1 + f2)), sk);
+            const double2 mid = *reinterpret_cast<const double2 *>(row + i0);   // i0 is even
+            sk = fma(w[b], fma(w[0], __ldg(row + im) + __ldg(row + ip), w[1] * (mid.x + mid.y)), sk);
         }
         s = fma(w[c], sk, s);
     }
-    coarse[q] = s;
+    coarse[I + (size_t)cnx * (J + (size_t)cny * K)] = s;
 }
 
 // fine += Pr coarse: fine cell 2I takes 3/4 c(I) + 1/4 c(I-1), cell 2I+1 takes 3/4 c(I) + 1/4 c(I+1),
-// per direction.  lv = the FINE level; one thread per fine cell.
-__global__ void __launch_bounds__(256)
+// per direction.  lv = the FINE level; one thread per fine cell, CTA = 32 x 8 cells of plane blockIdx.z.
+__global__ void __launch_bounds__(MBX * MBY)
 mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coarse,
                   double *__restrict__ fine)
 {
-    const size_t n = (size_t)lv.nx * lv.ny * lv.nz;
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y, k = blockIdx.z;
+    if (i >= lv.nx || j >= lv.ny) return;
     const int cnx = lv.nx / 2, cny = lv.ny / 2, cnz = lv.nz / 2;
-    const int i = (int)(q % lv.nx), j = (int)((q / lv.nx) % lv.ny), k = (int)(q / ((size_t)lv.nx * lv.ny));
     auto nb = [](int f, int cn, int &a, int &b) {   // a: the parent (3/4), b: the other one (1/4)
         a = f >> 1;
         b = (f & 1) ? (a + 1 == cn ? 0 : a + 1) : (a == 0 ? cn - 1 : a - 1);
@@ -155,7 +152,7 @@ mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coar
     auto at = [&](int I, int J, int K) { return __ldg(coarse + I + (size_t)cnx * (J + (size_t)cny * K)); };
     auto linex = [&](int J, int K) { return fma(0.25, at(ib, J, K), 0.75 * at(ia, J, K)); };
     auto planey = [&](int K) { return fma(0.25, linex(jb, K), 0.75 * linex(ja, K)); };
-    fine[q] += fma(0.25, planey(kb), 0.75 * planey(ka));
+    fine[i + (size_t)lv.nx * (j + (size_t)lv.ny * k)] += fma(0.25, planey(kb), 0.75 * planey(ka));
 }
 
 }  // namespace
@@ -288,14 +285,16 @@ int mg_vcycle(pbx_handle_s *h, const double *r, const double *mean, double *z)
         PBX_TRY(smooth_from_zero(h, L, L.r, mp, nu, &cur[l], &alt[l]));
         PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l]));          // residual into the spare
         MgLevel &C = m->lev[l + 1];
-        mg_restrict_kernel<<<blocks_for(C.n), 256, 0, h->stream>>>(L.lv, alt[l], C.r);
+        mg_restrict_kernel<<<dim3((C.lv.nx + MBX - 1) / MBX, (C.lv.ny + MBY - 1) / MBY, C.lv.nz), dim3(MBX, MBY), 0,
+                             h->stream>>>(L.lv, alt[l], C.r);
         ++h->launches;
     }
     // upward leg
     for (int l = nl - 2; l >= 0; --l) {
         MgLevel &L = m->lev[l];
         const double *mp = l == 0 ? mean : nullptr;
-        mg_prolong_kernel<<<blocks_for(L.n), 256, 0, h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
+        mg_prolong_kernel<<<dim3((L.lv.nx + MBX - 1) / MBX, (L.lv.ny + MBY - 1) / MBY, L.lv.nz), dim3(MBX, MBY), 0,
+                            h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
         ++h->launches;
         for (int s = 0; s < nu; ++s) {
             PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l]));

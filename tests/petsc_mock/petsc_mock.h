@@ -65,7 +65,7 @@ typedef struct _p_DM {
             return (err);                       \
         }                                       \
     } while (0)
-#define PetscNew(p) ((*(p) = calloc(1, sizeof(**(p)))) ? PETSC_SUCCESS : PETSC_ERR_LIB)
+#define PetscNew(p) ((*(void **)(p) = calloc(1, sizeof(**(p)))) ? PETSC_SUCCESS : PETSC_ERR_LIB)
 
 static inline PetscErrorCode MatShellGetContext(Mat A, void *ctx)
 {
