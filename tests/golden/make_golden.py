@@ -78,6 +78,15 @@ def main():
     out["cg16_x"] = x
     out["cg16_hist"] = hist
     out["cg16_meta"] = np.array([its, reason, rnorm])
+    # --- the 2nd-order star (what mfmult applies today) on the two bricks above, and CG on it ---
+    for tag in "ab":
+        out[f"f3{tag}_star"] = orc.star(out[f"f3{tag}_f"], out[f"f3{tag}_dx"])
+    bs = orc.star(xt, dx)
+    x, its, rnorm, reason, hist = orc.cg_solve(bs, dx, rtol=1e-8, op=1)
+    out["cgstar16_b"] = bs
+    out["cgstar16_x"] = x
+    out["cgstar16_hist"] = hist
+    out["cgstar16_meta"] = np.array([its, reason, rnorm])
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "oracle_vectors.npz"), len(out), "arrays")
 

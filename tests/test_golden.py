@@ -46,3 +46,11 @@ def test_cg_golden():
     assert (its, reason) == (int(G["cg16_meta"][0]), int(G["cg16_meta"][1]))
     assert np.array_equal(hist, G["cg16_hist"])
     assert np.array_equal(x, G["cg16_x"])
+
+
+def test_star_golden():
+    for tag in "ab":
+        assert np.array_equal(orc.star(G[f"f3{tag}_f"], G[f"f3{tag}_dx"]), G[f"f3{tag}_star"])
+    x, its, rnorm, reason, hist = orc.cg_solve(G["cgstar16_b"], (1 / 16,) * 3, rtol=1e-8, op=1)
+    assert (its, reason) == (int(G["cgstar16_meta"][0]), int(G["cgstar16_meta"][1]))
+    assert np.array_equal(hist, G["cgstar16_hist"]) and np.array_equal(x, G["cgstar16_x"])

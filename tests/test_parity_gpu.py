@@ -227,6 +227,7 @@ def test_fields_golden():
         assert np.array_equal(cs.div(v, dx), G[f"f3{tag}_div"])
         assert np.array_equal(cs.interp(f), G[f"f3{tag}_interp"])
         assert np.array_equal(cs.interp_div(f), G[f"f3{tag}_interpdiv"])
+        assert np.array_equal(pbx.compute_lapl.compute_lapl_pointwise(f, dx), G[f"f3{tag}_star"])
     f, dx = G["f3a_f"], G["f3a_dx"]
     assert_fast_close(cs.lapl(f, dx, mode=pbx.MODE_FAST), G["f3a_lapl"])
 
