@@ -284,7 +284,9 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get(f"{dom}pass_{n}")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": f"{dom}pass_kernel", "achieved": per[dom]["achieved_GBs"],
+        kname = {"x": "x_tma_kernel<false> (x pass)", "y": "yz_tma_kernel<false,false,false> (y pass)",
+                 "z": "yz_tma_kernel<true,false,false> (z pass)"}[dom]
+        roof = {"bound": "hbm", "kernel": kname, "achieved": per[dom]["achieved_GBs"],
                 "peak": peak, "unit": "GB/s", "frac": per[dom]["achieved_GBs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "passes": per,
                 "matmult": {"alg_bytes_per_dof": ALG_BYTES_MATMULT,
