@@ -41,6 +41,8 @@ struct Lv {
 
 // MODE 0: out = z + wd ((r - m) - S z)      damped Jacobi
 // MODE 1: out = (r - m) - S z               residual
+// MODE 2: the first TWO Jacobi sweeps from a zero guess in one pass over r (z = r on entry):
+//         z1 = wd (r - m),  out = z1 + wd ((r - m) - S z1) = wd ((r - m) + ((r - m) - wd S r))
 // A thread owns MKZ consecutive planes of one (i,j) column; all its loads (MKZ + 2 values of its own
 // column, 4 MKZ in-plane neighbours, MKZ right-hand sides) are issued before the arithmetic, so
 // that a warp keeps ~30 requests in flight instead of walking a dependent chain of planes.
@@ -74,7 +76,7 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
         zip[u] = in ? __ldg(z + pk + ip) : 0.0;
         zjm[u] = in ? __ldg(z + pk + jm) : 0.0;
         zjp[u] = in ? __ldg(z + pk + jp) : 0.0;
-        rr[u] = in ? r[col + pk] : 0.0;
+        rr[u] = (in && MODE != 2) ? r[col + pk] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < MKZ; ++u) {
@@ -83,8 +85,13 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
             double sz = lv.cx * (c2 - zim[u] - zip[u]);
             sz = fma(lv.cy, c2 - zjm[u] - zjp[u], sz);
             sz = fma(lv.cz, c2 - zc[u] - zc[u + 2], sz);
-            const double res = (rr[u] - m) - sz;
-            out[col + plane * (k0 + u)] = MODE == 0 ? fma(lv.wd, res, centre) : res;
+            if (MODE == 2) {
+                const double rb = centre - m;
+                out[col + plane * (k0 + u)] = lv.wd * (rb + fma(-lv.wd, sz, rb));
+            } else {
+                const double res = (rr[u] - m) - sz;
+                out[col + plane * (k0 + u)] = MODE == 0 ? fma(lv.wd, res, centre) : res;
+            }
         }
     }
 }
@@ -133,26 +140,43 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
 }
 
 // fine += Pr coarse: fine cell 2I takes 3/4 c(I) + 1/4 c(I-1), cell 2I+1 takes 3/4 c(I) + 1/4 c(I+1),
-// per direction.  lv = the FINE level; one thread per fine cell, CTA = 32 x 8 cells of plane blockIdx.z.
+// per direction.  lv = the FINE level.  A thread owns the fine column (i,j) over four fine planes
+// 4 B .. 4 B + 3 (B = blockIdx.z): it interpolates the four coarse planes 2 B - 1 .. 2 B + 2 in x and y
+// first (16 loads issued together), then along z.
 __global__ void __launch_bounds__(MBX * MBY)
 mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coarse,
                   double *__restrict__ fine)
 {
-    const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y, k = blockIdx.z;
+    const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
     if (i >= lv.nx || j >= lv.ny) return;
     const int cnx = lv.nx / 2, cny = lv.ny / 2, cnz = lv.nz / 2;
     auto nb = [](int f, int cn, int &a, int &b) {   // a: the parent (3/4), b: the other one (1/4)
         a = f >> 1;
         b = (f & 1) ? (a + 1 == cn ? 0 : a + 1) : (a == 0 ? cn - 1 : a - 1);
     };
-    int ia, ib, ja, jb, ka, kb;
+    int ia, ib, ja, jb;
     nb(i, cnx, ia, ib);
     nb(j, cny, ja, jb);
-    nb(k, cnz, ka, kb);
-    auto at = [&](int I, int J, int K) { return __ldg(coarse + I + (size_t)cnx * (J + (size_t)cny * K)); };
-    auto linex = [&](int J, int K) { return fma(0.25, at(ib, J, K), 0.75 * at(ia, J, K)); };
-    auto planey = [&](int K) { return fma(0.25, linex(jb, K), 0.75 * linex(ja, K)); };
-    fine[i + (size_t)lv.nx * (j + (size_t)lv.ny * k)] += fma(0.25, planey(kb), 0.75 * planey(ka));
+    const int K0 = 2 * blockIdx.z;                    // first of the two parent planes
+    double q[4];                                      // in-plane interpolants of planes K0 - 1 .. K0 + 2
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int K = K0 - 1 + u;
+        K = K < 0 ? cnz - 1 : (K >= cnz ? K - cnz : K);
+        const double *pl = coarse + (size_t)cnx * cny * K;
+        const double a0 = __ldg(pl + ia + (size_t)cnx * ja), b0 = __ldg(pl + ib + (size_t)cnx * ja);
+        const double a1 = __ldg(pl + ia + (size_t)cnx * jb), b1 = __ldg(pl + ib + (size_t)cnx * jb);
+        q[u] = fma(0.25, fma(0.25, b1, 0.75 * a1), 0.75 * fma(0.25, b0, 0.75 * a0));
+    }
+    const size_t plane = (size_t)lv.nx * lv.ny, col = i + (size_t)lv.nx * j;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k = 2 * K0 + u;                     // fine plane; parent K0 + u / 2
+        if (k < lv.nz) {
+            const double par = q[1 + u / 2], oth = (u & 1) ? q[2 + u / 2] : q[u / 2];
+            fine[col + plane * k] += fma(0.25, oth, 0.75 * par);
+        }
+    }
 }
 
 }  // namespace
@@ -176,8 +200,10 @@ int sweep(pbx_handle_s *h, int mode, const Lv &lv, const double *z, const double
     dim3 block(MBX, MBY), grid((lv.nx + MBX - 1) / MBX, (lv.ny + MBY - 1) / MBY, (lv.nz + MKZ - 1) / MKZ);
     if (mode == 0)
         mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
-    else
+    else if (mode == 1)
         mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+    else
+        mg_sweep_kernel<2><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
     ++h->launches;
     return PBX_OK;
 }
@@ -188,11 +214,20 @@ unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 int smooth_from_zero(pbx_handle_s *h, const MgLevel &L, const double *r, const double *mean, int count,
                      double **cur, double **alt)
 {
-    unsigned nb = blocks_for(L.n);
-    if (nb > 148 * 16) nb = 148 * 16;
-    mg_scale_kernel<<<nb, 256, 0, h->stream>>>(L.n, L.lv.wd, r, mean, *cur);
-    ++h->launches;
-    for (int s = 1; s < count; ++s) {
+    int done = 1;
+    if (count >= 2) {
+        // two sweeps in one pass; the caller's buffer parity counts sweeps, so the result goes where
+        // the second sweep would have put it
+        PBX_TRY(sweep(h, 2, L.lv, r, r, mean, *alt));
+        std::swap(*cur, *alt);
+        done = 2;
+    } else {
+        unsigned nb = blocks_for(L.n);
+        if (nb > 148 * 16) nb = 148 * 16;
+        mg_scale_kernel<<<nb, 256, 0, h->stream>>>(L.n, L.lv.wd, r, mean, *cur);
+        ++h->launches;
+    }
+    for (int s = done; s < count; ++s) {
         PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt));
         std::swap(*cur, *alt);
     }
@@ -293,8 +328,8 @@ int mg_vcycle(pbx_handle_s *h, const double *r, const double *mean, double *z)
     for (int l = nl - 2; l >= 0; --l) {
         MgLevel &L = m->lev[l];
         const double *mp = l == 0 ? mean : nullptr;
-        mg_prolong_kernel<<<dim3((L.lv.nx + MBX - 1) / MBX, (L.lv.ny + MBY - 1) / MBY, L.lv.nz), dim3(MBX, MBY), 0,
-                            h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
+        mg_prolong_kernel<<<dim3((L.lv.nx + MBX - 1) / MBX, (L.lv.ny + MBY - 1) / MBY, (L.lv.nz + 3) / 4),
+                            dim3(MBX, MBY), 0, h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
         ++h->launches;
         for (int s = 0; s < nu; ++s) {
             PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l]));
