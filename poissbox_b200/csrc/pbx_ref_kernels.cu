@@ -14,23 +14,12 @@ namespace {
 
 __device__ __forceinline__ double sgn_mul(int s, double v) { return s > 0 ? v : -v; }
 
-// rhs(i) of eval_1d_rhs (0-based i), periodic wrap (:356-370)
-__device__ __forceinline__ double rhs_at(const double *__restrict__ f, long long es, int n, int i,
-                                         int shift, int s, double a, double b)
-{
-    // stagger -1 (shift 0): a (f(i) + s f(i-1)) + b (f(i+1) + s f(i-2))
-    // stagger +1 (shift 1): a (f(i+1) + s f(i)) + b (f(i+2) + s f(i-1))
-    int i0 = i + shift, i1 = i - 1 + shift, i2 = i + 1 + shift, i3 = i - 2 + shift;
-    if (i0 >= n) i0 -= n;
-    if (i1 < 0) i1 += n;
-    if (i2 >= n) i2 -= n;
-    if (i3 < 0) i3 += n;
-    double t1 = __dmul_rn(a, __dadd_rn(f[i0 * es], sgn_mul(s, f[i1 * es])));
-    double t2 = __dmul_rn(b, __dadd_rn(f[i2 * es], sgn_mul(s, f[i3 * es])));
-    return __dadd_rn(t1, t2);
-}
-
 // One thread per line.  Line (l1, l2) starts at l1*ls1 + l2*ls2; element stride es.
+// The three sweeps are serial recurrences; each walks its line in blocks of PF points and loads
+// block k+1 into registers before it computes block k, so that the divide chain does not wait
+// on memory (same operations in the same order: same bits).
+constexpr int PF = 8;
+
 __global__ void __launch_bounds__(128)
 ref_line_kernel(int n, long long nl1, long long nl2, long long es, long long ls1, long long ls2,
                 int shift, int s, double a, double b, const double *__restrict__ w,
@@ -44,28 +33,94 @@ ref_line_kernel(int n, long long nl1, long long nl2, long long es, long long ls1
     double *d = out + l1 * ls1 + l2 * ls2;
 
     // eval_1d_rhs fused with fwd_sweep's data recurrence d(i) = d(i) - w d(i-1)   (tridsol.f90:93)
-    double prev = rhs_at(f, es, n, 0, shift, s, a, b);
-    d[0] = prev;
-    for (int i = 1; i < n; ++i) {
-        double r = rhs_at(f, es, n, i, shift, s, a, b);
-        prev = __dsub_rn(r, __dmul_rn(__ldg(w + i), prev));
-        d[i * es] = prev;
+    // rhs(i) = a (f(i+sh) + s f(i-1+sh)) + b (f(i+1+sh) + s f(i-2+sh)): a sliding window of four values
+    auto at = [&](int i) {
+        i += shift;
+        if (i < 0) i += n;
+        if (i >= n) i -= n;
+        return f[(long long)i * es];
+    };
+    double fm2 = at(-2), fm1 = at(-1), f0 = at(0);      // f(i-2+sh), f(i-1+sh), f(i+sh) for i = 0
+    double fn[PF], wn[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        fn[k] = k < n ? at(k + 1) : 0.0;                // f(i+1+sh) for i = k
+        wn[k] = (k >= 1 && k < n) ? __ldg(w + k) : 0.0;
+    }
+    double prev = 0.0;
+    for (int i0 = 0; i0 < n; i0 += PF) {
+        double fc[PF], wc[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            fc[k] = fn[k];
+            wc[k] = wn[k];
+            const int i = i0 + PF + k;
+            fn[k] = i < n ? at(i + 1) : 0.0;
+            wn[k] = i < n ? __ldg(w + i) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = i0 + k;
+            if (i < n) {
+                const double t1 = __dmul_rn(a, __dadd_rn(f0, sgn_mul(s, fm1)));
+                const double t2 = __dmul_rn(b, __dadd_rn(fc[k], sgn_mul(s, fm2)));
+                const double r = __dadd_rn(t1, t2);
+                prev = i == 0 ? r : __dsub_rn(r, __dmul_rn(wc[k], prev));
+                d[(long long)i * es] = prev;
+                fm2 = fm1;
+                fm1 = f0;
+                f0 = fc[k];
+            }
+        }
     }
     // bwd_sweep (tridsol.f90:108-113); c(i) = alpha folded by the caller into `a1g`'s sibling
     const double alpha = -a1g;   // a(1)/gamma = alpha/(-1)
     double x = __ddiv_rn(prev, __ldg(piv + n - 1));
     d[(long long)(n - 1) * es] = x;
     const double dn = x;
-    for (int i = n - 2; i >= 0; --i) {
-        double di = d[i * es];
-        x = __ddiv_rn(__dsub_rn(di, __dmul_rn(alpha, x)), __ldg(piv + i));
-        d[i * es] = x;
+    {
+        double dnx[PF], pn[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = n - 2 - k;
+            dnx[k] = i >= 0 ? d[(long long)i * es] : 0.0;
+            pn[k] = i >= 0 ? __ldg(piv + i) : 1.0;
+        }
+        for (int i0 = n - 2; i0 >= 0; i0 -= PF) {
+            double dc[PF], pc[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                dc[k] = dnx[k];
+                pc[k] = pn[k];
+                const int i = i0 - PF - k;
+                dnx[k] = i >= 0 ? d[(long long)i * es] : 0.0;
+                pn[k] = i >= 0 ? __ldg(piv + i) : 1.0;
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int i = i0 - k;
+                if (i >= 0) {
+                    x = __ddiv_rn(__dsub_rn(dc[k], __dmul_rn(alpha, x)), pc[k]);
+                    d[(long long)i * es] = x;
+                }
+            }
+        }
     }
     // Sherman-Morrison combine (tridsol.f90:69-70), old d(1), d(n) on the right-hand side
     const double fac = __dadd_rn(x, __dmul_rn(a1g, dn));
-    for (int i = 0; i < n; ++i) {
-        double di = d[i * es];
-        d[i * es] = __dsub_rn(di, __ddiv_rn(__dmul_rn(__ldg(u + i), fac), den));
+    for (int i0 = 0; i0 < n; i0 += PF) {
+        double dc[PF], uc[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = i0 + k;
+            dc[k] = i < n ? d[(long long)i * es] : 0.0;
+            uc[k] = i < n ? __ldg(u + i) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = i0 + k;
+            if (i < n) d[(long long)i * es] = __dsub_rn(dc[k], __ddiv_rn(__dmul_rn(uc[k], fac), den));
+        }
     }
 }
 
