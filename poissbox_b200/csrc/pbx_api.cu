@@ -58,18 +58,20 @@ Lines lines_of(const pbx_handle_s *h, int dir)
 
 // zslot: on a slab of a z-decomposed box a z operator takes the neighbours' messages that
 // line_boundary() put in slot `zslot` of the exchange buffers before the exchange
+// addend (FAST only): out = op(in) + addend
 int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in, double *out,
-            bool fast = false, int zslot = 0)
+            bool fast = false, int zslot = 0, const double *addend = nullptr)
 {
     if (h->nranks > 1 && dir == 2) {
         const double *lo = nullptr, *up = nullptr;
         PBX_TRY(dist_line_msgs(h, zslot, &lo, &up));
         return fast_line_op(h->stream, Brick{h->nx, h->ny, h->nz}, dir, kind, stagger, h->dx[dir], in,
-                            out, &h->launches, lo, up);
+                            out, &h->launches, lo, up, addend);
     }
     if (fast)
         return fast_line_op(h->stream, Brick{h->nx, h->ny, h->nz}, dir, kind, stagger, h->dx[dir], in,
-                            out, &h->launches);
+                            out, &h->launches, nullptr, nullptr, addend);
+    if (addend) return PBX_ERR_ARG;
     Lines L = lines_of(h, dir);
     return ref_line_op(h->stream, L.n, L.nl1, L.nl2, L.es, L.ls1, L.ls2, kind, stagger, h->dx[dir],
                        h->ref[dir][kind], in, out, &h->launches);
@@ -96,8 +98,10 @@ static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2,
 }
 
 // src/compact_schemes.f90:207-257 (X -> Y -> Z, forward stagger).  i1..i3 may be scratch 0..2.
-// div_stages_xy: the X and Y stages, leaving the inputs of the two Z operators in S[4]
-// (interpolation) and S[3] (derivative); div_stages_z: the Z stage.
+// div_stages_xy: the X and Y stages, leaving the inputs of the two Z operators in S[zi]
+// (interpolation; zi = 4, or 2 on the FAST schedule, which folds the sums into the operators'
+// stores) and S[3] (derivative); div_stages_z: the Z stage.
+static int div_zi(bool fast) { return fast ? 2 : 4; }
 static int div_stages_xy(pbx_handle_s *h, const double *i1, const double *i2, const double *i3,
                          bool fast = false)
 {
@@ -111,6 +115,10 @@ static int div_stages_xy(pbx_handle_s *h, const double *i1, const double *i2, co
     double *e3 = S[0];                                  // i1 (possibly S[0]) is consumed by now
     PBX_TRY(line_op(h, 0, OP_INTERP, F, i3, e3, fast));       // dfe3
     PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));   // dff1
+    if (fast) {
+        PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast, 0, S[1]));   // dff1 + dff2 (:249)
+        return line_op(h, 1, OP_INTERP, F, e3, S[3], fast);              // dff3
+    }
     PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast));    // dff2
     PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3], fast));     // dff3
     return ref_add(h->stream, N, S[1], S[2], S[4], &h->launches);   // :249
@@ -121,8 +129,9 @@ static int div_stages_z(pbx_handle_s *h, double *out, bool fast = false)
     double **S = h->scratch;
     const int F = PBX_STAGGER_FORWARD;
     const size_t N = (size_t)h->nx * h->ny * h->nz;
-    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[4], S[0], fast, 0));   // dfc
-    // the z derivative goes to a scratch field first: FAST line operators cannot run in place
+    PBX_TRY(line_op(h, 2, OP_INTERP, F, S[div_zi(fast)], S[0], fast, 0));   // dfc
+    if (fast) return line_op(h, 2, OP_DERIV, F, S[3], out, fast, 1, S[0]);    // df + dfc (:251)
+    // the z derivative goes to a scratch field first: the sum is a separate, reference-order step
     PBX_TRY(line_op(h, 2, OP_DERIV, F, S[3], S[1], fast, 1));    // df
     return ref_add(h->stream, N, S[1], S[0], out, &h->launches);    // :251
 }
@@ -177,7 +186,7 @@ int slab_op_phase1(pbx_handle_s *h, int op, const double *in)
         return line_boundary(h, 1, OP_DERIV, PBX_STAGGER_BACKWARD, in);
     case PBX_OP_DIV:
         PBX_TRY(div_stages_xy(h, in, in + N, in + 2 * N, true));
-        PBX_TRY(line_boundary(h, 0, OP_INTERP, PBX_STAGGER_FORWARD, h->scratch[4]));
+        PBX_TRY(line_boundary(h, 0, OP_INTERP, PBX_STAGGER_FORWARD, h->scratch[div_zi(true)]));
         return line_boundary(h, 1, OP_DERIV, PBX_STAGGER_FORWARD, h->scratch[3]);
     case PBX_OP_INTERP:
         return line_boundary(h, 0, OP_INTERP, PBX_STAGGER_BACKWARD, in);

@@ -173,7 +173,8 @@ struct LYZ {
 template <bool SLAB>
 __global__ void __launch_bounds__(NT, 3)
 lineop_yz_kernel(const __grid_constant__ LYZ p, const __grid_constant__ SlabMsg zo,
-                 const double *__restrict__ in, double *__restrict__ out)
+                 const double *__restrict__ in, const double *__restrict__ addend,
+                 double *__restrict__ out)
 {
     __shared__ double sm[10 * NT];
     const int tx = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
@@ -214,8 +215,13 @@ lineop_yz_kernel(const __grid_constant__ LYZ p, const __grid_constant__ SlabMsg 
         solve1_chunk(p.op.cc, xc, 0, v, BarAll());
     }
     if (live && sc.interior) {
+        if (addend != nullptr) {   // out = op(in) + addend: the sums of div (compact_schemes.f90:249, 251)
 #pragma unroll
-        for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
+            for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k] + __ldg(addend + base + k * p.sl);
+        } else {
+#pragma unroll
+            for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
+        }
     }
 }
 
@@ -352,7 +358,7 @@ int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger,
 // one 1-D compact operator along dir on a brick the FAST schedule supports (fast_supported())
 int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
                  const double *in, double *out, long long *launches, const double *from_lo,
-                 const double *from_up)
+                 const double *from_up, const double *addend)
 {
     if (in == out || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
         set_last_error("FAST line operators need distinct, 16-byte aligned input and output");
@@ -360,6 +366,7 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
     }
     const LineOp op = make_line_op(kind, stagger, dx);
     if (from_lo && (dir != 2 || !from_up)) return PBX_ERR_ARG;
+    if (addend && (dir == 0 || addend == out || (reinterpret_cast<uintptr_t>(addend) & 15))) return PBX_ERR_ARG;
     if (dir == 0) {
         LX p;
         p.op = op;
@@ -399,9 +406,9 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
             zo.from_lo = from_lo;
             zo.from_up = from_up;
             zo.nlines = (long long)g.nx * g.ny;
-            lineop_yz_kernel<true><<<grid, block, 0, s>>>(p, zo, in, out);
+            lineop_yz_kernel<true><<<grid, block, 0, s>>>(p, zo, in, addend, out);
         } else {
-            lineop_yz_kernel<false><<<grid, block, 0, s>>>(p, SlabMsg(), in, out);
+            lineop_yz_kernel<false><<<grid, block, 0, s>>>(p, SlabMsg(), in, addend, out);
         }
     }
     if (launches) ++*launches;

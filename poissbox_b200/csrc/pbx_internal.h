@@ -204,7 +204,7 @@ int fast_zpass_max_partials(const Brick &g);
 // neighbours' messages produced by fast_line_boundary ([3][nx*ny] each)
 int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
                  const double *in, double *out, long long *launches, const double *from_lo = nullptr,
-                 const double *from_up = nullptr);
+                 const double *from_up = nullptr, const double *addend = nullptr);   // out = op(in) + addend (y, z)
 int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger, double dx,
                        const double *in, double *msg_dn, double *msg_up, long long *launches);
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
