@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace pbx_emu {
@@ -145,11 +146,27 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                             f->ctx.uc_link = nullptr;
                             makecontext(&f->ctx, fiber_entry, 0);
                         }
+                // Thread order within a scheduling round.  A fiber runs undisturbed from one switch point
+                // (barrier, shuffle, mbarrier wait) to the next, so the order decides which of two
+                // unsynchronised accesses between the same barriers happens first: a kernel without
+                // such races gives the same bits under every order (PBX_EMU_SCHED = 0 ascending,
+                // 1 descending, n >= 2 pseudo-random with seed n, reshuffled every round).
+                static const int sched = getenv("PBX_EMU_SCHED") ? atoi(getenv("PBX_EMU_SCHED")) : 0;
+                std::vector<int> order(nthr);
+                for (int i = 0; i < nthr; ++i) order[i] = sched == 1 ? nthr - 1 - i : i;
+                unsigned long long rng = 0x9E3779B97F4A7C15ull * (unsigned long long)(sched + 1) + bx + 131 * by + 7919 * bz;
                 int remaining = nthr;
                 while (remaining > 0) {
                     const unsigned long long before = g_progress;
                     remaining = 0;
-                    for (int i = 0; i < nthr; ++i) {
+                    if (sched >= 2) {
+                        for (int i = nthr - 1; i > 0; --i) {
+                            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                            std::swap(order[i], order[(int)((rng >> 33) % (unsigned)(i + 1))]);
+                        }
+                    }
+                    for (int oi = 0; oi < nthr; ++oi) {
+                        const int i = order[oi];
                         Fiber *f = g_pool[i];
                         if (f->done) continue;
                         g_cur = f;
