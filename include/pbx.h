@@ -128,6 +128,13 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n);
 #define PBX_OP_STAR 5        /* the 2nd-order star: one plane travels each way */
 int pbx_slab_op_phase1(pbx_handle h, int op, const double *in);
 int pbx_slab_op_phase2(pbx_handle h, int op, const double *in, double *out);
+/* For a host that owns the exchange itself (MPI, sockets, ...): after phase 1 copy the two outgoing
+ * messages out, move them to the neighbours by any means, install what arrived, run phase 2.
+ * Every message is pbx_slab_message_count doubles (nine planes of nx*ny); all pointers are device
+ * pointers; `up` goes to rank+1 (which installs it as from_lo), `dn` to rank-1 (as from_up). */
+int pbx_slab_message_count(pbx_handle h, long long *count);
+int pbx_slab_get_messages(pbx_handle h, double *up, double *dn);
+int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *from_up);
 /* the same exchange over the handle's NCCL communicator, and the CG's scalar all-reduce (exposed
  * for profiling the communication steps on their own) */
 int pbx_slab_exchange(pbx_handle h);

@@ -45,6 +45,9 @@ SIGNATURES = {
     "pbx_slab_exchange_local": (c_int, [ctypes.POINTER(c_void_p), c_int]),
     "pbx_slab_op_phase1": (c_int, [c_void_p, c_int, c_void_p]),
     "pbx_slab_op_phase2": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "pbx_slab_message_count": (c_int, [c_void_p, ctypes.POINTER(c_ll)]),
+    "pbx_slab_get_messages": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pbx_slab_put_messages": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_slab_exchange": (c_int, [c_void_p]),
     "pbx_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int]),
     "pbx_dist_tables_host": (c_int, [c_int, c_double, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),

@@ -526,6 +526,42 @@ int pbx_slab_exchange_local(pbx_handle *hs, int n)
     return PBX_OK;
 }
 
+// ---- exchange owned by the host: outgoing messages out, incoming messages in -------------------
+int pbx_slab_message_count(pbx_handle h, long long *count)
+{
+    if (!h || !h->dist || !count) return PBX_ERR_ARG;
+    *count = (long long)DIST_MSG * ((DistState *)h->dist)->nlines;
+    return PBX_OK;
+}
+
+int pbx_slab_get_messages(pbx_handle h, double *up, double *dn)
+{
+    if (!h || !h->dist || !up || !dn) return PBX_ERR_ARG;
+    DistState *d = (DistState *)h->dist;
+    if (d->peer_map_up) {
+        set_last_error("this handle stores its messages straight into the neighbours' memory");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    PBX_CUDA(cudaSetDevice(h->device));
+    const size_t by = (size_t)DIST_MSG * d->nlines * sizeof(double);
+    PBX_CUDA(cudaMemcpyAsync(up, d->send_up, by, cudaMemcpyDeviceToDevice, h->stream));
+    PBX_CUDA(cudaMemcpyAsync(dn, d->send_dn, by, cudaMemcpyDeviceToDevice, h->stream));
+    PBX_CUDA(cudaStreamSynchronize(h->stream));
+    return PBX_OK;
+}
+
+int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *from_up)
+{
+    if (!h || !h->dist || !from_lo || !from_up) return PBX_ERR_ARG;
+    DistState *d = (DistState *)h->dist;
+    PBX_CUDA(cudaSetDevice(h->device));
+    const size_t by = (size_t)DIST_MSG * d->nlines * sizeof(double);
+    const int par = (int)(d->epoch & 1);
+    PBX_CUDA(cudaMemcpyAsync(d->recv_lo[par], from_lo, by, cudaMemcpyDeviceToDevice, h->stream));
+    PBX_CUDA(cudaMemcpyAsync(d->recv_up[par], from_up, by, cudaMemcpyDeviceToDevice, h->stream));
+    return PBX_OK;
+}
+
 // the exchange step alone, over the handle's communicator (profiling aid)
 int pbx_slab_exchange(pbx_handle h)
 {

@@ -66,6 +66,19 @@ class Handle:
                                      self._field(out, 3 if op == _lib.OP_GRAD else 1)))
         return out
 
+    def slab_get_messages(self):
+        """the two outgoing messages of phase 1 (to rank+1, to rank-1) for a host-owned exchange"""
+        n = ctypes.c_longlong()
+        check(LIB.pbx_slab_message_count(self._h, ctypes.byref(n)))
+        up = self._torch.empty(n.value, dtype=self._torch.float64, device=f"cuda:{self.device}")
+        dn = self._torch.empty_like(up)
+        check(LIB.pbx_slab_get_messages(self._h, ctypes.c_void_p(up.data_ptr()), ctypes.c_void_p(dn.data_ptr())))
+        return up, dn
+
+    def slab_put_messages(self, from_lo, from_up):
+        check(LIB.pbx_slab_put_messages(self._h, ctypes.c_void_p(from_lo.data_ptr()),
+                                        ctypes.c_void_p(from_up.data_ptr())))
+
     @staticmethod
     def slab_exchange_local(handles):
         arr = (ctypes.c_void_p * len(handles))(*[h._h for h in handles])

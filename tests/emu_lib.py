@@ -167,6 +167,16 @@ class EmuHandle:
         check(self.lib, self.lib.pbx_slab_op_phase2(self._h, op, ptr(self._f), ptr(out)))
         return out
 
+    def slab_get_messages(self):
+        n = ctypes.c_longlong()
+        check(self.lib, self.lib.pbx_slab_message_count(self._h, ctypes.byref(n)))
+        up, dn = np.empty(n.value), np.empty(n.value)
+        check(self.lib, self.lib.pbx_slab_get_messages(self._h, ptr(up), ptr(dn)))
+        return up, dn
+
+    def slab_put_messages(self, from_lo, from_up):
+        check(self.lib, self.lib.pbx_slab_put_messages(self._h, ptr(from_lo), ptr(from_up)))
+
     @staticmethod
     def slab_exchange_local(handles):
         lib = handles[0].lib

@@ -66,3 +66,20 @@ def test_slab_protocol_gloo_world2():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ZSLAB_OK" in o, o
+
+
+def test_slab_kernels_gloo_world2():
+    """two processes, gloo, and the library's own slab kernels (on the CPU kernel-logic harness):
+    Laplacian, grad, div, interp and star with the exchange owned by the host
+    (pbx_slab_get_messages / send-recv / pbx_slab_put_messages), plus the CG's all-reduced dot"""
+    import emu_lib
+
+    emu_lib.load()   # build once before the ranks start
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "emu_gloo_worker.py"), str(r), "2"],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "EMU_GLOO_OK" in o, o

@@ -74,6 +74,31 @@ def test_slab_grad_div_interp_match_single_brick(shape, P):
         h.close()
 
 
+def test_slab_host_owned_exchange():
+    """the exchange owned by the host: pbx_slab_get_messages / pbx_slab_put_messages instead of
+    pbx_slab_exchange_local (what an MPI host does between phase 1 and phase 2)"""
+    import torch
+
+    nx, ny, nz, P = 64, 32, 128, 2
+    nzl = nz // P
+    dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    whole = pbx.Handle(nx, ny, nz, dx)
+    ref = whole.lapl(f)
+    slabs = [pbx.Handle(nx, ny, nzl, dx, slab=(r, P)) for r in range(P)]
+    for r, h in enumerate(slabs):
+        h.slab_phase1(f[r * nzl:(r + 1) * nzl].contiguous())
+    msgs = [h.slab_get_messages() for h in slabs]          # (to rank+1, to rank-1)
+    for r, h in enumerate(slabs):
+        h.slab_put_messages(msgs[(r - 1) % P][0], msgs[(r + 1) % P][1])
+    out = torch.cat([h.slab_phase2() for h in slabs], dim=0)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() <= 1e-13 * ref.abs().max().item()
+    for h in slabs + [whole]:
+        h.close()
+
+
 def test_slab_needs_64_to_512_planes():
     for nzl in (48, 528):
         with pytest.raises(pbx.PbxError) as e:
