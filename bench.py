@@ -366,24 +366,27 @@ def run_ours(args):
         # role of the reference's `-pc_type gamg` on P); single GPU.  Reported beside the headline,
         # which stays the reference's unpreconditioned configuration.
         if world == 1:
-            from poissbox_b200 import _lib as _pl
+            try:
+                from poissbox_b200 import _lib as _pl
 
-            h2.set_pc(_pl.PC_MG, 2)
-            h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=2)
-            torch.cuda.synchronize()
-            l1 = h2.launches
-            t0 = time.perf_counter()
-            x, its, rnorm, reason, hist = h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=args.cg_maxit)
-            torch.cuda.synchronize()
-            dtp = time.perf_counter() - t0
-            rres = h2.lapl(x) - b
-            true_rel = float(torch.sqrt((rres * rres).sum() / (b * b).sum()).item())
-            del rres
-            cg["multigrid_pc"] = {"pc": "V(2,2) geometric multigrid on the 2nd-order star, damped Jacobi",
-                                  "time_s": dtp, "its": its, "reason": reason,
-                                  "rnorm_rel": rnorm / hist[0] if hist[0] else 0.0,
-                                  "true_residual_rel": true_rel, "ms_per_it": dtp / max(1, its) * 1e3,
-                                  "speedup_vs_pc_none": dt / dtp, "gpu_launches": h2.launches - l1}
+                h2.set_pc(_pl.PC_MG, 2)
+                h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=2)
+                torch.cuda.synchronize()
+                l1 = h2.launches
+                t0 = time.perf_counter()
+                x, its, rnorm, reason, hist = h2.cg_solve(b, x, rtol=args.cg_rtol, maxit=args.cg_maxit)
+                torch.cuda.synchronize()
+                dtp = time.perf_counter() - t0
+                rres = h2.lapl(x) - b
+                true_rel = float(torch.sqrt((rres * rres).sum() / (b * b).sum()).item())
+                del rres
+                cg["multigrid_pc"] = {"pc": "V(2,2) geometric multigrid on the 2nd-order star, damped Jacobi",
+                                      "time_s": dtp, "its": its, "reason": reason,
+                                      "rnorm_rel": rnorm / hist[0] if hist[0] else 0.0,
+                                      "true_residual_rel": true_rel, "ms_per_it": dtp / max(1, its) * 1e3,
+                                      "speedup_vs_pc_none": dt / dtp, "gpu_launches": h2.launches - l1}
+            except Exception as exc:   # the optional leg must never cost the headline line
+                cg["multigrid_pc"] = {"error": repr(exc)}
         h2.close()
         del b, x
 
