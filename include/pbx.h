@@ -135,8 +135,24 @@ int pbx_slab_op_phase2(pbx_handle h, int op, const double *in, double *out);
 int pbx_slab_message_count(pbx_handle h, long long *count);
 int pbx_slab_get_messages(pbx_handle h, double *up, double *dn);
 int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *from_up);
-/* the same exchange over the handle's NCCL communicator, and the CG's scalar all-reduce (exposed
- * for profiling the communication steps on their own) */
+/* Peer boards: ranks that can store into one another's memory (slab handles of one process on
+ * one device or on peer-enabled devices; NVLink peer mappings the host has opened itself; in the
+ * tests, processes sharing a mapping) need neither NCCL nor a host-owned exchange.  Every rank owns
+ * a receive buffer of pbx_slab_recv_bytes bytes (pbx_slab_recv_buffer: the one the handle allocated;
+ * 128-byte aligned, zeroed), and pbx_slab_link_peers hands the handle all n of them, bufs[r] being
+ * rank r's buffer as addressable from this handle's device (bufs[rank]: its own; a pointer other
+ * than the handle's buffer replaces it and stays owned by the caller, who has zeroed it BEFORE any
+ * rank links).  From then on the boundary sweeps store their messages straight into the neighbours'
+ * buffers, the exchange is a flag barrier between neighbours, the CG's sums are all-reduced inside
+ * its reduction kernels, and pbx_lapl_device / pbx_grad_device / ... / pbx_cg_solve_device work on
+ * the handle as they do on one created with an NCCL communicator.  Each rank needs its own stream
+ * and host thread: the kernels wait on the device for their peers.  (With a communicator,
+ * PBX_PEER_SYNC=1 in the environment makes pbx_create set up the same thing over cudaIpc.) */
+int pbx_slab_recv_bytes(pbx_handle h, size_t *bytes);
+int pbx_slab_recv_buffer(pbx_handle h, void **buf);
+int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n);
+/* the exchange step alone (NCCL communicator or peer boards), and the CG's scalar all-reduce
+ * (exposed for profiling the communication steps on their own) */
 int pbx_slab_exchange(pbx_handle h);
 int pbx_allreduce_sum(pbx_handle h, double *dev, int count);
 int pbx_dist_tables_host(int nzl, double dz, int *ncs, int *nrow, int R[2], double *U,

@@ -498,7 +498,7 @@ int pbx_lapl_profile_device(pbx_handle h, const double *f, double *d2f, int reps
 // on a z-decomposed box: phase 1, the exchange over the communicator, phase 2
 static int slab_op(pbx_handle h, int op, const double *in, double *out)
 {
-    if (!h->comm) {
+    if (!dist_connected(h)) {
         set_last_error("slab handle without a communicator: drive it with pbx_slab_op_phase1/2");
         return PBX_ERR_UNSUPPORTED;
     }

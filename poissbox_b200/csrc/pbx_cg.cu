@@ -22,6 +22,7 @@
 #include <cmath>
 
 #include "pbx_internal.h"
+#include "pbx_peer.cuh"
 
 namespace pbx {
 
@@ -257,9 +258,8 @@ k_init_pc(size_t N, const double *__restrict__ b, double *__restrict__ x, double
 //   phase 5: mean of the updated residual (S1 about m0), the right-hand side's mean for the next PC
 //   phase 6: as phase 4 after an iteration: counts it, b = beta/beta_old, tests
 //   phase 7 / 8: SC_MEAN / SC_MZ = S1 / N (stand-alone preconditioner application)
-__global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
+__device__ void scalar_phase(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double N = sc[SC_NTOT];
     if (phase == 0) {
         sc[SC_M0] = sc[SC_S1] / N;
@@ -367,6 +367,42 @@ __global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict_
         sc[SC_STATUS] = PBX_DIVERGED_ITS;
 }
 
+__global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    scalar_phase(sc, phase, hist, nhist);
+}
+
+// Multi-rank CG over the peer boards: ONE kernel sums the per-CTA partials of `narr` arrays, all-
+// reduces the sums with the other ranks over NVLink (peer_exchange_sum: same bits on every rank)
+// and runs the scalar step `phase` of the loop on them -- what k_reduce + ncclAllReduce + k_scalar
+// do in three launches.  narr <= PEER_VALS; dst points into the scalar block.
+__global__ void __launch_bounds__(VT)
+k_reduce_peer(const double *__restrict__ part, int cnt, int stride, int narr, double *__restrict__ dst,
+              double *__restrict__ sc, int guarded, const __grid_constant__ PeerLinks L,
+              unsigned long long seq, int phase, double *__restrict__ hist, int nhist)
+{
+    __shared__ double sh[VT / 32];
+    __shared__ double mine[PEER_VALS];
+    __shared__ double all[PEER_MAXR][PEER_VALS];
+    // the status word is the same on every rank (it derives from all-reduced sums), so either all
+    // ranks skip this exchange or none does
+    if (guarded && sc[SC_STATUS] != 0.0) return;
+    for (int a = 0; a < narr; ++a) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < cnt; i += VT) s += part[a * stride + i];
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) mine[a] = s;
+        __syncthreads();
+    }
+    double res[PEER_VALS];
+    peer_exchange_sum(L, seq, mine, narr, all, res);
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < narr; ++a) dst[a] = res[a];
+        if (phase >= 0) scalar_phase(sc, phase, hist, nhist);
+    }
+}
+
 int vec_grid(size_t N)
 {
     size_t nb = (N + (size_t)VT * 8 - 1) / ((size_t)VT * 8);
@@ -403,6 +439,33 @@ int cg_alloc(pbx_handle_s *h, int maxit)
     return PBX_OK;
 }
 
+// Sums of `narr` arrays of per-CTA partials into dst[0 .. narr) (inside the scalar block), summed
+// over all ranks, followed by scalar step `phase` of the loop (phase < 0: none).  Single rank or
+// NCCL: k_reduce, ncclAllReduce, k_scalar.  Peer boards: the one fused kernel k_reduce_peer.
+int reduce_step(pbx_handle_s *h, const double *part, int cnt, int stride, int narr, double *dst,
+                int guarded, int phase)
+{
+    cudaStream_t s = h->stream;
+    double *sc = h->cg_scal;
+    PeerLinks L;
+    unsigned long long seq;
+    if (h->nranks > 1 && narr <= PEER_VALS && dist_peer_next(h, &L, &seq)) {
+        k_reduce_peer<<<1, VT, 0, s>>>(part, cnt, stride, narr, dst, sc, guarded, L, seq, phase,
+                                       h->cg_hist, h->cg_hist_cap);
+        ++h->launches;
+    } else {
+        k_reduce<<<1, VT, 0, s>>>(part, cnt, stride, narr, dst, sc, guarded);
+        ++h->launches;
+        if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, dst, narr));
+        if (phase >= 0) {
+            k_scalar<<<1, 1, 0, s>>>(sc, phase, h->cg_hist, h->cg_hist_cap);
+            ++h->launches;
+        }
+    }
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
 __global__ void k_dot_generic(size_t N, const double *__restrict__ a, const double *__restrict__ b,
                               double *__restrict__ part)
 {
@@ -415,8 +478,8 @@ __global__ void k_dot_generic(size_t N, const double *__restrict__ a, const doub
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
-// w = A p and the local part of p.w into dst (device)
-int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int guarded)
+// w = A p and p.w (over all ranks) into dst (device), then scalar step `phase` (< 0: none)
+int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int guarded, int phase)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     cudaStream_t s = h->stream;
@@ -438,10 +501,8 @@ int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int gu
         k_dot_generic<<<np, VT, 0, s>>>(N, p, w, h->cg_partials);
         ++h->launches;
     }
-    k_reduce<<<1, VT, 0, s>>>(h->cg_partials, np, np, 1, dst, h->cg_scal, guarded);
-    ++h->launches;
     PBX_CUDA(cudaGetLastError());
-    return PBX_OK;
+    return reduce_step(h, h->cg_partials, np, np, 1, dst, guarded, phase);
 }
 
 }  // namespace
@@ -463,9 +524,7 @@ void cg_free(pbx_handle_s *h)
 int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev)
 {
     PBX_TRY(cg_alloc(h, 1));
-    PBX_TRY(matmult_dot(h, f, out, dot_dev, 0));
-    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, dot_dev, 1));
-    return PBX_OK;
+    return matmult_dot(h, f, out, dot_dev, 0, -1);
 }
 
 // z = M^-1 (r - *mean) for the handle's preconditioner (no mean removal of z)
@@ -548,7 +607,7 @@ static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol,
     int issued = 0;
     while (!done && issued < maxit) {
         const int slot = issued & 1;
-        if ((rc = matmult_dot(h, p, w, sc + SC_PW, 1)) != PBX_OK) break;
+        if ((rc = matmult_dot(h, p, w, sc + SC_PW, 1, -1)) != PBX_OK) break;
         k_scalar<<<1, 1, 0, s>>>(sc, 2, nullptr, 0);
         k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
         k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 1);
@@ -620,16 +679,11 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
 
     // mean of b, then r = b, x = 0, p = z = b - mean, ||z||
     k_sum<<<nb, VT, 0, s>>>(N, b, part);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
-    h->launches += 2;
-    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, sc + SC_S1, 1));
-    k_scalar<<<1, 1, 0, s>>>(sc, 0, nullptr, 0);
-    k_init<<<nb, VT, 0, s>>>(N, b, x, r, p, sc, part, np);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 0);
-    h->launches += 3;
-    if (h->nranks > 1) PBX_TRY(dist_allreduce_sum(h, sc + SC_S1, 2));
-    k_scalar<<<1, 1, 0, s>>>(sc, 1, h->cg_hist, h->cg_hist_cap);
     ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 1, sc + SC_S1, 0, 0));
+    k_init<<<nb, VT, 0, s>>>(N, b, x, r, p, sc, part, np);
+    ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 2, sc + SC_S1, 0, 1));
     PBX_CUDA(cudaGetLastError());
 
     // The host runs one iteration ahead of the status it has seen: every kernel that changes
@@ -646,17 +700,13 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
     int issued = 0;
     while (!done && issued < maxit) {
         const int slot = issued & 1;
-        rc = matmult_dot(h, p, w, sc + SC_PW, 1);
+        rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2);
         if (rc != PBX_OK) break;
-        if (h->nranks > 1 && (rc = dist_allreduce_sum(h, sc + SC_PW, 1)) != PBX_OK) break;
-        k_scalar<<<1, 1, 0, s>>>(sc, 2, nullptr, 0);
         k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
-        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 1);
-        h->launches += 3;
-        if (h->nranks > 1 && (rc = dist_allreduce_sum(h, sc + SC_S1, 2)) != PBX_OK) break;
-        k_scalar<<<1, 1, 0, s>>>(sc, 3, h->cg_hist, h->cg_hist_cap);
+        ++h->launches;
+        if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;
         k_pupdate<<<vec_grid(N), VT, 0, s>>>(N, r, p, sc);
-        h->launches += 2;
+        ++h->launches;
         cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double),
                         cudaMemcpyDeviceToHost, s);
         cudaEventRecord(ev[slot], s);

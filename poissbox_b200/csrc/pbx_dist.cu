@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "pbx_internal.h"
+#include "pbx_peer.cuh"
 
 namespace pbx {
 
@@ -96,17 +97,28 @@ int nccl_fail(int e, const char *what)
 struct DistState {
     double *buf = nullptr;        // local send arrays (used when there is no peer mapping)
     double *send_up, *send_dn;    // [DIST_MSG][nlines]
-    double *rbuf = nullptr;       // receive arrays, 2 parities x (recv_lo, recv_up); shared by cudaIpc
+    // receive buffer: 2 parities x (recv_lo, recv_up), then the peer board; shared by cudaIpc or
+    // provided by the host (pbx_slab_link_peers)
+    double *rbuf = nullptr;
+    bool rbuf_owned = true;
     double *recv_lo[2], *recv_up[2];
-    // NVLink peer mappings of the neighbours' receive arrays (nullptr: use ncclSend/Recv)
-    void *peer_map_up = nullptr, *peer_map_lo = nullptr;
+    // mappings of the other ranks' receive buffers (cudaIpc over NVLink); nullptr: not mapped
+    void *peer_map[PEER_MAXR] = {nullptr};
     double *peer_up_recv_lo[2] = {nullptr, nullptr};   // where my "up" message lands in the upper rank
     double *peer_lo_recv_up[2] = {nullptr, nullptr};   // where my "down" message lands in the lower rank
+    // peer boards of ALL ranks mapped: barrier and all-reduce without NCCL (PeerBoard, pbx_internal.h)
+    bool peer_sync = false;
+    PeerLinks links;
+    unsigned long long ar_seq = 0, bar_seq = 0;
     double *sync_word = nullptr;  // device scalar all-reduced as the inter-rank barrier
     unsigned long long epoch = 0; // MatMult counter: parity selects the receive arrays
     long long nlines = 0;
     int lower = 0, upper = 0;
     ZOpen zo;                     // constants of the slab z pass
+    size_t per() const { return (size_t)DIST_MSG * (size_t)nlines; }
+    size_t board_offset() const { return (4 * per() * sizeof(double) + 127) & ~(size_t)127; }
+    size_t recv_bytes() const { return board_offset() + sizeof(PeerBoard); }
+    bool peer_stores() const { return peer_up_recv_lo[0] != nullptr; }
 };
 
 namespace {
@@ -198,7 +210,86 @@ k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
     }
 }
 
+
+// Neighbour barrier of the slab exchange over the peer boards: the boundary sweep that precedes this
+// kernel on the stream has stored my messages into the neighbours' receive arrays; publish that
+// (release at system scope: the stores of the earlier kernel happen before it) and wait until both
+// neighbours have published theirs.  One thread.
+__global__ void k_peer_barrier(const __grid_constant__ PeerLinks L, unsigned long long seq)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ptx::fence_sys();
+    ptx::st_release_sys(&L.board[L.upper]->bar_from_lo, seq);
+    ptx::st_release_sys(&L.board[L.lower]->bar_from_up, seq);
+    const PeerBoard *mine = L.board[L.rank];
+    const long long t0 = ptx::spin_start();
+    while (ptx::ld_acquire_sys(&mine->bar_from_lo) < seq || ptx::ld_acquire_sys(&mine->bar_from_up) < seq)
+        ptx::spin_pause(t0);
+}
+
+// All-reduce (sum) of count <= PEER_VALS doubles over the peer boards, in place.  One CTA of
+// PEER_MAXR threads at least; thread r talks to rank r.  (The CG folds the same exchange into its
+// reduction kernel, pbx_cg.cu; this stand-alone version serves pbx_allreduce_sum.)
+__global__ void k_peer_allreduce(const __grid_constant__ PeerLinks L, unsigned long long seq,
+                                 double *__restrict__ v, int count)
+{
+    __shared__ double all[PEER_MAXR][PEER_VALS];
+    __shared__ double mine[PEER_VALS];
+    if ((int)threadIdx.x < count) mine[threadIdx.x] = v[threadIdx.x];
+    __syncthreads();
+    double res[PEER_VALS];
+    peer_exchange_sum(L, seq, mine, count, all, res);
+    if (threadIdx.x == 0)
+        for (int a = 0; a < count; ++a) v[a] = res[a];
+}
+
 }  // namespace
+
+static void close_peer_maps(DistState *d)
+{
+    for (int r = 0; r < PEER_MAXR; ++r) {
+        if (!d->peer_map[r]) continue;
+        cudaIpcCloseMemHandle(d->peer_map[r]);
+        for (int q = r + 1; q < PEER_MAXR; ++q)
+            if (d->peer_map[q] == d->peer_map[r]) d->peer_map[q] = nullptr;
+        d->peer_map[r] = nullptr;
+    }
+    d->peer_sync = false;
+    for (int par = 0; par < 2; ++par) d->peer_up_recv_lo[par] = d->peer_lo_recv_up[par] = nullptr;
+}
+
+static void set_recv_pointers(DistState *d)
+{
+    const size_t per = d->per();
+    for (int par = 0; par < 2; ++par) {
+        d->recv_lo[par] = d->rbuf + (size_t)(2 * par) * per;
+        d->recv_up[par] = d->rbuf + (size_t)(2 * par + 1) * per;
+    }
+}
+
+// bufs[r]: rank r's receive buffer as addressable from this device (bufs[rank] = my own).  With
+// only the two neighbours given the boundary sweep stores its messages straight into their
+// memory; with ALL ranks given the peer boards take over the barrier and the all-reduce as well.
+static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs)
+{
+    const size_t per = d->per();
+    for (int par = 0; par < 2; ++par) {
+        d->peer_up_recv_lo[par] = (double *)bufs[d->upper] + (size_t)(2 * par) * per;
+        d->peer_lo_recv_up[par] = (double *)bufs[d->lower] + (size_t)(2 * par + 1) * per;
+    }
+    bool all = h->nranks <= PEER_MAXR;
+    for (int r = 0; r < h->nranks && all; ++r) all = bufs[r] != nullptr;
+    d->peer_sync = false;
+    if (!all) return;
+    PeerLinks &L = d->links;
+    for (int r = 0; r < PEER_MAXR; ++r)
+        L.board[r] = r < h->nranks ? (PeerBoard *)((char *)bufs[r] + d->board_offset()) : nullptr;
+    L.n = h->nranks;
+    L.rank = h->rank;
+    L.lower = d->lower;
+    L.upper = d->upper;
+    d->peer_sync = true;
+}
 
 int dist_setup(pbx_handle_s *h, int rank, int nranks)
 {
@@ -221,12 +312,9 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
     PBX_CUDA(cudaMemset(d->buf, 0, 2 * per * sizeof(double)));
     d->send_up = d->buf;
     d->send_dn = d->buf + per;
-    PBX_CUDA(cudaMalloc(&d->rbuf, 4 * per * sizeof(double)));
-    PBX_CUDA(cudaMemset(d->rbuf, 0, 4 * per * sizeof(double)));
-    for (int par = 0; par < 2; ++par) {
-        d->recv_lo[par] = d->rbuf + (size_t)(2 * par) * per;
-        d->recv_up[par] = d->rbuf + (size_t)(2 * par + 1) * per;
-    }
+    PBX_CUDA(cudaMalloc(&d->rbuf, d->recv_bytes()));
+    PBX_CUDA(cudaMemset(d->rbuf, 0, d->recv_bytes()));
+    set_recv_pointers(d);
     PBX_CUDA(cudaMalloc(&d->sync_word, sizeof(double)));
     PBX_CUDA(cudaMemset(d->sync_word, 0, sizeof(double)));
     d->lower = (rank + nranks - 1) % nranks;
@@ -263,7 +351,7 @@ int dist_attach(pbx_handle_s *h)
     // Any failure leaves the ncclSend/Recv path in place.
     DistState *d = (DistState *)h->dist;
     const char *e = getenv("PBX_NO_PEER");
-    if (e && e[0] == '1') return PBX_OK;
+    if ((e && e[0] == '1') || n > PEER_MAXR) return PBX_OK;
     cudaIpcMemHandle_t mine;
     if (cudaIpcGetMemHandle(&mine, d->rbuf) != cudaSuccess) {
         cudaGetLastError();
@@ -283,12 +371,16 @@ int dist_attach(pbx_handle_s *h)
         cudaGetLastError();
         return PBX_OK;
     }
-    bool ok = cudaIpcOpenMemHandle(&d->peer_map_up, all[d->upper], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-    if (ok) {
-        if (d->lower == d->upper)
-            d->peer_map_lo = d->peer_map_up;
-        else
-            ok = cudaIpcOpenMemHandle(&d->peer_map_lo, all[d->lower], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    // PBX_PEER_SYNC=1: map EVERY rank's buffer, so that the barrier of the exchange and the CG's
+    // all-reduces run over the peer boards (no NCCL call inside an iteration); otherwise the two
+    // neighbours only (messages by peer stores, a one-word ncclAllReduce as the barrier)
+    const char *ps = getenv("PBX_PEER_SYNC");
+    const bool want_all = ps && ps[0] == '1' && n <= PEER_MAXR;
+    bool ok = true;
+    for (int r = 0; r < n && ok; ++r) {
+        if (r == h->rank) continue;
+        if (!want_all && r != d->upper && r != d->lower) continue;
+        ok = cudaIpcOpenMemHandle(&d->peer_map[r], all[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
     }
     // every rank must take the same path: agree on success with an all-reduce
     double flag = ok ? 0.0 : 1.0;
@@ -298,17 +390,13 @@ int dist_attach(pbx_handle_s *h)
     PBX_CUDA(cudaStreamSynchronize(h->stream));
     cudaGetLastError();
     if (flag != 0.0) {
-        if (d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_up);
-        if (d->peer_map_lo && d->peer_map_lo != d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_lo);
-        d->peer_map_up = d->peer_map_lo = nullptr;
+        close_peer_maps(d);
         cudaGetLastError();
         return PBX_OK;
     }
-    const size_t per = (size_t)DIST_MSG * d->nlines;
-    for (int par = 0; par < 2; ++par) {
-        d->peer_up_recv_lo[par] = (double *)d->peer_map_up + (size_t)(2 * par) * per;
-        d->peer_lo_recv_up[par] = (double *)d->peer_map_lo + (size_t)(2 * par + 1) * per;
-    }
+    void *bufs[PEER_MAXR] = {nullptr};
+    for (int r = 0; r < n; ++r) bufs[r] = r == h->rank ? (void *)d->rbuf : d->peer_map[r];
+    set_peer_pointers(h, d, bufs);
     return PBX_OK;
 }
 
@@ -316,24 +404,50 @@ void dist_free(pbx_handle_s *h)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return;
-    if (d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_up);
-    if (d->peer_map_lo && d->peer_map_lo != d->peer_map_up) cudaIpcCloseMemHandle(d->peer_map_lo);
+    close_peer_maps(d);
     if (d->buf) cudaFree(d->buf);
-    if (d->rbuf) cudaFree(d->rbuf);
+    if (d->rbuf && d->rbuf_owned) cudaFree(d->rbuf);
     if (d->sync_word) cudaFree(d->sync_word);
     delete d;
     h->dist = nullptr;
 }
 
+bool dist_connected(const pbx_handle_s *h)
+{
+    const DistState *d = (const DistState *)h->dist;
+    return h->comm != nullptr || (d && d->peer_sync);
+}
+
+bool dist_peer_next(pbx_handle_s *h, PeerLinks *L, unsigned long long *seq)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || !d->peer_sync) return false;
+    *L = d->links;
+    *seq = ++d->ar_seq;
+    return true;
+}
+
 int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
 {
     if (h->nranks <= 1) return PBX_OK;
-    if (!h->comm) {
+    if (!dist_connected(h)) {
         set_last_error("this slab handle has no communicator (phase-driven handles cannot reduce)");
         return PBX_ERR_UNSUPPORTED;
     }
     static const bool skip = getenv("PBX_DEBUG_NO_ALLREDUCE") != nullptr;   // timing experiments only
     if (skip) return PBX_OK;
+    PeerLinks L;
+    unsigned long long seq;
+    if (count <= PEER_VALS && dist_peer_next(h, &L, &seq)) {
+        k_peer_allreduce<<<1, 32, 0, h->stream>>>(L, seq, dev, count);
+        ++h->launches;
+        PBX_CUDA(cudaGetLastError());
+        return PBX_OK;
+    }
+    if (!h->comm) {
+        set_last_error("peer-board all-reduce carries at most PEER_VALS doubles");
+        return PBX_ERR_UNSUPPORTED;
+    }
     PBX_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->comm,
                               h->stream));
     return PBX_OK;
@@ -408,12 +522,20 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
     return fast_pass(h, 2, S[0], S[1], out, nullptr, p, partials, &zo);
 }
 
-static int dist_exchange_nccl(pbx_handle_s *h)
+static int dist_exchange_run(pbx_handle_s *h)
 {
     DistState *d = (DistState *)h->dist;
+    if (d->peer_sync) {
+        // messages already stored into the neighbours' arrays; flags on the peer boards order the
+        // neighbours' boundary sweeps before my z pass
+        k_peer_barrier<<<1, 32, 0, h->stream>>>(d->links, ++d->bar_seq);
+        ++h->launches;
+        PBX_CUDA(cudaGetLastError());
+        return PBX_OK;
+    }
     ncclComm_t c = (ncclComm_t)h->comm;
     const int par = (int)(d->epoch & 1);
-    if (d->peer_map_up) {
+    if (d->peer_stores()) {
         // the boundary sweep has already stored into the neighbours' arrays over NVLink; a
         // one-word all-reduce is the barrier that orders their kernels before my z pass
         PBX_NCCL(g_nccl.AllReduce(d->sync_word, d->sync_word, 1, ncclFloat64, ncclSum, c, h->stream));
@@ -431,13 +553,13 @@ static int dist_exchange_nccl(pbx_handle_s *h)
 
 int dist_exchange(pbx_handle_s *h)
 {
-    if (!h->dist || !h->comm) return PBX_ERR_ARG;
-    return dist_exchange_nccl(h);
+    if (!h->dist || !dist_connected(h)) return PBX_ERR_ARG;
+    return dist_exchange_run(h);
 }
 
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)
 {
-    if (!h->comm) {
+    if (!dist_connected(h)) {
         set_last_error("slab handle without a communicator: drive it with pbx_slab_phase1/2");
         return PBX_ERR_UNSUPPORTED;
     }
@@ -447,7 +569,7 @@ int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, do
     }
     PBX_TRY(dist_phase1(h, f));
     static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;   // timing experiments only
-    if (!skipx) PBX_TRY(dist_exchange_nccl(h));
+    if (!skipx) PBX_TRY(dist_exchange_run(h));
     return dist_phase2(h, out, p, partials);
 }
 
@@ -538,7 +660,7 @@ int pbx_slab_get_messages(pbx_handle h, double *up, double *dn)
 {
     if (!h || !h->dist || !up || !dn) return PBX_ERR_ARG;
     DistState *d = (DistState *)h->dist;
-    if (d->peer_map_up) {
+    if (d->peer_stores()) {
         set_last_error("this handle stores its messages straight into the neighbours' memory");
         return PBX_ERR_UNSUPPORTED;
     }
@@ -562,12 +684,54 @@ int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *fro
     return PBX_OK;
 }
 
+// ---- peer boards linked by the host --------------------------------------------------------------
+int pbx_slab_recv_bytes(pbx_handle h, size_t *bytes)
+{
+    if (!h || !h->dist || !bytes) return PBX_ERR_ARG;
+    *bytes = ((DistState *)h->dist)->recv_bytes();
+    return PBX_OK;
+}
+
+int pbx_slab_recv_buffer(pbx_handle h, void **buf)
+{
+    if (!h || !h->dist || !buf) return PBX_ERR_ARG;
+    *buf = ((DistState *)h->dist)->rbuf;
+    return PBX_OK;
+}
+
+int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n)
+{
+    if (!h || !h->dist || !bufs || n != h->nranks || n < 2) return PBX_ERR_ARG;
+    if (n > PEER_MAXR) {
+        set_last_error("peer boards serve at most 16 ranks");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    for (int r = 0; r < n; ++r)
+        if (!bufs[r] || (reinterpret_cast<uintptr_t>(bufs[r]) & 127)) return PBX_ERR_ARG;
+    DistState *d = (DistState *)h->dist;
+    PBX_CUDA(cudaSetDevice(h->device));
+    if (d->peer_stores() && d->peer_map[d->upper]) {
+        set_last_error("this handle is already linked to its peers over cudaIpc");
+        return PBX_ERR_UNSUPPORTED;
+    }
+    if (bufs[h->rank] != (void *)d->rbuf) {
+        // the host provides my receive buffer (e.g. memory it shares with the other ranks)
+        PBX_CUDA(cudaStreamSynchronize(h->stream));
+        if (d->rbuf_owned) cudaFree(d->rbuf);
+        d->rbuf = (double *)bufs[h->rank];
+        d->rbuf_owned = false;
+        set_recv_pointers(d);
+    }
+    set_peer_pointers(h, d, bufs);
+    return PBX_OK;
+}
+
 // the exchange step alone, over the handle's communicator (profiling aid)
 int pbx_slab_exchange(pbx_handle h)
 {
-    if (!h || !h->dist || !h->comm) return PBX_ERR_ARG;
+    if (!h || !h->dist || !dist_connected(h)) return PBX_ERR_ARG;
     PBX_CUDA(cudaSetDevice(h->device));
-    return dist_exchange_nccl(h);
+    return dist_exchange_run(h);
 }
 
 // sum `count` device doubles over the handle's communicator, in place (profiling aid)

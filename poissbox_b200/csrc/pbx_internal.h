@@ -149,6 +149,34 @@ struct ZOpen {
     double rinv = 0;                                // 1 / r of the interpolation recursion
 };
 
+// Peer boards (pbx_dist.cu): a small block of flags and records at the end of every rank's receive
+// buffer, stored into by the other ranks over NVLink peer mappings (or, for slab handles linked by
+// the host with pbx_slab_link_peers, through whatever shared mapping the host provides).  With the
+// boards in place the ranks synchronise and reduce among themselves without NCCL:
+//   * neighbour barrier of the slab exchange: each rank stores a sequence number into its two
+//     neighbours' boards after its boundary sweep and waits for theirs;
+//   * all-reduce of up to PEER_VALS doubles: every rank stores its partial into record
+//     [seq % PEER_RING][rank] of EVERY board, waits for all records of its own board and sums them
+//     in rank order -- the same bits on every rank.  A rank can be at most one reduction ahead of
+//     the slowest one, so a ring of PEER_RING records is never overrun.
+constexpr int PEER_MAXR = 16;
+constexpr int PEER_RING = 4;
+constexpr int PEER_VALS = 4;
+struct PeerRec {
+    double v[PEER_VALS];
+    unsigned long long seq;
+    unsigned long long pad_[3];
+};
+struct PeerBoard {
+    unsigned long long bar_from_lo, pad0_[15];
+    unsigned long long bar_from_up, pad1_[15];
+    PeerRec rec[PEER_RING][PEER_MAXR];
+};
+struct PeerLinks {
+    PeerBoard *board[PEER_MAXR];   // board[r]: rank r's board as addressable from this device
+    int n, rank, lower, upper;
+};
+
 // Long lines.  A CTA holds at most SEG_T chunks (512 points) of a y or z line.  A longer line is cut
 // into segments of `iseg` chunks that are computed independently as OPEN lines of SEG_T chunks:
 // `hlo` halo chunks below and the rest above the segment are loaded (wrapping around the periodic
@@ -301,4 +329,8 @@ int dist_line_msgs(pbx_handle_s *h, int slot, const double **from_lo, const doub
 int dist_exchange(pbx_handle_s *h);                                            // over the communicator
 // sum `count` doubles in place over the handle's communicator (no-op for a single rank)
 int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count);
+// true when the handle can talk to the other ranks (NCCL communicator or linked peer boards)
+bool dist_connected(const pbx_handle_s *h);
+// peer boards in place: fills *L and the sequence number of the next all-reduce, returns true
+bool dist_peer_next(pbx_handle_s *h, PeerLinks *L, unsigned long long *seq);
 }  // namespace pbx

@@ -104,5 +104,40 @@ __device__ __forceinline__ void fence_mbar_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+
+// ---- system-scope flags in peer-mapped (NVLink) or local global memory -------------------------
+// A rank publishes data with plain stores followed by st_release_sys of a sequence number; the
+// owner of the memory spins on ld_acquire_sys of that word (its own L2 is the point of coherence
+// for the peers' stores) and then reads the data with ld_relaxed_sys (never through L1).
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// bounded spin: a peer that never shows up traps the kernel (after ~2 minutes) instead of hanging
+// the GPU for good
+__device__ __forceinline__ long long spin_start() { return clock64(); }
+__device__ __forceinline__ void spin_pause(long long t0)
+{
+    __nanosleep(40);
+    if (clock64() - t0 > 240000000000LL) __trap();
+}
+
 }  // namespace ptx
 }  // namespace pbx

@@ -84,6 +84,23 @@ class Handle:
         arr = (ctypes.c_void_p * len(handles))(*[h._h for h in handles])
         check(LIB.pbx_slab_exchange_local(arr, len(handles)))
 
+    @staticmethod
+    def slab_link_local(handles):
+        """Peer boards (include/pbx.h, pbx_slab_link_peers) for a ring of slab handles living in ONE
+        process on one device (or peer-enabled devices): afterwards every handle works like one
+        created with a communicator -- lapl / grad / div / interp / cg_solve exchange and reduce
+        among themselves on the device.  Each handle needs its own stream (set_stream) and its own
+        host thread, because its kernels wait on the device for the other ranks'."""
+        n = len(handles)
+        bufs = []
+        for h in handles:
+            p = ctypes.c_void_p()
+            check(LIB.pbx_slab_recv_buffer(h._h, ctypes.byref(p)))
+            bufs.append(p.value)
+        arr = (ctypes.c_void_p * n)(*bufs)
+        for h in handles:
+            check(LIB.pbx_slab_link_peers(h._h, arr, n))
+
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self):
         if self._h:

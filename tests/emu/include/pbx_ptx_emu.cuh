@@ -5,7 +5,10 @@
 
 #include <cuda.h>
 
+#include <sched.h>
+
 #include <cstdint>
+#include <ctime>
 
 #include "pbx_emu.h"
 
@@ -147,6 +150,27 @@ inline void tma_wait_read0() {}
 inline void tma_wait_all0() {}
 inline void fence_proxy_async() {}
 inline void fence_mbar_init() {}
+
+
+// system-scope flags: the "peers" of the harness are other PROCESSES sharing the memory (mmap),
+// so these are real atomics; a spinning thread yields the CPU and gives up after two minutes
+inline void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+inline unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+inline void st_relaxed_sys(double *p, double v) { *(volatile double *)p = v; }
+inline double ld_relaxed_sys(const double *p) { return *(const volatile double *)p; }
+inline void fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline long long spin_start() { return (long long)time(nullptr); }
+inline void spin_pause(long long t0)
+{
+    sched_yield();
+    if ((long long)time(nullptr) - t0 > 120) pbx_emu::die("peer flag never arrived");
+}
 
 }  // namespace ptx
 }  // namespace pbx

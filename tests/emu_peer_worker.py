@@ -1,0 +1,113 @@
+"""worker of test_zslab_cpu.py::test_peer_boards_world*: one process per rank; the ranks share their
+receive buffers (POSIX shared memory standing in for NVLink peer mappings), link them with
+pbx_slab_link_peers and from then on run the library's own multi-rank code paths on the CPU
+kernel-logic harness (tests/emu) WITHOUT any host-side exchange: boundary sweeps storing into the
+neighbours' buffers, the flag barrier, the all-reduce inside the CG's reduction kernel.  gloo is
+only the rendezvous (and the referee of the final verdict)."""
+import ctypes
+import os
+import sys
+from multiprocessing import resource_tracker, shared_memory
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import emu_lib
+from poissbox_b200 import _lib
+
+rank, world, tag = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+nx, ny, nzl = 16, 16, 64
+nz = nzl * world
+dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+rng = np.random.default_rng(4242)
+f = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz)))
+v = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz, 3)))
+mine = slice(rank * nzl, (rank + 1) * nzl)
+h = emu_lib.EmuHandle(nx, ny, nzl, dx, slab=(rank, world))
+lib = h.lib
+
+# every rank creates its own (zero-filled) segment, then maps everybody's
+nbytes = ctypes.c_size_t()
+emu_lib.check(lib, lib.pbx_slab_recv_bytes(h._h, ctypes.byref(nbytes)))
+own = shared_memory.SharedMemory(name=f"pbxpeer_{tag}_{rank}", create=True, size=nbytes.value)
+dist.barrier()
+segs = [own if r == rank else shared_memory.SharedMemory(name=f"pbxpeer_{tag}_{r}") for r in range(world)]
+for r, sgm in enumerate(segs):
+    if r != rank:   # only the creator unlinks (Python < 3.13 registers attachments as well)
+        resource_tracker.unregister(sgm._name, "shared_memory")
+addr = [ctypes.addressof(ctypes.c_char.from_buffer(s.buf)) for s in segs]
+bufs = (ctypes.c_void_p * world)(*addr)
+emu_lib.check(lib, lib.pbx_slab_link_peers(h._h, bufs, world))
+dist.barrier()
+
+errs = {}
+whole = emu_lib.EmuHandle(nx, ny, nz, dx)
+ref = whole.lapl(f)
+for rep in range(3):   # three rounds: both parities of the receive arrays and a reused one
+    out = h.lapl(np.asfortranarray(f[:, :, mine]))
+    errs[f"lapl{rep}"] = np.max(np.abs(out - ref[:, :, mine])) / np.max(np.abs(ref))
+for name, fn, src, want in (("grad", h.grad, f, whole.grad(f)), ("div", h.div, v, whole.div(v)),
+                            ("interp", h.interp, f, whole.interp(f)), ("star", h.star, f, whole.star(f))):
+    got = fn(np.asfortranarray(src[:, :, mine]))
+    errs[name] = np.max(np.abs(got - want[:, :, mine])) / np.max(np.abs(want))
+# the fused z pass + dot + all-reduce
+_, dot = h.lapl_dot(np.asfortranarray(f[:, :, mine]))
+ref_dot = float(np.vdot(f, ref))
+errs["dot"] = abs(dot - ref_dot) / abs(ref_dot)
+# the stand-alone all-reduce: every rank must see the same bits
+vals = np.array([rank + 1.0, 0.1 * (rank + 1), -3.0, 1e-3 * rank])
+emu_lib.check(lib, lib.pbx_allreduce_sum(h._h, emu_lib.ptr(vals), 4))
+want_vals = [sum(r + 1.0 for r in range(world)), sum(0.1 * (r + 1) for r in range(world)), -3.0 * world,
+             sum(1e-3 * r for r in range(world))]
+errs["allreduce"] = float(np.max(np.abs(vals - want_vals)))
+gathered = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(gathered, torch.from_numpy(vals.copy()))
+same_bits = all(torch.equal(g, gathered[0]) for g in gathered)
+
+MAXIT = 60   # bounded: the harness runs ~10 iterations a second
+# the distributed CG against the single-handle CG on the whole brick: same iteration count, same
+# residual history (to rounding of the differently associated sums), same solution
+# (b = A f with a full-spectrum f: for smooth right-hand sides the history is governed by rounding
+# noise -- SURVEY section 7 -- and differently associated sums part ways after a few dozen iterations)
+b = ref
+x1, its1, rn1, why1, hist1 = whole.cg_solve(b, rtol=1e-8, maxit=MAXIT)
+xs, its, rn, why, hist = h.cg_solve(np.asfortranarray(b[:, :, mine]), rtol=1e-8, maxit=MAXIT)
+errs["cg_x"] = np.max(np.abs(xs - x1[:, :, mine])) / np.max(np.abs(x1))
+n = min(len(hist), len(hist1))
+errs["cg_hist"] = float(np.max(np.abs(hist[:n] - hist1[:n]) / hist1[:n]))
+cg_ok = why == why1 and its == its1
+# a solve that converges: the iteration issued after convergence is a no-op on every rank (the
+# guarded kernels skip their exchange everywhere or nowhere), and the boards stay in step after it
+_, its2a, _, why2a, _ = whole.cg_solve(b, rtol=3e-1, maxit=MAXIT)
+_, its2, _, why2, _ = h.cg_solve(np.asfortranarray(b[:, :, mine]), rtol=3e-1, maxit=MAXIT)
+cg_ok = cg_ok and why2 == why2a == 2 and its2 == its2a
+out = h.lapl(np.asfortranarray(f[:, :, mine]))
+errs["lapl_after_cg"] = np.max(np.abs(out - ref[:, :, mine])) / np.max(np.abs(ref))
+# ranks agree on the iteration count (the status word derives from all-reduced sums)
+its_all = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(its_all, torch.tensor([its], dtype=torch.int64))
+cg_ok = cg_ok and all(int(t) == its for t in its_all)
+
+tol = {"star": 0.0, "dot": 1e-12, "allreduce": 1e-15, "cg_x": 1e-6, "cg_hist": 1e-9}
+ok = all(e <= tol.get(k, 1e-13) for k, e in errs.items()) and same_bits and cg_ok
+dist.barrier()
+h.close()
+whole.close()
+del bufs, addr
+for s in segs:
+    try:
+        s.close()
+    except BufferError:
+        pass
+dist.barrier()
+try:
+    own.unlink()
+except FileNotFoundError:
+    pass
+dist.destroy_process_group()
+print(("EMU_PEER_OK " if ok else "EMU_PEER_FAIL ") + f"its {its} vs {its1} why {why}; {its2} vs {its2a} why {why2}; bits {same_bits} " + str(errs))
+sys.exit(0 if ok else 1)

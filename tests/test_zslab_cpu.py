@@ -83,3 +83,24 @@ def test_slab_kernels_gloo_world2():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "EMU_GLOO_OK" in o, o
+
+
+@pytest.mark.parametrize("world,port", [(2, 29621), (3, 29623)])
+def test_peer_boards(world, port):
+    """`world` processes (gloo rendezvous) sharing their receive buffers: the library's own multi-rank
+    paths -- peer stores of the boundary messages, the neighbour flag barrier, the all-reduce fused
+    into the CG's reduction kernel (pbx_slab_link_peers) -- on the CPU kernel-logic harness, with no
+    host-side exchange at all: Laplacian, grad, div, interp, star, dot and the distributed CG against
+    one handle on the whole brick (same iteration counts, same bits of the sums on every rank)"""
+    import emu_lib
+
+    emu_lib.load()   # build once before the ranks start
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    tag = f"{os.getpid()}w{world}"
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "emu_peer_worker.py"), str(r), str(world), tag],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "EMU_PEER_OK" in o, o

@@ -104,3 +104,60 @@ def test_slab_needs_64_to_512_planes():
         with pytest.raises(pbx.PbxError) as e:
             pbx.Handle(32, 32, nzl, (1, 1, 1), slab=(0, 2))
         assert e.value.code == 4
+
+
+@pytest.mark.skipif(os.environ.get("PBX_TEST_PEER_BOARDS") != "1",
+                    reason="peer boards (device-side barrier and all-reduce) were written in a round whose GPU "
+                           "budget was already spent: CPU-harness tested only (tests/test_zslab_cpu.py::"
+                           "test_peer_boards); set PBX_TEST_PEER_BOARDS=1 to run them on the GPU")
+@pytest.mark.parametrize("P", [2, 4])
+def test_peer_boards_one_gpu(P):
+    """P slab handles of one process on one GPU, each on its own stream and host thread, linked by
+    pbx_slab_link_peers: boundary messages by direct stores, flag barrier, all-reduce inside the CG's
+    reduction kernel -- against one handle on the whole brick"""
+    import threading
+
+    import torch
+
+    nx, ny, nzl = 64, 32, 64
+    nz = nzl * P
+    dx = (1.0 / nx, 0.7 / ny, 1.3 / nz)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    whole = pbx.Handle(nx, ny, nz, dx)
+    ref = whole.lapl(f)
+    x1, its1, _, why1, hist1 = whole.cg_solve(ref, rtol=1e-6, maxit=2000)
+    torch.cuda.synchronize()
+    slabs = [pbx.Handle(nx, ny, nzl, dx, slab=(r, P)) for r in range(P)]
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    for h, s in zip(slabs, streams):
+        h.set_stream(s.cuda_stream)
+    pbx.Handle.slab_link_local(slabs)
+    res = [None] * P
+
+    def work(r):
+        h = slabs[r]
+        part = f[r * nzl:(r + 1) * nzl].contiguous()
+        bpart = ref[r * nzl:(r + 1) * nzl].contiguous()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(streams[r]):
+            outs = [h.lapl(part) for _ in range(3)]
+            x, its, _, why, hist = h.cg_solve(bpart, rtol=1e-6, maxit=2000)
+            h.synchronize()
+        res[r] = (outs, x, its, why, hist)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+    assert all(r is not None for r in res), "a rank did not finish"
+    scale = ref.abs().max().item()
+    for r in range(P):
+        outs, x, its, why, hist = res[r]
+        for o in outs:
+            assert (o - ref[r * nzl:(r + 1) * nzl]).abs().max().item() <= 1e-13 * scale
+        assert why == why1 == 2 and abs(its - its1) <= 1, (its, its1, why)
+        assert (x - x1[r * nzl:(r + 1) * nzl]).abs().max().item() <= 1e-6 * x1.abs().max().item()
+    for h in slabs + [whole]:
+        h.close()
