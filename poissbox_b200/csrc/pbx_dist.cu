@@ -211,6 +211,82 @@ k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
 }
 
 
+// Thin slabs (nzl < 2 BM, e.g. 64 planes per rank on eight GPUs): the bottom and the top window of
+// the interpolation input overlap, and k_boundary would read the planes in the overlap twice.  Here one
+// thread per z line walks the planes of C ONCE, upwards, feeding both the bottom moments (running
+// power of r instead of Horner's rule) and the top recursion: 64 planes read instead of 96.  Same
+// numbers as k_boundary to rounding; the derivative part is unchanged.
+__global__ void __launch_bounds__(128)
+k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
+                const __grid_constant__ CompositeCoef D, const double *__restrict__ C,
+                const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up)
+{
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlines) return;
+    double P = 0.0, Q = 0.0, rj = 1.0, c0 = 0.0, c1 = 0.0;
+    double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
+    const int top0 = nzl - BM;
+    for (int j = 0; j < nzl; ++j) {
+        const double c = __ldg(C + (long long)j * nlines + l);
+        if (j < BM) {
+            const double t = rj * c;
+            P += t;
+            Q = fma((double)j, t, Q);
+            rj *= M.r;
+            if (j == 0) c0 = c;
+            if (j == 1) c1 = c;
+        }
+        if (j >= top0) {
+            y = fma(M.r, y, c);
+            z2 = z1;
+            z1 = z;
+            z = fma(M.r, z, y);
+        }
+    }
+    {
+        double w[BD + 3];
+#pragma unroll
+        for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)j * nlines + l);
+        double PD = 0.0, QD = 0.0;
+#pragma unroll
+        for (int j = BD - 1; j >= 0; --j) {
+            const double sj = sd_at(D, w, BD + 3, j);
+            QD = D.r * (QD + PD);
+            PD = fma(D.r, PD, sj);
+        }
+        msg_dn[0 * nlines + l] = P;
+        msg_dn[1 * nlines + l] = Q;
+        msg_dn[2 * nlines + l] = PD;
+        msg_dn[3 * nlines + l] = QD;
+        msg_dn[4 * nlines + l] = w[0];
+        msg_dn[5 * nlines + l] = w[1];
+        msg_dn[6 * nlines + l] = w[2];
+        msg_dn[7 * nlines + l] = c0;
+        msg_dn[8 * nlines + l] = c1;
+    }
+    {
+        double w[BD + 3];
+#pragma unroll
+        for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)(nzl - BD - 3 + j) * nlines + l);
+        double yD = 0.0, zD = 0.0;
+#pragma unroll
+        for (int j = 3; j < BD + 3; ++j) {
+            const double sj = sd_at(D, w, BD + 3, j);
+            yD = fma(D.r, yD, sj);
+            zD = fma(D.r, zD, yD);
+        }
+        msg_up[0 * nlines + l] = y;
+        msg_up[1 * nlines + l] = z;
+        msg_up[2 * nlines + l] = z1;
+        msg_up[3 * nlines + l] = z2;
+        msg_up[4 * nlines + l] = yD;
+        msg_up[5 * nlines + l] = zD;
+        msg_up[6 * nlines + l] = w[BD + 2];
+        msg_up[7 * nlines + l] = w[BD + 1];
+        msg_up[8 * nlines + l] = w[BD];
+    }
+}
+
 // Neighbour barrier of the slab exchange over the peer boards: the boundary sweep that precedes this
 // kernel on the stream has stored my messages into the neighbours' receive arrays; publish that
 // (release at system scope: the stores of the earlier kernel happen before it) and wait until both
@@ -470,9 +546,15 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     // with peer mappings the messages are stored straight into the neighbours' receive arrays
     double *dst_dn = d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn;
     double *dst_up = d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up;
-    dim3 grid((unsigned)((d->nlines + 127) / 128), 2);
-    k_boundary<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn,
-                                            dst_up);
+    static const bool thin_ok = getenv("PBX_NO_THIN_BOUNDARY") == nullptr;
+    if (thin_ok && h->nz < 2 * BM) {
+        k_boundary_thin<<<(unsigned)((d->nlines + 127) / 128), 128, 0, h->stream>>>(
+            d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
+    } else {
+        dim3 grid((unsigned)((d->nlines + 127) / 128), 2);
+        k_boundary<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn,
+                                                dst_up);
+    }
     ++h->launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -146,7 +146,7 @@ def test_emu_cg_matches_oracle():
     assert np.max(np.abs(x - xo)) <= 1e-6 * np.max(np.abs(xo))
 
 
-@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 16, 256), 4), ((16, 528, 128), 2)])
+@pytest.mark.parametrize("shape,P", [((32, 16, 128), 2), ((16, 16, 256), 4), ((16, 528, 128), 2), ((16, 16, 192), 2)])
 @pytest.mark.parametrize("no_tma", ["0", "1"])
 def test_emu_slabs_match_single_brick(shape, P, no_tma):
     nx, ny, nz = shape
