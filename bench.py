@@ -402,7 +402,11 @@ def run_ours(args):
             "config": {"workload": f"compact Laplacian apply (FAST schedule), {n}^3 fp64 periodic box, S2 random field "
                                    f"U[-1,1], dx = 1/{n}; N>1: z-slabs of {nzl} planes",
                        "grid": [n, n, n], "local_brick": [n, n, nzl], "l2": "field (1 GiB at 512^3) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"zslab{world}"},
+                       "parallelism": f"zslab{world}",
+                       "rank_sync": ("n/a" if world == 1 else
+                                     "peer boards (flag barrier + all-reduce in the CG's reduction kernel, no NCCL per iteration)"
+                                     if os.environ.get("PBX_PEER_SYNC") == "1" else
+                                     "peer stores of the boundary messages + ncclAllReduce (barrier, CG scalars)")},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "cg": cg,
         }

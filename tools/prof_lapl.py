@@ -11,14 +11,16 @@ import poissbox_b200 as pbx
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=512)
+ap.add_argument("--shape", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"), help="brick instead of n^3")
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--cg-its", type=int, default=0)
 a = ap.parse_args()
 n = a.n
-h = pbx.Handle(n, n, n, (1.0 / n,) * 3)
+nx, ny, nz = a.shape if a.shape else (n, n, n)
+h = pbx.Handle(nx, ny, nz, (1.0 / nx, 1.0 / ny, 1.0 / nz))
 h.use_current_stream()
 g = torch.Generator(device="cuda").manual_seed(1234)
-f = torch.rand((n, n, n), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
 out = h.empty()
 for _ in range(a.reps):
     h.lapl(f, out)
@@ -28,4 +30,4 @@ if a.cg_its:
     h.cg_solve(b, rtol=1e-30, maxit=a.cg_its)
     torch.cuda.synchronize()
 ms = h.lapl_profile(f, out, reps=5)
-print("pass ms (x,y,z):", ms, "total", sum(ms), "GDoF/s", n**3 / sum(ms) / 1e6)
+print("pass ms (x,y,z):", ms, "total", sum(ms), "GDoF/s", nx * ny * nz / sum(ms) / 1e6)

@@ -1,0 +1,24 @@
+# Round-2 first GPU call for the peer boards (written in round 1 after the GPU budget was spent;
+# CPU-harness tested only).  Stage A needs ONE GPU; stage B is the same thing over cudaIpc and needs
+# `gpurun --gpus 2` (then 8).  Every stage is wrapped in its own timeout: the kernels' bounded spins
+# trap after ~2 minutes if a peer never shows up.
+set -x
+mkdir -p gpurun_out
+# A. P slab handles of one process on one GPU, own streams + host threads (tests/test_zslab_gpu.py)
+PBX_TEST_PEER_BOARDS=1 timeout 600 python -m pytest tests/test_zslab_gpu.py -k peer_boards -q -x 2>&1 | tail -5 > gpurun_out/r2_peer_onegpu.log
+cat gpurun_out/r2_peer_onegpu.log
+N=$(python -c "import torch; print(torch.cuda.device_count())")
+if [ "$N" -ge 2 ]; then
+  for W in 2 $( [ "$N" -ge 8 ] && echo 8 ); do
+    # B. correctness over NCCL-bootstrapped cudaIpc mappings, with and without the peer boards
+    for PS in 0 1; do
+      PBX_PEER_SYNC=$PS timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 \
+        --master-port 29555 tools/dist_check.py 512 > gpurun_out/r2_dist_check_w${W}_ps${PS}.log 2>&1
+      tail -3 gpurun_out/r2_dist_check_w${W}_ps${PS}.log
+      # C. the bench line (MatMult + CG time-to-solution)
+      PBX_PEER_SYNC=$PS timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 \
+        --master-port 29556 bench.py --gpus $W --no-cpu --no-e2e > gpurun_out/r2_bench_w${W}_ps${PS}.json 2> gpurun_out/r2_bench_w${W}_ps${PS}.err
+      cat gpurun_out/r2_bench_w${W}_ps${PS}.json
+    done
+  done
+fi
