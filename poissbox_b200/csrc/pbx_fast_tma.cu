@@ -498,6 +498,21 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
 
 bool fast_tma_available() { return encode_fn() != nullptr; }
 
+// 2-D fp64 tensor map {dim0 (contiguous), dim1} with row stride `stride1_bytes` (a multiple of 16)
+bool tma_make_map_2d(CUtensorMap_st *m, const double *base, unsigned long long dim0, unsigned long long dim1,
+                     unsigned long long stride1_bytes, unsigned box0, unsigned box1, bool swizzle128)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {stride1_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // returns PBX_ERR_UNSUPPORTED when the shape does not fit the TMA kernels (caller falls back)
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
                    double *B, int rev, long long *launches)

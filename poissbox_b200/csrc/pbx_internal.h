@@ -10,6 +10,8 @@
 
 #include "../../include/pbx.h"
 
+struct CUtensorMap_st;
+
 namespace pbx {
 
 // ------------------------------------------------------------------------------------------------
@@ -237,6 +239,15 @@ int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger,
                        const double *in, double *msg_dn, double *msg_up, long long *launches);
 // TMA-pipelined persistent variants (pbx_fast_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
 bool fast_tma_available();
+bool tma_make_map_2d(CUtensorMap_st *m, const double *base, unsigned long long dim0, unsigned long long dim1,
+                     unsigned long long stride1_bytes, unsigned box0, unsigned box1, bool swizzle128);
+// line-major batches by TMA tiles (pbx_tdma_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel
+int tdma_fwd_batch_lm(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *a,
+                      double *b, const double *c, double *d);
+int tdma_bwd_batch_lm(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *b,
+                      const double *c, double *d);
+int tdma_periodic_batch_lm(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *a,
+                           const double *b, const double *c, double *d, double *ws);
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
                    double *B, int rev, long long *launches);
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,

@@ -243,6 +243,8 @@ int tdma_fwd_batch(cudaStream_t s, int n, long long nl, long long es, long long 
 {
     if (n < 1 || nl < 0) return PBX_ERR_ARG;
     if (nl == 0) return PBX_OK;
+    const int rc = tdma_fwd_batch_lm(s, n, nl, es, ls, a, b, c, d);
+    if (rc != PBX_ERR_UNSUPPORTED) return rc;
     fwd_kernel<<<nblocks(nl, 128), 128, 0, s>>>(n, nl, es, ls, a, b, c, d);
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
@@ -253,6 +255,8 @@ int tdma_bwd_batch(cudaStream_t s, int n, long long nl, long long es, long long 
 {
     if (n < 1 || nl < 0) return PBX_ERR_ARG;
     if (nl == 0) return PBX_OK;
+    const int rc = tdma_bwd_batch_lm(s, n, nl, es, ls, b, c, d);
+    if (rc != PBX_ERR_UNSUPPORTED) return rc;
     bwd_kernel<<<nblocks(nl, 128), 128, 0, s>>>(n, nl, es, ls, b, c, d);
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
@@ -265,6 +269,11 @@ int tdma_periodic_batch(cudaStream_t s, int n, long long nl, long long es, long 
     if (nl == 0) return PBX_OK;
     double *ws = nullptr;
     PBX_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * (size_t)n * (size_t)nl, s));
+    const int rc = tdma_periodic_batch_lm(s, n, nl, es, ls, a, b, c, d, ws);
+    if (rc != PBX_ERR_UNSUPPORTED) {
+        cudaFreeAsync(ws, s);
+        return rc;
+    }
     periodic_kernel<<<nblocks(nl, 128), 128, 0, s>>>(n, nl, es, ls, a, b, c, d, ws,
                                                      ws + (size_t)n * (size_t)nl);
     cudaError_t e = cudaGetLastError();

@@ -19,7 +19,7 @@ enum CUtensorMapSwizzle {
 enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_NONE = 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
 enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
 
-struct alignas(64) CUtensorMap {
+struct alignas(64) CUtensorMap_st {
     // what cuTensorMapEncodeTiled was told (fp64 elements)
     double *base;
     int rank;
@@ -29,4 +29,5 @@ struct alignas(64) CUtensorMap {
     uint32_t box[3];
     uint32_t pad_[5];
 };
+typedef CUtensorMap_st CUtensorMap;
 static_assert(sizeof(CUtensorMap) == 128, "keep the size of the real descriptor");

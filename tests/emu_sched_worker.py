@@ -57,6 +57,17 @@ def main():
     h.set_pc(_lib.PC_MG, 2)
     x, its, _, _, _ = h.cg_solve(b, rtol=1e-6)
     res.append(f"{its}:{digest(x)}")
+    # line-major tridiagonal batches through the TMA tiles (pbx_tdma_tma.cu)
+    os.environ["PBX_TDMA_TMA"] = "1"
+    n, nl = 40, 45
+    for per in (0, 1):
+        a, c = rng.uniform(-0.3, 0.3, (nl, n)), rng.uniform(-0.3, 0.3, (nl, n))
+        bd, d = 1.0 + rng.uniform(0, 0.5, (nl, n)), rng.uniform(-1, 1, (nl, n))
+        arrs = [emu_lib.aligned(np.asfortranarray(v.T)) for v in (a, bd, c, d)]    # memory: [line][i]
+        fn = h.lib.pbx_tdma_periodic_batch_device if per else h.lib.pbx_tdma_batch_device
+        emu_lib.check(h.lib, fn(n, nl, 1, n, *[emu_lib.ptr(v) for v in arrs], None))
+        res += [digest(arrs[1]), digest(arrs[3])]
+    os.environ.pop("PBX_TDMA_TMA")
     print(hashlib.md5(" ".join(res).encode()).hexdigest())
 
 

@@ -302,3 +302,41 @@ def test_emu_no_device_is_an_error():
         assert rc == _lib.PBX_ERR_CUDA
     finally:
         os.environ.pop("PBX_EMU_NO_DEVICE", None)
+
+
+@pytest.mark.parametrize("n,nl,pad", [(5, 37, 1), (64, 37, 0), (203, 70, 1), (128, 32, 0), (48, 3, 4), (16, 33, 0)])
+def test_emu_tridsol_line_major_tma(n, nl, pad, monkeypatch):
+    """PBX_TDMA_TMA=1: contiguous lines travel as swizzled TMA tiles (pbx_tdma_tma.cu), a warp per 32
+    lines, results written in place into the tiles -- same bits as the oracle, for lines that do not
+    fill the last 16-point block, batches that do not fill the last CTA and padded line strides"""
+    lib = emu_lib.load()
+    monkeypatch.setenv("PBX_TDMA_TMA", "1")
+    rng = np.random.default_rng(100 * n + nl)
+    ls = n + pad + ((n + pad) & 1)                 # even line stride (16-byte aligned rows)
+    for per in (False, True):
+        sys_ = [tdma_init(n, rng, per) for _ in range(nl)]
+        want_t = np.stack([orc.tdma(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_])
+        want_p = np.stack([orc.tdma_periodic(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_])
+        want_b = np.stack([orc.fwd_sweep(s_[0], s_[1], s_[2], s_[4])[0] for s_ in sys_])
+
+        def padded(i):
+            v = emu_lib.new_field((ls, nl))        # Fortran order: [line][ls] in memory, poison in the padding
+            v[:n, :] = np.stack([s_[i] for s_ in sys_]).T
+            return v
+
+        a, b, c, d = (padded(i) for i in (0, 1, 2, 4))
+        maps0 = lib.pbx_emu_tensor_maps_total()
+        emu_lib.check(lib, lib.pbx_tdma_batch_device(n, nl, 1, ls, emu_lib.ptr(a), emu_lib.ptr(b), emu_lib.ptr(c),
+                                                     emu_lib.ptr(d), None))
+        assert lib.pbx_emu_tensor_maps_total() - maps0 == 7, "the TMA kernels did not run"
+        assert np.array_equal(d[:n].T, want_t) and np.array_equal(b[:n].T, want_b)
+        assert np.all(d[n:] == 73.29) and np.all(b[n:] == 73.29), "padding between the lines touched"
+        a, b, c, d = (padded(i) for i in (0, 1, 2, 4))
+        b0 = b.copy()
+        maps0 = lib.pbx_emu_tensor_maps_total()
+        emu_lib.check(lib, lib.pbx_tdma_periodic_batch_device(n, nl, 1, ls, emu_lib.ptr(a), emu_lib.ptr(b),
+                                                              emu_lib.ptr(c), emu_lib.ptr(d), None))
+        if n % 2 == 0:
+            assert lib.pbx_emu_tensor_maps_total() - maps0 == 6, "the TMA kernel did not run"
+        assert np.array_equal(d[:n].T, want_p) and np.array_equal(b, b0)
+        assert np.all(d[n:] == 73.29)

@@ -106,6 +106,41 @@ def test_tridsol_batch_strided():
         assert np.array_equal(got, want)
 
 
+@pytest.mark.skipif(os.environ.get("PBX_TEST_TDMA_TMA") != "1",
+                    reason="line-major TMA tridsol kernels (pbx_tdma_tma.cu) were written after the round's GPU "
+                           "budget was spent: CPU-harness tested only (test_emu_tridsol_line_major_tma); set "
+                           "PBX_TEST_TDMA_TMA=1 to run them on the GPU")
+@pytest.mark.parametrize("n,nl,pad", [(5, 37, 1), (64, 300, 0), (203, 70, 1), (512, 4096, 0), (2048, 33, 2)])
+def test_tridsol_line_major_tma(n, nl, pad, monkeypatch):
+    """PBX_TDMA_TMA=1: contiguous lines as swizzled TMA tiles, same bits as the generic kernels and the oracle"""
+    import ctypes
+
+    import torch
+
+    rng = np.random.default_rng(100 * n + nl)
+    ls = n + pad + ((n + pad) & 1)
+    for per in (False, True):
+        sys_ = [tdma_init(n, rng, per) for _ in range(min(nl, 64))]
+        reps = (nl + len(sys_) - 1) // len(sys_)
+        host = []
+        for i in (0, 1, 2, 4):
+            v = np.full((nl, ls), 73.29)
+            v[:, :n] = np.tile(np.stack([s_[i] for s_ in sys_]), (reps, 1))[:nl]
+            host.append(v)
+        want_t = np.tile(np.stack([orc.tdma(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_]), (reps, 1))[:nl]
+        want_p = np.tile(np.stack([orc.tdma_periodic(s_[0], s_[1], s_[2], s_[4]) for s_ in sys_]), (reps, 1))[:nl]
+        for fn, want in ((pbx.LIB.pbx_tdma_batch_device, want_t), (pbx.LIB.pbx_tdma_periodic_batch_device, want_p)):
+            got = {}
+            for tma in ("0", "1"):
+                monkeypatch.setenv("PBX_TDMA_TMA", tma)
+                arrs = [torch.from_numpy(v.copy()).cuda() for v in host]
+                pbx.check(fn(n, nl, 1, ls, *[ctypes.c_void_p(t.data_ptr()) for t in arrs], None))
+                torch.cuda.synchronize()
+                got[tma] = (arrs[1].cpu().numpy(), arrs[3].cpu().numpy())
+            assert np.array_equal(got["1"][1][:, :n], want)
+            assert np.array_equal(got["0"][0], got["1"][0]) and np.array_equal(got["0"][1], got["1"][1])
+
+
 # ------------------------------------------------------------------------------------ 1-D operators
 @pytest.mark.parametrize("n", [3, 4, 5, 37, 128, 1000])
 def test_lines_bit_exact(n):

@@ -37,3 +37,25 @@ for ln in (64, 512, 2048):
     tt = tm(run_tdma)
     pts = ln * nl
     print(f"tdma batch n={ln} lines={nl}: tdma_periodic {tp:.3f} ms ({pts/tp/1e6:.2f} Gpt/s, {48*pts/tp/1e6:.0f} GB/s alg)  tdma(+copy) {tt:.3f} ms ({pts/tt/1e6:.2f} Gpt/s)")
+
+# line-major batches (contiguous lines): the generic thread-per-line kernels against the TMA-tile
+# kernels of pbx_tdma_tma.cu (PBX_TDMA_TMA=1, read per call)
+for ln, nl in ((64, 262144), (512, 32768), (2048, 8192)):
+    a, b, c, d = (torch.rand((nl, ln), dtype=torch.float64, device="cuda") for _ in range(4))
+    b += 2.5
+    b2 = b.clone()
+    ptr = [ctypes.c_void_p(t.data_ptr()) for t in (a, b, c, d)]
+    ptr2 = [ctypes.c_void_p(t.data_ptr()) for t in (a, b2, c, d)]
+
+    def run_tdma():
+        b2.copy_(b)
+        check(LIB.pbx_tdma_batch_device(ln, nl, 1, ln, *ptr2, None))
+
+    row = []
+    for tma in ("0", "1"):
+        os.environ["PBX_TDMA_TMA"] = tma
+        tp = tm(lambda: check(LIB.pbx_tdma_periodic_batch_device(ln, nl, 1, ln, *ptr, None)))
+        tt = tm(run_tdma)
+        row.append(f"TMA={tma}: periodic {ln * nl / tp / 1e6:.2f} Gpt/s, tdma(+copy) {ln * nl / tt / 1e6:.2f} Gpt/s")
+    os.environ.pop("PBX_TDMA_TMA")
+    print(f"tdma LINE-MAJOR n={ln} lines={nl}: " + "   ".join(row))
