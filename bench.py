@@ -363,9 +363,11 @@ def run_ours(args):
               "alg_bytes_per_dof_it": 152.0, "frac_of_hbm_peak": 152.0 * ndof_total * its / dt / 1e9 / peak / world,
               "gpu_launches": h2.launches - l1}
         # the same solve with the multigrid preconditioner on the 2nd-order star (the
-        # role of the reference's `-pc_type gamg` on P); single GPU.  Reported beside the headline,
-        # which stays the reference's unpreconditioned configuration.
-        if world == 1:
+        # role of the reference's `-pc_type gamg` on P).  Reported beside the headline, which stays the
+        # reference's unpreconditioned configuration.  On slabs (N > 1: distributed levels with one-plane
+        # halo exchanges, coarse levels all-gathered) the leg is opt-in, PBX_BENCH_MG_SLABS=1, until it
+        # has run on the GPUs once: it was written after the round's GPU budget was spent.
+        if world == 1 or os.environ.get("PBX_BENCH_MG_SLABS") == "1":
             try:
                 from poissbox_b200 import _lib as _pl
 
@@ -378,7 +380,14 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 dtp = time.perf_counter() - t0
                 rres = h2.lapl(x) - b
-                true_rel = float(torch.sqrt((rres * rres).sum() / (b * b).sum()).item())
+                num, den = (rres * rres).sum(), (b * b).sum()
+                if world > 1:
+                    t = torch.tensor([dtp], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dtp = t.item()
+                    dist.all_reduce(num)
+                    dist.all_reduce(den)
+                true_rel = float(torch.sqrt(num / den).item())
                 del rres
                 cg["multigrid_pc"] = {"pc": "V(2,2) geometric multigrid on the 2nd-order star, damped Jacobi",
                                       "time_s": dtp, "its": its, "reason": reason,

@@ -552,8 +552,8 @@ int pbx_set_pc(pbx_handle h, int pc, int nu)
 {
     if (!h || (pc != PBX_PC_NONE && pc != PBX_PC_MG) || nu < 0) return PBX_ERR_ARG;
     if (pc == PBX_PC_MG) {
-        if (h->nranks > 1) {
-            set_last_error("the multigrid preconditioner is single-rank");
+        if (h->nranks > 1 && !dist_connected(h)) {
+            set_last_error("multigrid on slabs needs a communicator or linked peer boards");
             return PBX_ERR_UNSUPPORTED;
         }
         PBX_CUDA(cudaSetDevice(h->device));

@@ -545,18 +545,17 @@ int pc_apply(pbx_handle_s *h, const double *r, double *z)
     cudaStream_t s = h->stream;
     double *sc = h->cg_scal, *part = h->cg_partials;
     const int np = h->cg_npartials, nb = vec_grid(N);
-    const double ntot = (double)N;
+    const double ntot = (double)N * (double)h->nranks;
     PBX_CUDA(cudaMemcpyAsync(sc + SC_NTOT, &ntot, sizeof ntot, cudaMemcpyHostToDevice, s));
     k_sum<<<nb, VT, 0, s>>>(N, r, part);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
-    k_scalar<<<1, 1, 0, s>>>(sc, 7, nullptr, 0);
-    h->launches += 3;
+    ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 1, sc + SC_S1, 0, 7));
     PBX_TRY(pc_raw(h, r, sc + SC_MEAN, z));
     k_sum<<<nb, VT, 0, s>>>(N, z, part);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
-    k_scalar<<<1, 1, 0, s>>>(sc, 8, nullptr, 0);
+    ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 1, sc + SC_S1, 0, 8));
     k_center<<<nb, VT, 0, s>>>(N, z, sc + SC_MZ);
-    h->launches += 4;
+    ++h->launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
 }
@@ -566,10 +565,6 @@ static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol,
                        int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
-    if (h->nranks > 1) {
-        set_last_error("the preconditioned CG is single-rank");
-        return PBX_ERR_UNSUPPORTED;
-    }
     PBX_TRY(cg_alloc(h, maxit));
     cudaStream_t s = h->stream;
     double *sc = h->cg_scal, *part = h->cg_partials;
@@ -581,19 +576,19 @@ static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol,
     init[SC_RTOL] = rtol;
     init[SC_ABSTOL] = abstol;
     init[SC_MAXIT] = (double)maxit;
-    init[SC_NTOT] = (double)N;
+    init[SC_NTOT] = (double)N * (double)h->nranks;
     PBX_CUDA(cudaMemcpyAsync(sc, init, sizeof init, cudaMemcpyHostToDevice, s));
     k_sum<<<nb, VT, 0, s>>>(N, b, part);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 1, sc + SC_S1, sc, 0);
-    k_scalar<<<1, 1, 0, s>>>(sc, 0, nullptr, 0);        // m0 = mean(b) = mean(r) from here on
+    ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 1, sc + SC_S1, 0, 0));   // m0 = mean(b) = mean(r) from here on
     k_init_pc<<<nb, VT, 0, s>>>(N, b, x, r);
-    h->launches += 4;
+    ++h->launches;
     PBX_TRY(pc_raw(h, r, sc + SC_MEAN, z));
     k_pcdots<<<nb, VT, 0, s>>>(N, z, r, sc, part, np);
-    k_reduce<<<1, VT, 0, s>>>(part, nb, np, 4, sc + SC_SZ, sc, 0);
-    k_scalar<<<1, 1, 0, s>>>(sc, 4, h->cg_hist, h->cg_hist_cap);
+    ++h->launches;
+    PBX_TRY(reduce_step(h, part, nb, np, 4, sc + SC_SZ, 0, 4));
     k_pupdate_pc<<<nb, VT, 0, s>>>(N, z, p, sc);
-    h->launches += 4;
+    ++h->launches;
     PBX_CUDA(cudaGetLastError());
 
     cudaEvent_t ev[2];
@@ -607,18 +602,16 @@ static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol,
     int issued = 0;
     while (!done && issued < maxit) {
         const int slot = issued & 1;
-        if ((rc = matmult_dot(h, p, w, sc + SC_PW, 1, -1)) != PBX_OK) break;
-        k_scalar<<<1, 1, 0, s>>>(sc, 2, nullptr, 0);
+        if ((rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2)) != PBX_OK) break;
         k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
-        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 2, sc + SC_S1, sc, 1);
-        k_scalar<<<1, 1, 0, s>>>(sc, 5, nullptr, 0);
-        h->launches += 4;
+        ++h->launches;
+        if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 5)) != PBX_OK) break;
         if ((rc = pc_raw(h, r, sc + SC_MEAN, z)) != PBX_OK) break;
         k_pcdots<<<nb, VT, 0, s>>>(N, z, r, sc, part, np);
-        k_reduce<<<1, VT, 0, s>>>(part, nb, np, 4, sc + SC_SZ, sc, 1);
-        k_scalar<<<1, 1, 0, s>>>(sc, 6, h->cg_hist, h->cg_hist_cap);
+        ++h->launches;
+        if ((rc = reduce_step(h, part, nb, np, 4, sc + SC_SZ, 1, 6)) != PBX_OK) break;
         k_pupdate_pc<<<nb, VT, 0, s>>>(N, z, p, sc);
-        h->launches += 4;
+        ++h->launches;
         cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s);
         cudaEventRecord(ev[slot], s);
         ++issued;

@@ -115,9 +115,14 @@ struct DistState {
     long long nlines = 0;
     int lower = 0, upper = 0;
     ZOpen zo;                     // constants of the slab z pass
+    // all-gather area of the multigrid preconditioner (mg_slab_plan): 2 parities x gather_cap doubles
+    // behind the board
+    size_t gather_cap = 0;
+    unsigned long long gather_seq = 0;
     size_t per() const { return (size_t)DIST_MSG * (size_t)nlines; }
     size_t board_offset() const { return (4 * per() * sizeof(double) + 127) & ~(size_t)127; }
-    size_t recv_bytes() const { return board_offset() + sizeof(PeerBoard); }
+    size_t gather_offset() const { return (board_offset() + sizeof(PeerBoard) + 127) & ~(size_t)127; }
+    size_t recv_bytes() const { return gather_offset() + 2 * gather_cap * sizeof(double); }
     bool peer_stores() const { return peer_up_recv_lo[0] != nullptr; }
 };
 
@@ -383,6 +388,7 @@ int dist_setup(pbx_handle_s *h, int rank, int nranks)
     DistState *d = new DistState();
     h->dist = d;
     d->nlines = (long long)h->nx * h->ny;
+    mg_slab_plan(h->nx, h->ny, h->nz, nranks, &d->gather_cap);
     const size_t per = (size_t)DIST_MSG * d->nlines;
     PBX_CUDA(cudaMalloc(&d->buf, 2 * per * sizeof(double)));
     PBX_CUDA(cudaMemset(d->buf, 0, 2 * per * sizeof(double)));
@@ -637,6 +643,48 @@ int dist_exchange(pbx_handle_s *h)
 {
     if (!h->dist || !dist_connected(h)) return PBX_ERR_ARG;
     return dist_exchange_run(h);
+}
+
+// One plane each way: my bottom plane of `field` (nz planes of `plane` doubles) becomes the lower
+// rank's *hi, my top plane the upper rank's *lo -- the exchange of the star operator (slot 0 of the
+// message arrays), for the multigrid levels.
+int dist_halo_planes(pbx_handle_s *h, const double *field, size_t plane, int nz, const double **lo,
+                     const double **hi)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || !dist_connected(h) || plane > (size_t)d->nlines) return PBX_ERR_ARG;
+    PBX_TRY(dist_begin_epoch(h));
+    double *dn = nullptr, *up = nullptr;
+    PBX_TRY(dist_line_dst(h, 0, &dn, &up));
+    PBX_CUDA(cudaMemcpyAsync(dn, field, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    PBX_CUDA(cudaMemcpyAsync(up, field + plane * (size_t)(nz - 1), plane * sizeof(double),
+                             cudaMemcpyDeviceToDevice, h->stream));
+    PBX_TRY(dist_exchange_run(h));
+    return dist_line_msgs(h, 0, lo, hi);
+}
+
+// All-gather `count` doubles per rank, rank order, into *full (valid until the gather after next).
+// Peer boards: every rank copies its part into every rank's gather area (two parities) and an
+// all-reduce over the boards is the barrier; otherwise ncclAllGather.
+int dist_allgather(pbx_handle_s *h, const double *mine, size_t count, double **full)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || !dist_connected(h) || count * (size_t)h->nranks > d->gather_cap) return PBX_ERR_ARG;
+    const int par = (int)(++d->gather_seq & 1);
+    const size_t off = d->gather_offset() + (size_t)par * d->gather_cap * sizeof(double);
+    double *own = (double *)((char *)d->rbuf + off);
+    if (d->peer_sync) {
+        for (int r = 0; r < h->nranks; ++r) {
+            char *base = (char *)d->links.board[r] - d->board_offset();   // rank r's receive buffer
+            PBX_CUDA(cudaMemcpyAsync((double *)(base + off) + (size_t)h->rank * count, mine, count * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, h->stream));
+        }
+        PBX_TRY(dist_allreduce_sum(h, d->sync_word, 1));
+    } else {
+        PBX_NCCL(g_nccl.AllGather(mine, own, count, ncclFloat64, (ncclComm_t)h->comm, h->stream));
+    }
+    *full = own;
+    return PBX_OK;
 }
 
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials)

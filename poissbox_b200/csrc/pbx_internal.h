@@ -340,6 +340,11 @@ int dist_line_msgs(pbx_handle_s *h, int slot, const double **from_lo, const doub
 int dist_exchange(pbx_handle_s *h);                                            // over the communicator
 // sum `count` doubles in place over the handle's communicator (no-op for a single rank)
 int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count);
+// multigrid on slabs (pbx_mg.cu): one plane each way, and an all-gather of `count` doubles per rank
+int dist_halo_planes(pbx_handle_s *h, const double *field, size_t plane, int nz, const double **lo,
+                     const double **hi);
+int dist_allgather(pbx_handle_s *h, const double *mine, size_t count, double **full);
+int mg_slab_plan(int nx, int ny, int nzl, int nranks, size_t *gather_doubles);
 // true when the handle can talk to the other ranks (NCCL communicator or linked peer boards)
 bool dist_connected(const pbx_handle_s *h);
 // peer boards in place: fills *L and the sequence number of the next all-reduce, returns true

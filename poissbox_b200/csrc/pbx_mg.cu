@@ -50,7 +50,7 @@ template <int MODE>
 __global__ void __launch_bounds__(MBX * MBY)
 mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
                 const double *__restrict__ r, const double *__restrict__ mean,
-                double *__restrict__ out)
+                double *__restrict__ out, const double *__restrict__ zlo, const double *__restrict__ zhi)
 {
     const int nx = lv.nx, ny = lv.ny, nz = lv.nz;
     const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
@@ -64,9 +64,12 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
     double zc[MKZ + 2], zim[MKZ], zip[MKZ], zjm[MKZ], zjp[MKZ], rr[MKZ];
 #pragma unroll
     for (int u = 0; u < MKZ + 2; ++u) {
-        int k = k0 - 1 + u;
-        k = k < 0 ? nz - 1 : (k >= nz ? k - nz : k);
-        zc[u] = (k0 + u - 1 <= nz) ? z[col + plane * k] : 0.0;
+        // plane k0 - 1 + u of the column; below / above the brick: the periodic image, or on a slab
+        // (zlo / zhi given) the neighbour rank's plane
+        const int k = k0 - 1 + u;
+        const double *src = k < 0 ? (zlo ? zlo + col : z + col + plane * (nz - 1))
+                                  : (k >= nz ? (zhi ? zhi + col : z + col + plane * (k - nz)) : z + col + plane * k);
+        zc[u] = (k <= nz) ? *src : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < MKZ; ++u) {
@@ -112,7 +115,7 @@ mg_scale_kernel(size_t n, double wd, const double *__restrict__ r, const double 
 // coarse cells of plane blockIdx.z.
 __global__ void __launch_bounds__(MBX * MBY)
 mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fine,
-                   double *__restrict__ coarse)
+                   double *__restrict__ coarse, const double *__restrict__ flo, const double *__restrict__ fhi)
 {
     const int cnx = lv.nx / 2, cny = lv.ny / 2;
     const int I = blockIdx.x * MBX + threadIdx.x, J = blockIdx.y * MBY + threadIdx.y, K = blockIdx.z;
@@ -123,14 +126,17 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        int k = 2 * K - 1 + c;
-        k = k < 0 ? k + lv.nz : (k >= lv.nz ? k - lv.nz : k);
+        const int k = 2 * K - 1 + c;
+        // fine plane k; below / above the brick: periodic image or the neighbour rank's plane
+        const double *pl = k < 0 ? (flo ? flo : fine + (size_t)lv.nx * lv.ny * (k + lv.nz))
+                                 : (k >= lv.nz ? (fhi ? fhi : fine + (size_t)lv.nx * lv.ny * (k - lv.nz))
+                                               : fine + (size_t)lv.nx * lv.ny * k);
         double sk = 0.0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             int j = 2 * J - 1 + b;
             j = j < 0 ? j + lv.ny : (j >= lv.ny ? j - lv.ny : j);
-            const double *row = fine + (size_t)lv.nx * (j + (size_t)lv.ny * k);
+            const double *row = pl + (size_t)lv.nx * j;
             const double2 mid = *reinterpret_cast<const double2 *>(row + i0);   // i0 is even
             sk = fma(w[b], fma(w[0], __ldg(row + im) + __ldg(row + ip), w[1] * (mid.x + mid.y)), sk);
         }
@@ -145,7 +151,7 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
 // first (16 loads issued together), then along z.
 __global__ void __launch_bounds__(MBX * MBY)
 mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coarse,
-                  double *__restrict__ fine)
+                  double *__restrict__ fine, const double *__restrict__ clo, const double *__restrict__ chi)
 {
     const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
     if (i >= lv.nx || j >= lv.ny) return;
@@ -161,9 +167,10 @@ mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coar
     double q[4];                                      // in-plane interpolants of planes K0 - 1 .. K0 + 2
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        int K = K0 - 1 + u;
-        K = K < 0 ? cnz - 1 : (K >= cnz ? K - cnz : K);
-        const double *pl = coarse + (size_t)cnx * cny * K;
+        const int K = K0 - 1 + u;
+        const size_t cplane = (size_t)cnx * cny;
+        const double *pl = K < 0 ? (clo ? clo : coarse + cplane * (cnz - 1))
+                                 : (K >= cnz ? (chi ? chi : coarse + cplane * (K - cnz)) : coarse + cplane * K);
         const double a0 = __ldg(pl + ia + (size_t)cnx * ja), b0 = __ldg(pl + ib + (size_t)cnx * ja);
         const double a1 = __ldg(pl + ia + (size_t)cnx * jb), b1 = __ldg(pl + ib + (size_t)cnx * jb);
         q[u] = fma(0.25, fma(0.25, b1, 0.75 * a1), 0.75 * fma(0.25, b0, 0.75 * a0));
@@ -187,38 +194,85 @@ struct MgLevel {
     size_t n = 0;
 };
 
+// One hierarchy: lev[0] is its finest grid.  `own0`: r and z of lev[0] belong to the hierarchy (false
+// for the handle's finest grid, whose r and z are the caller's vectors).
+struct MgHier {
+    std::vector<MgLevel> lev;
+    bool own0 = false;
+};
+
+// On z slabs (nranks > 1) the cycle is the same cycle, split at level g (mg_slab_plan):
+//   levels 0 .. g-1   distributed like the fine grid: every rank owns its planes; a kernel that needs
+//                     the planes next to the slab gets them from the neighbours first (dist_halo_planes:
+//                     one plane each way, the exchange of the star operator);
+//   levels g ..       too thin to cut (<= 4 planes per rank): the right-hand side of level g is
+//                     all-gathered (dist_allgather) and every rank runs the rest of the cycle on the
+//                     whole coarse grid, redundantly, then prolongs its own part.
+// Point for point the arithmetic is that of the single-rank cycle, so the result carries the same bits.
 struct MgState {
-    std::vector<MgLevel> lev;   // lev[0] = the finest grid (r and z are the caller's arrays)
+    MgHier top;        // single rank: the whole hierarchy; slabs: the distributed levels 0 .. g-1
+    MgHier rep;        // slabs: levels g .. on the whole (global) coarse grid, replicated
+    double *gsrc = nullptr;   // slabs: my planes of level g's right-hand side
+    size_t gcount = 0;        //        their number of doubles
     int nu = 2;
 };
 
 namespace {
 
 int sweep(pbx_handle_s *h, int mode, const Lv &lv, const double *z, const double *r, const double *mean,
-          double *out)
+          double *out, const double *zlo = nullptr, const double *zhi = nullptr)
 {
     dim3 block(MBX, MBY), grid((lv.nx + MBX - 1) / MBX, (lv.ny + MBY - 1) / MBY, (lv.nz + MKZ - 1) / MKZ);
     if (mode == 0)
-        mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+        mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
     else if (mode == 1)
-        mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+        mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
     else
-        mg_sweep_kernel<2><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out);
+        mg_sweep_kernel<2><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
+    ++h->launches;
+    return PBX_OK;
+}
+
+int restrict_to(pbx_handle_s *h, const Lv &fine, const double *res, double *coarse_r,
+                const double *flo = nullptr, const double *fhi = nullptr)
+{
+    const int cnx = fine.nx / 2, cny = fine.ny / 2, cnz = fine.nz / 2;
+    mg_restrict_kernel<<<dim3((cnx + MBX - 1) / MBX, (cny + MBY - 1) / MBY, cnz), dim3(MBX, MBY), 0, h->stream>>>(
+        fine, res, coarse_r, flo, fhi);
+    ++h->launches;
+    return PBX_OK;
+}
+
+int prolong_add(pbx_handle_s *h, const Lv &fine, const double *coarse_z, double *fine_z,
+                const double *clo = nullptr, const double *chi = nullptr)
+{
+    mg_prolong_kernel<<<dim3((fine.nx + MBX - 1) / MBX, (fine.ny + MBY - 1) / MBY, (fine.nz + 3) / 4),
+                        dim3(MBX, MBY), 0, h->stream>>>(fine, coarse_z, fine_z, clo, chi);
     ++h->launches;
     return PBX_OK;
 }
 
 unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
-// `count` Jacobi sweeps on S z = r - mean from a zero guess; the result ends in *cur (the spare in *alt)
-int smooth_from_zero(pbx_handle_s *h, const MgLevel &L, const double *r, const double *mean, int count,
-                     double **cur, double **alt)
+// the planes next to my slab of `field` (slab = true), or nothing (periodic brick)
+int halo(pbx_handle_s *h, bool slab, const Lv &lv, const double *field, const double **lo, const double **hi)
 {
+    *lo = *hi = nullptr;
+    if (!slab) return PBX_OK;
+    return dist_halo_planes(h, field, (size_t)lv.nx * lv.ny, lv.nz, lo, hi);
+}
+
+// `count` Jacobi sweeps on S z = r - mean from a zero guess; the result ends in *cur (the spare in *alt)
+int smooth_from_zero(pbx_handle_s *h, bool slab, const MgLevel &L, const double *r, const double *mean,
+                     int count, double **cur, double **alt)
+{
+    const double *lo, *hi;
     int done = 1;
     if (count >= 2) {
         // two sweeps in one pass; the caller's buffer parity counts sweeps, so the result goes where
         // the second sweep would have put it
-        PBX_TRY(sweep(h, 2, L.lv, r, r, mean, *alt));
+        PBX_TRY(halo(h, slab, L.lv, r, &lo, &hi));
+        PBX_TRY(sweep(h, 2, L.lv, r, r, mean, *alt, lo, hi));
         std::swap(*cur, *alt);
         done = 2;
     } else {
@@ -228,25 +282,147 @@ int smooth_from_zero(pbx_handle_s *h, const MgLevel &L, const double *r, const d
         ++h->launches;
     }
     for (int s = done; s < count; ++s) {
-        PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt));
+        PBX_TRY(halo(h, slab, L.lv, *cur, &lo, &hi));
+        PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt, lo, hi));
         std::swap(*cur, *alt);
     }
     return PBX_OK;
 }
 
+void free_hier(MgHier &H)
+{
+    for (size_t l = 0; l < H.lev.size(); ++l) {
+        if (l > 0 || H.own0) {
+            cudaFree(H.lev[l].r);
+            cudaFree(H.lev[l].z);
+        }
+        cudaFree(H.lev[l].t);
+    }
+    H.lev.clear();
+}
+
+bool is_coarsest(const int n[3])
+{
+    return n[0] <= 4 || n[1] <= 4 || n[2] <= 4 || (n[0] & 1) || (n[1] & 1) || (n[2] & 1);
+}
+
+// levels from grid n (spacing hh) down: at most `maxlev` of them (0: until the coarsest grid); the z
+// extent of a level's arrays is n[2] / zdiv (zdiv > 1: my planes of a slab decomposition)
+int build_hier(MgHier &H, const int n0[3], const double hh0[3], int zdiv, int maxlev, bool own0)
+{
+    int n[3] = {n0[0], n0[1], n0[2]};
+    double hh[3] = {hh0[0], hh0[1], hh0[2]};
+    H.own0 = own0;
+    for (int l = 0;; ++l) {
+        MgLevel L;
+        L.lv.nx = n[0];
+        L.lv.ny = n[1];
+        L.lv.nz = n[2] / zdiv;
+        L.lv.cx = 1.0 / (hh[0] * hh[0]);
+        L.lv.cy = 1.0 / (hh[1] * hh[1]);
+        L.lv.cz = 1.0 / (hh[2] * hh[2]);
+        L.lv.wd = MG_OMEGA / (2.0 * (L.lv.cx + L.lv.cy + L.lv.cz));
+        L.n = (size_t)L.lv.nx * L.lv.ny * L.lv.nz;
+        H.lev.push_back(L);
+        MgLevel &R = H.lev.back();
+        if (cudaMalloc(&R.t, L.n * sizeof(double)) != cudaSuccess ||
+            ((l > 0 || own0) && (cudaMalloc(&R.r, L.n * sizeof(double)) != cudaSuccess ||
+                                 cudaMalloc(&R.z, L.n * sizeof(double)) != cudaSuccess))) {
+            cudaGetLastError();
+            set_last_error("multigrid hierarchy allocation failed");
+            return PBX_ERR_NOMEM;
+        }
+        if (is_coarsest(n) || (maxlev > 0 && l + 1 == maxlev)) break;
+        for (int d = 0; d < 3; ++d) {
+            n[d] /= 2;
+            hh[d] *= 2.0;
+        }
+    }
+    return PBX_OK;
+}
+
+// One V(nu, nu) cycle on hierarchy H (lev[0].r and lev[0].z set by the caller).  slab: the levels are
+// my planes of a z-decomposed box.  `below`: called when the downward leg has produced the right-hand
+// side `next_r` of the level under H's last one (nullptr: H ends with the coarsest grid); it returns
+// that level's solution as (coarse, clo, chi).
+template <class Below>
+int cycle(pbx_handle_s *h, MgHier &H, bool slab, int nu, const double *mean, double *next_r, Below below)
+{
+    const int nl = (int)H.lev.size();
+    std::vector<double *> cur(nl), alt(nl);
+    const double *lo, *hi;
+    const int ndown = next_r ? nl : nl - 1;        // levels that smooth, form a residual and restrict it
+    for (int l = 0; l < nl; ++l) {
+        MgLevel &L = H.lev[l];
+        const double *mp = l == 0 ? mean : nullptr;
+        if (l == ndown) {
+            // coarsest grid: a fixed number of sweeps, ending in L.z
+            cur[l] = (MG_COARSE_SWEEPS & 1) ? L.z : L.t;
+            alt[l] = (MG_COARSE_SWEEPS & 1) ? L.t : L.z;
+            PBX_TRY(smooth_from_zero(h, slab, L, L.r, mp, MG_COARSE_SWEEPS, &cur[l], &alt[l]));
+            break;
+        }
+        // nu pre-sweeps (the first from the zero guess) + nu post-sweeps = 2 nu - 1 buffer swaps: start
+        // in the spare so that the result ends in L.z
+        cur[l] = L.t;
+        alt[l] = L.z;
+        PBX_TRY(smooth_from_zero(h, slab, L, L.r, mp, nu, &cur[l], &alt[l]));
+        PBX_TRY(halo(h, slab, L.lv, cur[l], &lo, &hi));
+        PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l], lo, hi));          // residual into the spare
+        PBX_TRY(halo(h, slab, L.lv, alt[l], &lo, &hi));
+        PBX_TRY(restrict_to(h, L.lv, alt[l], l + 1 < nl ? H.lev[l + 1].r : next_r, lo, hi));
+    }
+    for (int l = ndown - 1; l >= 0; --l) {
+        MgLevel &L = H.lev[l];
+        const double *mp = l == 0 ? mean : nullptr;
+        const double *coarse = nullptr;
+        if (l + 1 < nl) {
+            coarse = H.lev[l + 1].z;
+            MgLevel &C = H.lev[l + 1];
+            PBX_TRY(halo(h, slab, C.lv, coarse, &lo, &hi));
+        } else {
+            PBX_TRY(below(&coarse, &lo, &hi));
+        }
+        PBX_TRY(prolong_add(h, L.lv, coarse, cur[l], lo, hi));
+        for (int s = 0; s < nu; ++s) {
+            PBX_TRY(halo(h, slab, L.lv, cur[l], &lo, &hi));
+            PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l], lo, hi));
+            std::swap(cur[l], alt[l]);
+        }
+        if (cur[l] != L.z) {
+            set_last_error("multigrid buffer parity broken");
+            return PBX_ERR_ARG;
+        }
+    }
+    return PBX_OK;
+}
+
+int no_below(const double **, const double **, const double **) { return PBX_ERR_ARG; }
+
 }  // namespace
+
+// Slab decomposition: the number g of distributed levels for bricks of nzl planes on each of P ranks
+// (0: the hierarchy cannot be cut) and the size of level g's global grid, which is all-gathered.
+int mg_slab_plan(int nx, int ny, int nzl, int nranks, size_t *gather_doubles)
+{
+    int n[3] = {nx, ny, nzl * nranks};
+    int g = 0, loc = nzl;
+    while (!is_coarsest(n) && loc > 4 && !(loc & 1)) {
+        for (int d = 0; d < 3; ++d) n[d] /= 2;
+        loc /= 2;
+        ++g;
+    }
+    if (gather_doubles) *gather_doubles = (size_t)n[0] * n[1] * n[2];
+    return g;
+}
 
 void mg_free(pbx_handle_s *h)
 {
     MgState *m = (MgState *)h->mg;
     if (!m) return;
-    for (size_t l = 0; l < m->lev.size(); ++l) {
-        if (l > 0) {
-            cudaFree(m->lev[l].r);
-            cudaFree(m->lev[l].z);
-        }
-        cudaFree(m->lev[l].t);
-    }
+    free_hier(m->top);
+    free_hier(m->rep);
+    if (m->gsrc) cudaFree(m->gsrc);
     delete m;
     h->mg = nullptr;
 }
@@ -261,36 +437,34 @@ int mg_setup(pbx_handle_s *h, int nu)
     MgState *m = new MgState();
     m->nu = nu;
     h->mg = m;
-    int n[3] = {h->nx, h->ny, h->nz};
-    double hh[3] = {h->dx[0], h->dx[1], h->dx[2]};
-    for (int l = 0;; ++l) {
-        MgLevel L;
-        L.lv.nx = n[0];
-        L.lv.ny = n[1];
-        L.lv.nz = n[2];
-        L.lv.cx = 1.0 / (hh[0] * hh[0]);
-        L.lv.cy = 1.0 / (hh[1] * hh[1]);
-        L.lv.cz = 1.0 / (hh[2] * hh[2]);
-        L.lv.wd = MG_OMEGA / (2.0 * (L.lv.cx + L.lv.cy + L.lv.cz));
-        L.n = (size_t)n[0] * n[1] * n[2];
-        m->lev.push_back(L);
-        MgLevel &R = m->lev.back();
-        if (cudaMalloc(&R.t, L.n * sizeof(double)) != cudaSuccess ||
-            (l > 0 && (cudaMalloc(&R.r, L.n * sizeof(double)) != cudaSuccess ||
-                       cudaMalloc(&R.z, L.n * sizeof(double)) != cudaSuccess))) {
-            cudaGetLastError();
+    const int P = h->nranks;
+    const int n[3] = {h->nx, h->ny, h->nz * P};
+    int rc;
+    if (P == 1) {
+        rc = build_hier(m->top, n, h->dx, 1, 0, false);
+    } else {
+        size_t gd = 0;
+        const int g = mg_slab_plan(h->nx, h->ny, h->nz, P, &gd);
+        if (g < 1) {
             mg_free(h);
-            set_last_error("multigrid hierarchy allocation failed");
-            return PBX_ERR_NOMEM;
+            set_last_error("multigrid on slabs: the brick cannot be coarsened");
+            return PBX_ERR_UNSUPPORTED;
         }
-        const bool coarsest = n[0] <= 4 || n[1] <= 4 || n[2] <= 4 || (n[0] & 1) || (n[1] & 1) || (n[2] & 1);
-        if (coarsest) break;
-        for (int d = 0; d < 3; ++d) {
-            n[d] /= 2;
-            hh[d] *= 2.0;
+        rc = build_hier(m->top, n, h->dx, P, g, false);
+        if (rc == PBX_OK) {
+            int ng[3] = {n[0] >> g, n[1] >> g, n[2] >> g};
+            double hg[3] = {h->dx[0] * (1 << g), h->dx[1] * (1 << g), h->dx[2] * (1 << g)};
+            rc = build_hier(m->rep, ng, hg, 1, 0, true);
+            m->gcount = gd / P;
+            if (rc == PBX_OK && cudaMalloc(&m->gsrc, m->gcount * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                set_last_error("multigrid hierarchy allocation failed");
+                rc = PBX_ERR_NOMEM;
+            }
         }
     }
-    return PBX_OK;
+    if (rc != PBX_OK) mg_free(h);
+    return rc;
 }
 
 // z = M^-1 (r - mean): one V(nu, nu) cycle on S = -P.  mean: device scalar (may be nullptr = 0).
@@ -298,49 +472,31 @@ int mg_vcycle(pbx_handle_s *h, const double *r, const double *mean, double *z)
 {
     MgState *m = (MgState *)h->mg;
     if (!m) return PBX_ERR_ARG;
-    const int nl = (int)m->lev.size(), nu = m->nu;
-    m->lev[0].r = const_cast<double *>(r);
-    m->lev[0].z = z;
-    std::vector<double *> cur(nl), alt(nl);
-    // downward leg
-    for (int l = 0; l < nl; ++l) {
-        MgLevel &L = m->lev[l];
-        const double *mp = l == 0 ? mean : nullptr;
-        if (l == nl - 1) {
-            // coarsest grid: a fixed number of sweeps, ending in L.z
-            cur[l] = (MG_COARSE_SWEEPS & 1) ? L.z : L.t;
-            alt[l] = (MG_COARSE_SWEEPS & 1) ? L.t : L.z;
-            PBX_TRY(smooth_from_zero(h, L, L.r, mp, MG_COARSE_SWEEPS, &cur[l], &alt[l]));
-            break;
-        }
-        // nu pre-sweeps (the first from the zero guess) + nu post-sweeps = 2 nu - 1 buffer swaps: start
-        // in the spare so that the result ends in L.z
-        cur[l] = L.t;
-        alt[l] = L.z;
-        PBX_TRY(smooth_from_zero(h, L, L.r, mp, nu, &cur[l], &alt[l]));
-        PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l]));          // residual into the spare
-        MgLevel &C = m->lev[l + 1];
-        mg_restrict_kernel<<<dim3((C.lv.nx + MBX - 1) / MBX, (C.lv.ny + MBY - 1) / MBY, C.lv.nz), dim3(MBX, MBY), 0,
-                             h->stream>>>(L.lv, alt[l], C.r);
-        ++h->launches;
+    m->top.lev[0].r = const_cast<double *>(r);
+    m->top.lev[0].z = z;
+    int rc;
+    if (h->nranks == 1) {
+        rc = cycle(h, m->top, false, m->nu, mean, nullptr, no_below);
+    } else {
+        rc = cycle(h, m->top, true, m->nu, mean, m->gsrc,
+                   [&](const double **coarse, const double **lo, const double **hi) -> int {
+                       // level g: gather its right-hand side, solve the rest of the hierarchy on the
+                       // whole coarse grid (every rank the same), hand back my planes and their neighbours
+                       double *full = nullptr;
+                       PBX_TRY(dist_allgather(h, m->gsrc, m->gcount, &full));
+                       MgLevel &G = m->rep.lev[0];
+                       PBX_CUDA(cudaMemcpyAsync(G.r, full, G.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                       PBX_TRY(cycle(h, m->rep, false, m->nu, nullptr, nullptr, no_below));
+                       const size_t plane = (size_t)G.lv.nx * G.lv.ny;
+                       const int nzg = G.lv.nz, mine = nzg / h->nranks, k0 = h->rank * mine;
+                       *coarse = G.z + plane * k0;
+                       *lo = G.z + plane * ((k0 + nzg - 1) % nzg);
+                       *hi = G.z + plane * ((k0 + mine) % nzg);
+                       return PBX_OK;
+                   });
     }
-    // upward leg
-    for (int l = nl - 2; l >= 0; --l) {
-        MgLevel &L = m->lev[l];
-        const double *mp = l == 0 ? mean : nullptr;
-        mg_prolong_kernel<<<dim3((L.lv.nx + MBX - 1) / MBX, (L.lv.ny + MBY - 1) / MBY, (L.lv.nz + 3) / 4),
-                            dim3(MBX, MBY), 0, h->stream>>>(L.lv, m->lev[l + 1].z, cur[l]);
-        ++h->launches;
-        for (int s = 0; s < nu; ++s) {
-            PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l]));
-            std::swap(cur[l], alt[l]);
-        }
-        if (cur[l] != L.z) {
-            set_last_error("multigrid buffer parity broken");
-            return PBX_ERR_ARG;
-        }
-    }
-    m->lev[0].r = m->lev[0].z = nullptr;
+    m->top.lev[0].r = m->top.lev[0].z = nullptr;
+    PBX_TRY(rc);
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;
 }

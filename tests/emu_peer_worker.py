@@ -87,12 +87,52 @@ _, its2, _, why2, _ = h.cg_solve(np.asfortranarray(b[:, :, mine]), rtol=3e-1, ma
 cg_ok = cg_ok and why2 == why2a == 2 and its2 == its2a
 out = h.lapl(np.asfortranarray(f[:, :, mine]))
 errs["lapl_after_cg"] = np.max(np.abs(out - ref[:, :, mine])) / np.max(np.abs(ref))
+# the multigrid preconditioner on slabs (distributed levels with one-plane halo exchanges, the
+# coarse levels all-gathered and solved redundantly) against the single-rank cycle: the V-cycle is
+# the same arithmetic point for point, so z carries the same bits; the PCG the same iterations
+c = [(np.arange(m) + 0.5) * 2 * np.pi / m for m in (nx, ny, nz)]
+u = np.exp(np.sin(c[0])[:, None, None] + np.sin(c[1])[None, :, None] + np.sin(c[2])[None, None, :])
+hp = (2 * np.pi / nz,) * 3   # isotropic spacing: point Jacobi smooths it well
+whole_p = emu_lib.EmuHandle(nx, ny, nz, hp)
+h_p = emu_lib.EmuHandle(nx, ny, nzl, hp, slab=(rank, world))
+own_p = shared_memory.SharedMemory(name=f"pbxpeerp_{tag}_{rank}", create=True, size=nbytes.value)
+dist.barrier()
+segs_p = [own_p if r == rank else shared_memory.SharedMemory(name=f"pbxpeerp_{tag}_{r}") for r in range(world)]
+for r, sgm in enumerate(segs_p):
+    if r != rank:
+        resource_tracker.unregister(sgm._name, "shared_memory")
+bufs_p = (ctypes.c_void_p * world)(*[ctypes.addressof(ctypes.c_char.from_buffer(s_.buf)) for s_ in segs_p])
+emu_lib.check(lib, lib.pbx_slab_link_peers(h_p._h, bufs_p, world))
+dist.barrier()
+bu = whole_p.lapl(np.asfortranarray(u))
+whole_p.set_pc(_lib.PC_MG, 2)
+h_p.set_pc(_lib.PC_MG, 2)
+zw = whole_p.pc_apply(bu)
+zs = h_p.pc_apply(np.asfortranarray(bu[:, :, mine]))
+errs["mg_vcycle"] = float(np.max(np.abs(zs - zw[:, :, mine])) / np.max(np.abs(zw)))
+xw, itw, _, whyw, histw = whole_p.cg_solve(bu, rtol=1e-8, maxit=40)
+xq, itq, _, whyq, histq = h_p.cg_solve(np.asfortranarray(bu[:, :, mine]), rtol=1e-8, maxit=40)
+errs["pcg_x"] = float(np.max(np.abs(xq - xw[:, :, mine])) / np.max(np.abs(xw)))
+cg_ok = cg_ok and whyq == whyw == 2 and itq == itw and itq <= 20
+h_p.close()
+whole_p.close()
+del bufs_p
+for s_ in segs_p:
+    try:
+        s_.close()
+    except BufferError:
+        pass
+dist.barrier()
+try:
+    own_p.unlink()
+except FileNotFoundError:
+    pass
 # ranks agree on the iteration count (the status word derives from all-reduced sums)
 its_all = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
 dist.all_gather(its_all, torch.tensor([its], dtype=torch.int64))
 cg_ok = cg_ok and all(int(t) == its for t in its_all)
 
-tol = {"star": 0.0, "dot": 1e-12, "allreduce": 1e-15, "cg_x": 1e-6, "cg_hist": 1e-9}
+tol = {"mg_vcycle": 1e-14, "pcg_x": 1e-9, "star": 0.0, "dot": 1e-12, "allreduce": 1e-15, "cg_x": 1e-6, "cg_hist": 1e-9}
 ok = all(e <= tol.get(k, 1e-13) for k, e in errs.items()) and same_bits and cg_ok
 dist.barrier()
 h.close()
@@ -109,5 +149,5 @@ try:
 except FileNotFoundError:
     pass
 dist.destroy_process_group()
-print(("EMU_PEER_OK " if ok else "EMU_PEER_FAIL ") + f"its {its} vs {its1} why {why}; {its2} vs {its2a} why {why2}; bits {same_bits} " + str(errs))
+print(("EMU_PEER_OK " if ok else "EMU_PEER_FAIL ") + f"its {its} vs {its1} why {why}; {its2} vs {its2a} why {why2}; pcg {itq} vs {itw} why {whyq}; bits {same_bits} " + str(errs))
 sys.exit(0 if ok else 1)

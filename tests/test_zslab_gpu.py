@@ -127,6 +127,8 @@ def test_peer_boards_one_gpu(P):
     whole = pbx.Handle(nx, ny, nz, dx)
     ref = whole.lapl(f)
     x1, its1, _, why1, hist1 = whole.cg_solve(ref, rtol=1e-6, maxit=2000)
+    whole.set_pc(_lib.PC_MG, 2)
+    xm1, itm1, _, whym1, _ = whole.cg_solve(ref, rtol=1e-6, maxit=200)
     torch.cuda.synchronize()
     slabs = [pbx.Handle(nx, ny, nzl, dx, slab=(r, P)) for r in range(P)]
     streams = [torch.cuda.Stream() for _ in range(P)]
@@ -143,8 +145,11 @@ def test_peer_boards_one_gpu(P):
         with torch.cuda.stream(streams[r]):
             outs = [h.lapl(part) for _ in range(3)]
             x, its, _, why, hist = h.cg_solve(bpart, rtol=1e-6, maxit=2000)
+            # the multigrid-preconditioned CG on slabs (halo exchanges per level, coarse levels gathered)
+            h.set_pc(_lib.PC_MG, 2)
+            xm, itm, _, whym, _ = h.cg_solve(bpart, rtol=1e-6, maxit=200)
             h.synchronize()
-        res[r] = (outs, x, its, why, hist)
+        res[r] = (outs, x, its, why, hist, xm, itm, whym)
 
     threads = [threading.Thread(target=work, args=(r,)) for r in range(P)]
     for t in threads:
@@ -154,7 +159,8 @@ def test_peer_boards_one_gpu(P):
     assert all(r is not None for r in res), "a rank did not finish"
     scale = ref.abs().max().item()
     for r in range(P):
-        outs, x, its, why, hist = res[r]
+        outs, x, its, why, hist, xm, itm, whym = res[r]
+        assert whym == whym1 and abs(itm - itm1) <= 1, (itm, itm1, whym, whym1)
         for o in outs:
             assert (o - ref[r * nzl:(r + 1) * nzl]).abs().max().item() <= 1e-13 * scale
         assert why == why1 == 2 and abs(its - its1) <= 1, (its, its1, why)

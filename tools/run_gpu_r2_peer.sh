@@ -16,7 +16,7 @@ if [ "$N" -ge 2 ]; then
         --master-port 29555 tools/dist_check.py 512 > gpurun_out/r2_dist_check_w${W}_ps${PS}.log 2>&1
       tail -3 gpurun_out/r2_dist_check_w${W}_ps${PS}.log
       # C. the bench line (MatMult + CG time-to-solution)
-      PBX_PEER_SYNC=$PS timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 \
+      PBX_PEER_SYNC=$PS PBX_BENCH_MG_SLABS=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 \
         --master-port 29556 bench.py --gpus $W --no-cpu --no-e2e > gpurun_out/r2_bench_w${W}_ps${PS}.json 2> gpurun_out/r2_bench_w${W}_ps${PS}.err
       cat gpurun_out/r2_bench_w${W}_ps${PS}.json
     done
