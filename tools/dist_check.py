@@ -70,11 +70,37 @@ torch.cuda.synchronize()
 xerr = (xs - x1[rank * nzl:(rank + 1) * nzl]).norm().item() / x1.norm().item()
 m = min(len(hist1), len(hist2)) // 2
 herr = float(np.max(np.abs(hist1[:m] - hist2[:m]) / hist1[:m]))
-ok = err <= 1e-13 and gerr <= 1e-13 and derr <= 1e-12 and why1 == why2 == 2 and abs(its1 - its2) <= 1 and xerr <= 1e-5 and herr <= 1e-6
+# the multigrid-preconditioned CG on slabs (PBX_CHECK_MG=0 skips it): same cycle, same iteration count
+mg_note = "skipped"
+mg_ok = True
+if os.environ.get("PBX_CHECK_MG", "1") == "1":
+    from poissbox_b200 import _lib
+
+    hh = 2 * np.pi / n
+    c = (torch.arange(n, dtype=torch.float64, device=dev) + 0.5) * hh
+    u = torch.exp(torch.sin(c)[None, None, :] + torch.sin(c)[None, :, None] + torch.sin(c)[:, None, None]).contiguous()
+    wm = pbx.Handle(n, n, n, (hh,) * 3, device=local)
+    hm = pbx.Handle(n, n, nzl, (hh,) * 3, device=local, comm=comm.value)
+    bu = wm.lapl(u)
+    wm.set_pc(_lib.PC_MG, 2)
+    hm.set_pc(_lib.PC_MG, 2)
+    zw = wm.pc_apply(bu)
+    zs = hm.pc_apply(bu[sl].contiguous())
+    torch.cuda.synchronize()
+    zerr = (zs - zw[sl]).abs().max().item() / zw.abs().max().item()
+    xw, itw, _, whyw, _ = wm.cg_solve(bu, rtol=1e-8, maxit=100)
+    xq, itq, _, whyq, _ = hm.cg_solve(bu[sl].contiguous(), rtol=1e-8, maxit=100)
+    torch.cuda.synchronize()
+    xmerr = (xq - xw[sl]).norm().item() / xw.norm().item()
+    mg_ok = zerr <= 1e-13 and whyw == whyq == 2 and abs(itw - itq) <= 1 and xmerr <= 1e-6
+    mg_note = f"vcycle err {zerr:.2e} pcg its {itw} vs {itq} reasons {whyw},{whyq} xerr {xmerr:.2e}"
+    hm.close()
+    wm.close()
+ok = mg_ok and err <= 1e-13 and gerr <= 1e-13 and derr <= 1e-12 and why1 == why2 == 2 and abs(its1 - its2) <= 1 and xerr <= 1e-5 and herr <= 1e-6
 res = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
 print(f"rank {rank}/{world}: lapl err {err:.2e} grad/div/interp err {gerr:.2e} dot err {derr:.2e} cg its {its1} vs {its2} reasons {why1},{why2} "
-      f"xerr {xerr:.2e} hist err {herr:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+      f"xerr {xerr:.2e} hist err {herr:.2e}; multigrid: {mg_note} -> {'OK' if ok else 'FAIL'}", flush=True)
 h.close()
 whole.close()
 pbx.LIB.pbx_comm_destroy(comm)
