@@ -264,6 +264,11 @@ int pbx_pc_apply_device(pbx_handle h, const double *r, double *z);
  * ------------------------------------------------------------------------------------------- */
 int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], double *d2f,
                   int mode);
+/* `count` independent fields of the same box through one call, double-buffered on three streams
+ * (copy-in of the next field and copy-out of the previous one overlap the compute of the current
+ * one): f[k] -> d2f[k].  Host buffers should be pinned for the overlap to take place. */
+int pbx_lapl_host_batch(int nx, int ny, int nz, int count, const double *const *f, const double dx[3],
+                        double *const *d2f, int mode);
 int pbx_grad_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df);
 int pbx_div_host(int nx, int ny, int nz, const double *f, const double dx[3], double *df);
 int pbx_interp_host(int nx, int ny, int nz, const double *f, double *fi, int stagger);

@@ -75,6 +75,8 @@ SIGNATURES = {
     "pbx_set_pc": (c_int, [c_void_p, c_int, c_int]),
     "pbx_pc_apply_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp, c_int]),
+    "pbx_lapl_host_batch": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), _d3,
+                                    ctypes.POINTER(c_void_p), c_int]),
     "pbx_grad_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp]),
     "pbx_div_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp]),
     "pbx_interp_host": (c_int, [c_int, c_int, c_int, _dp, _dp, c_int]),

@@ -40,6 +40,23 @@ def lapl(f, dx, mode=MODE_FAST):
     return out
 
 
+def lapl_batch(fields, dx, mode=MODE_FAST):
+    """compact_schemes::lapl of several fields of one box in one call (pbx_lapl_host_batch): copies in,
+    compute and copies out of consecutive fields overlap on three streams"""
+    import ctypes
+
+    fs = [_f(f) for f in fields]
+    nx, ny, nz = fs[0].shape
+    if any(f.shape != (nx, ny, nz) for f in fs):
+        raise ValueError("lapl_batch expects fields of one shape")
+    outs = [_poisoned((nx, ny, nz)) for _ in fs]
+    n = len(fs)
+    pin = (ctypes.c_void_p * n)(*[f.ctypes.data for f in fs])
+    pout = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+    check(LIB.pbx_lapl_host_batch(nx, ny, nz, n, pin, _lib._d3(*[float(v) for v in dx]), pout, mode))
+    return outs
+
+
 def grad(f, dx):
     """compact_schemes::grad, :42-88 -> df(nx,ny,nz,3)"""
     f = _f(f)

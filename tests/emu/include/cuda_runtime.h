@@ -92,6 +92,14 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "pbx_emu error"; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
+{
+    *s = nullptr;   // everything runs in program order on the harness
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e)
 {
     *e = new pbx_emu_event();

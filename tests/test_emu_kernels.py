@@ -340,3 +340,24 @@ def test_emu_tridsol_line_major_tma(n, nl, pad, monkeypatch):
             assert lib.pbx_emu_tensor_maps_total() - maps0 == 6, "the TMA kernel did not run"
         assert np.array_equal(d[:n].T, want_p) and np.array_equal(b, b0)
         assert np.all(d[n:] == 73.29)
+
+
+def test_emu_lapl_host_batch():
+    """pbx_lapl_host_batch: several fields of one box per call (double-buffered staging slots, three
+    streams on the GPU): every output equals the single-field call's, for more fields than slots"""
+    from poissbox_b200 import _lib
+
+    lib = emu_lib.load()
+    n, dx = (32, 16, 16), (0.1, 0.2, 0.3)
+    rng = np.random.default_rng(0)
+    fs = [emu_lib.aligned(np.asfortranarray(rng.uniform(-1, 1, n))) for _ in range(5)]
+    outs = [emu_lib.new_field(n) for _ in fs]
+    pin = (ctypes.c_void_p * 5)(*[f.ctypes.data for f in fs])
+    pout = (ctypes.c_void_p * 5)(*[o.ctypes.data for o in outs])
+    for mode in (0, 1):
+        emu_lib.check(lib, lib.pbx_lapl_host_batch(*n, 5, pin, _lib._d3(*dx), pout, mode))
+        h = handle(n, dx)
+        h.set_mode(mode)
+        assert all(np.array_equal(h.lapl(f), o) for f, o in zip(fs, outs))
+        h.close()
+    assert lib.pbx_lapl_host_batch(*n, 0, pin, _lib._d3(*dx), pout, 0) != 0
