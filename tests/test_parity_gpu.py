@@ -106,7 +106,7 @@ def test_tridsol_batch_strided():
         assert np.array_equal(got, want)
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_TDMA_TMA") != "1",
+@pytest.mark.skipif(os.environ.get("PBX_TEST_TDMA_TMA") != "1" and os.environ.get("PBX_TEST_ROUND2") != "1",
                     reason="line-major TMA tridsol kernels (pbx_tdma_tma.cu) were written after the round's GPU "
                            "budget was spent: CPU-harness tested only (test_emu_tridsol_line_major_tma); set "
                            "PBX_TEST_TDMA_TMA=1 to run them on the GPU")
@@ -139,6 +139,19 @@ def test_tridsol_line_major_tma(n, nl, pad, monkeypatch):
                 got[tma] = (arrs[1].cpu().numpy(), arrs[3].cpu().numpy())
             assert np.array_equal(got["1"][1][:, :n], want)
             assert np.array_equal(got["0"][0], got["1"][0]) and np.array_equal(got["0"][1], got["1"][1])
+
+
+@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
+                    reason="pbx_lapl_host_batch was written after the round's GPU budget was spent: CPU-harness "
+                           "tested only (test_emu_lapl_host_batch); PBX_TEST_ROUND2=1 runs it on the GPU")
+def test_lapl_host_batch():
+    rng = np.random.default_rng(8)
+    n, dx = (64, 32, 48), (0.1, 0.2, 0.3)
+    fs = [np.asfortranarray(rng.uniform(-1, 1, n)) for _ in range(5)]
+    for mode in (pbx.MODE_FAST, pbx.MODE_REFERENCE):
+        outs = cs.lapl_batch(fs, dx, mode=mode)
+        for f, o in zip(fs, outs):
+            assert np.array_equal(o, cs.lapl(f, dx, mode=mode))
 
 
 # ------------------------------------------------------------------------------------ 1-D operators

@@ -4,6 +4,13 @@
 # trap after ~2 minutes if a peer never shows up.
 set -x
 mkdir -p gpurun_out
+# 0. everything that is gated because it has never run on a GPU (peer boards on one GPU, TMA line-major
+#    tridsol, host batch), each in its own process so that a trap cannot poison the next
+for K in peer_boards line_major_tma host_batch; do
+  PBX_TEST_ROUND2=1 timeout 600 python -m pytest tests -m gpu -k $K -q -x 2>&1 | tail -4 > gpurun_out/r2_gated_$K.log
+  cat gpurun_out/r2_gated_$K.log
+done
+timeout 200 python tools/prof_ops.py 256 > gpurun_out/r2_prof_ops.log 2>&1; tail -8 gpurun_out/r2_prof_ops.log
 # A. P slab handles of one process on one GPU, own streams + host threads (tests/test_zslab_gpu.py)
 PBX_TEST_PEER_BOARDS=1 timeout 600 python -m pytest tests/test_zslab_gpu.py -k peer_boards -q -x 2>&1 | tail -5 > gpurun_out/r2_peer_onegpu.log
 cat gpurun_out/r2_peer_onegpu.log
