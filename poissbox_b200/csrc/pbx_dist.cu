@@ -349,16 +349,16 @@ static void set_recv_pointers(DistState *d)
 }
 
 // bufs[r]: rank r's receive buffer as addressable from this device (bufs[rank] = my own).  With
-// only the two neighbours given the boundary sweep stores its messages straight into their
-// memory; with ALL ranks given the peer boards take over the barrier and the all-reduce as well.
-static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs)
+// the two neighbours given the boundary sweep stores its messages straight into their memory;
+// with ALL ranks given and `boards` set the peer boards take over the barrier and the all-reduce.
+static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs, bool boards)
 {
     const size_t per = d->per();
     for (int par = 0; par < 2; ++par) {
         d->peer_up_recv_lo[par] = (double *)bufs[d->upper] + (size_t)(2 * par) * per;
         d->peer_lo_recv_up[par] = (double *)bufs[d->lower] + (size_t)(2 * par + 1) * per;
     }
-    bool all = h->nranks <= PEER_MAXR;
+    bool all = boards && h->nranks <= PEER_MAXR;
     for (int r = 0; r < h->nranks && all; ++r) all = bufs[r] != nullptr;
     d->peer_sync = false;
     if (!all) return;
@@ -478,7 +478,7 @@ int dist_attach(pbx_handle_s *h)
     }
     void *bufs[PEER_MAXR] = {nullptr};
     for (int r = 0; r < n; ++r) bufs[r] = r == h->rank ? (void *)d->rbuf : d->peer_map[r];
-    set_peer_pointers(h, d, bufs);
+    set_peer_pointers(h, d, bufs, want_all);
     return PBX_OK;
 }
 
@@ -852,7 +852,7 @@ int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n)
         d->rbuf_owned = false;
         set_recv_pointers(d);
     }
-    set_peer_pointers(h, d, bufs);
+    set_peer_pointers(h, d, bufs, true);
     return PBX_OK;
 }
 
