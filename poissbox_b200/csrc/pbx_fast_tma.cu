@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "pbx_fast_common.cuh"
 
@@ -103,7 +104,14 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
     }
 }
 
-template <bool ZPASS, bool SLAB, bool SEG>
+// ROT (opt-in, PBX_YZ_ROT=1): the tiles are fetched with the 128-byte swizzle and threads with an odd
+// chunk index read the two halves of their chunk's second index bit in swapped order.  Without it the
+// four chunk rows a warp reads per instruction lie 16 rows apart, i.e. in the same banks (the profile of
+// round 1: 37-43 % of the passes' shared-memory wavefronts are bank conflicts); with it the two rows of
+// a half-warp differ in bit 2 of (row & 7), the swizzle sends them to different halves of the 128-byte
+// bank line, and 16 register swaps put the values back in order.  Whole lines in one CTA only (no
+// segments, no slab), and for the z pass one line per tile row (G == 1: lines of 512 points).
+template <bool ZPASS, bool SLAB, bool SEG, bool ROT>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -113,7 +121,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     extern __shared__ __align__(1024) unsigned char smraw[];
     YZShared &S = *reinterpret_cast<YZShared *>(smraw);
     const int tid = threadIdx.x;
-    if ((smem_u32(smraw) & 127u) != 0) __trap();   // TMA destinations need 128-byte alignment
+    if ((smem_u32(smraw) & (ROT ? 1023u : 127u)) != 0) __trap();   // TMA destinations: 128 bytes, swizzled 1 KiB
 
     if (tid == 0) {
         mbar_init(&S.full, 1);
@@ -155,7 +163,42 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             slab_load_messages(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, lo9, up9);
         mbar_wait(&S.full, (uint32_t)(it & 1));
         double a[LC], eb[LC + 6];
-        {
+        if (ROT) {
+            const int i0 = t * LC, odd = t & 1, flip = 4 * odd;
+            const int x = grp * XW + tx;                       // column of the 16-wide tile
+            const int qb = (ZPASS ? 0 : tz * npts) + i0;       // first tile row of my chunk (a multiple of 16)
+            // load k fetches row qb + (k ^ flip); (row & 7) = (k & 7) ^ flip =: c ^ flip.  Eight base
+            // offsets, one per c; the rest of the address is the immediate 16 k.
+            int B[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                B[c] = (qb + ((c & 4) ? -flip : flip)) * 16 + ((((x >> 1) ^ c ^ flip) << 1) | (x & 1));
+#pragma unroll
+            for (int k = 0; k < LC; ++k) {
+                a[k] = S.tile[0][B[k & 7] + 16 * k];
+                eb[k + 3] = S.tile[1][B[k & 7] + 16 * k];
+            }
+#pragma unroll
+            for (int k = 0; k < LC; ++k) {
+                if (!(k & 4)) {     // the value fetched by load k belongs to index k ^ flip
+                    const double a0 = a[k], a1 = a[k | 4], b0 = eb[k + 3], b1 = eb[(k | 4) + 3];
+                    a[k] = odd ? a1 : a0;
+                    a[k | 4] = odd ? a0 : a1;
+                    eb[k + 3] = odd ? b1 : b0;
+                    eb[(k | 4) + 3] = odd ? b0 : b1;
+                }
+            }
+            const int q0 = (ZPASS ? 0 : tz * npts);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int il = i0 - 3 + k, ir = i0 + LC + k;
+                if (il < 0) il += npts;
+                if (ir >= npts) ir -= npts;
+                const int ql = q0 + il, qr = q0 + ir;
+                eb[k] = S.tile[1][ql * 16 + ((((x >> 1) ^ (ql & 7)) << 1) | (x & 1))];
+                eb[LC + 3 + k] = S.tile[1][qr * 16 + ((((x >> 1) ^ (qr & 7)) << 1) | (x & 1))];
+            }
+        } else {
             const double *ta = S.tile[0] + soff, *tb = S.tile[1] + soff;
             const int i0 = t * LC;
 #pragma unroll
@@ -413,7 +456,7 @@ EncodeTiledFn encode_fn()
 }
 
 // 3-D map of a brick for the y / z pass tiles
-bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &p)
+bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &p, bool swizzle = false)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -423,7 +466,7 @@ bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &
                          (cuuint32_t)(p.zdir ? p.RB : p.G)};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims, strides, box,
-              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -563,34 +606,42 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     p.rev = rev;
     p.M = fc.M;
     p.D = fc.D[dir];
+    const bool segd = p.seg.nseg > 1;
+    const char *re = getenv("PBX_YZ_ROT");
+    const bool rot = re && re[0] == '1' && !segd && !zo.open && (dir == 1 || p.G == 1) && p.T >= 2 && g.nx % XWT == 0;
     CUtensorMap m0, m1;
-    if (!make_map_yz(&m0, in0, g, p) || !make_map_yz(&m1, in1, g, p)) return PBX_ERR_UNSUPPORTED;
+    if (!make_map_yz(&m0, in0, g, p, rot) || !make_map_yz(&m1, in1, g, p, rot)) return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(YZShared);
     static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
         const int a = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, true, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, true, false>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    const bool segd = p.seg.nseg > 1;
-    if (dir == 1 && !segd)
-        yz_tma_kernel<false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    if (rot && dir == 1)
+        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    else if (rot)
+        yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+    else if (dir == 1 && !segd)
+        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
     else if (dir == 1)
-        yz_tma_kernel<false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
     else if (zo.open)
-        yz_tma_kernel<true, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     else if (!segd)
-        yz_tma_kernel<true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     else
-        yz_tma_kernel<true, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

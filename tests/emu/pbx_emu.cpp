@@ -11,6 +11,7 @@
 namespace pbx_emu {
 
 long long tensor_maps_total();
+long long tensor_maps3_swizzled_total();
 
 uint3 g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
@@ -201,7 +202,7 @@ int device_count()
 }
 
 namespace {
-long long g_maps = 0;
+long long g_maps = 0, g_maps3_swz = 0;
 CUresult encode_tiled(CUtensorMap *m, CUtensorMapDataType dt, cuuint32_t rank, void *base,
                       const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box,
                       const cuuint32_t *estr, CUtensorMapInterleave, CUtensorMapSwizzle sw,
@@ -211,6 +212,7 @@ CUresult encode_tiled(CUtensorMap *m, CUtensorMapDataType dt, cuuint32_t rank, v
     if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || rank < 1 || rank > 3) return CUDA_ERROR_INVALID_VALUE;
     if ((uintptr_t)base & 15) return CUDA_ERROR_INVALID_VALUE;
     ++g_maps;
+    if (rank == 3 && sw == CU_TENSOR_MAP_SWIZZLE_128B) ++g_maps3_swz;
     memset((void *)m, 0, sizeof *m);
     m->base = (double *)base;
     m->rank = (int)rank;
@@ -232,6 +234,7 @@ CUresult encode_tiled(CUtensorMap *m, CUtensorMapDataType dt, cuuint32_t rank, v
 }  // namespace
 
 long long tensor_maps_total() { return g_maps; }
+long long tensor_maps3_swizzled_total() { return g_maps3_swz; }
 
 void *driver_entry_point(const char *name)
 {
@@ -245,3 +248,4 @@ void *driver_entry_point(const char *name)
 
 extern "C" long long pbx_emu_launches_total(void) { return pbx_emu::launches_total(); }
 extern "C" long long pbx_emu_tensor_maps_total(void) { return pbx_emu::tensor_maps_total(); }
+extern "C" long long pbx_emu_tensor_maps3_swizzled_total(void) { return pbx_emu::tensor_maps3_swizzled_total(); }

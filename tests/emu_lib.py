@@ -29,6 +29,7 @@ def load():
             fn.argtypes = args
         lib.pbx_emu_launches_total.restype = ctypes.c_longlong
         lib.pbx_emu_tensor_maps_total.restype = ctypes.c_longlong
+        lib.pbx_emu_tensor_maps3_swizzled_total.restype = ctypes.c_longlong
         _cached = lib
     return _cached
 

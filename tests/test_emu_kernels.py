@@ -361,3 +361,25 @@ def test_emu_lapl_host_batch():
         assert all(np.array_equal(h.lapl(f), o) for f, o in zip(fs, outs))
         h.close()
     assert lib.pbx_lapl_host_batch(*n, 0, pin, _lib._d3(*dx), pout, 0) != 0
+
+
+@pytest.mark.parametrize("shape", [(32, 512, 16), (16, 64, 512), (48, 256, 32), (16, 32, 512), (32, 128, 16)])
+def test_emu_yz_rot_bit_identical(shape, monkeypatch):
+    """PBX_YZ_ROT=1: swizzled y/z tiles read in a bank-conflict-free order and put back in place by
+    register swaps -- the same bits as the unswizzled TMA kernels and the generic ones, dot included"""
+    dx = tuple(1.0 / n for n in shape)
+    f = field(shape, 21)
+    lib = emu_lib.load()
+    h = handle(shape, dx)
+    ref, dref = h.lapl_dot(f)
+    monkeypatch.setenv("PBX_YZ_ROT", "1")
+    maps0 = lib.pbx_emu_tensor_maps3_swizzled_total()
+    out, dot = h.lapl_dot(f)
+    # swizzled 3-D maps: two per rotated pass (y always; z when the tile holds one line per row)
+    assert lib.pbx_emu_tensor_maps3_swizzled_total() - maps0 == (4 if shape[2] == 512 else 2)
+    assert np.array_equal(out, ref) and dot == dref
+    monkeypatch.delenv("PBX_YZ_ROT")
+    g = handle(shape, dx, no_tma="1")
+    assert np.array_equal(g.lapl(f), ref)
+    h.close()
+    g.close()

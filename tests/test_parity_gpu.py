@@ -154,6 +154,25 @@ def test_lapl_host_batch():
             assert np.array_equal(o, cs.lapl(f, dx, mode=mode))
 
 
+@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
+                    reason="PBX_YZ_ROT (swizzled y/z tiles) was written after the round's GPU budget was spent: "
+                           "CPU-harness tested only (test_emu_yz_rot_bit_identical)")
+@pytest.mark.parametrize("shape", [(512, 512, 512), (64, 256, 512), (32, 128, 64)])
+def test_yz_rot_bit_identical(shape, monkeypatch):
+    import torch
+
+    nx, ny, nz = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    h = pbx.Handle(nx, ny, nz, (1.0 / nx, 1.0 / ny, 1.0 / nz))
+    ref, dref = h.lapl_dot(f)
+    monkeypatch.setenv("PBX_YZ_ROT", "1")
+    out, dot = h.lapl_dot(f)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and dot.item() == dref.item()
+    h.close()
+
+
 # ------------------------------------------------------------------------------------ 1-D operators
 @pytest.mark.parametrize("n", [3, 4, 5, 37, 128, 1000])
 def test_lines_bit_exact(n):

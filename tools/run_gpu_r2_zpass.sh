@@ -16,3 +16,10 @@ for shape in "2048 512 128" "1024 512 256" "512 512 512"; do
     python tools/prof_lapl.py --shape $1 $2 $3 > gpurun_out/r2_zpass_ncu_$3.log 2>&1
   tail -3 gpurun_out/r2_zpass_plain_$3.log
 done
+# the same with the bank-conflict-free tile reads (PBX_YZ_ROT=1: swizzled tiles + register swaps)
+for rot in 0 1; do
+  PBX_YZ_ROT=$rot timeout 120 python tools/prof_lapl.py --n 512 > gpurun_out/r2_rot${rot}_plain.log 2>&1 && \
+  PBX_YZ_ROT=$rot timeout 300 ncu --metrics $M --clock-control none -k regex:yz_tma_kernel --csv --log-file gpurun_out/r2_rot${rot}_ncu.csv \
+    python tools/prof_lapl.py --n 512 > gpurun_out/r2_rot${rot}_ncu.log 2>&1
+  tail -2 gpurun_out/r2_rot${rot}_plain.log
+done
