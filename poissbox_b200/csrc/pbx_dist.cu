@@ -663,6 +663,23 @@ int dist_halo_planes(pbx_handle_s *h, const double *field, size_t plane, int nz,
     return dist_line_msgs(h, 0, lo, hi);
 }
 
+// The same exchange with the copies left to the producing kernel: begin hands out where my bottom and
+// top plane go (the neighbours' buffers of the next round), end is the barrier of that round and returns
+// the planes that arrived.
+int dist_halo_begin(pbx_handle_s *h, double **dn, double **up)
+{
+    DistState *d = (DistState *)h->dist;
+    if (!d || !dist_connected(h)) return PBX_ERR_ARG;
+    PBX_TRY(dist_begin_epoch(h));
+    return dist_line_dst(h, 0, dn, up);
+}
+
+int dist_halo_end(pbx_handle_s *h, const double **lo, const double **hi)
+{
+    PBX_TRY(dist_exchange_run(h));
+    return dist_line_msgs(h, 0, lo, hi);
+}
+
 // All-gather `count` doubles per rank, rank order, into *full (valid until the gather after next).
 // Peer boards: every rank copies its part into every rank's gather area (two parities) and an
 // all-reduce over the boards is the barrier; otherwise ncclAllGather.

@@ -343,6 +343,8 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count);
 // multigrid on slabs (pbx_mg.cu): one plane each way, and an all-gather of `count` doubles per rank
 int dist_halo_planes(pbx_handle_s *h, const double *field, size_t plane, int nz, const double **lo,
                      const double **hi);
+int dist_halo_begin(pbx_handle_s *h, double **dn, double **up);
+int dist_halo_end(pbx_handle_s *h, const double **lo, const double **hi);
 int dist_allgather(pbx_handle_s *h, const double *mine, size_t count, double **full);
 int mg_slab_plan(int nx, int ny, int nzl, int nranks, size_t *gather_doubles);
 // true when the handle can talk to the other ranks (NCCL communicator or linked peer boards)

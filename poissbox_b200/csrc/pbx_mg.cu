@@ -50,7 +50,8 @@ template <int MODE>
 __global__ void __launch_bounds__(MBX * MBY)
 mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
                 const double *__restrict__ r, const double *__restrict__ mean,
-                double *__restrict__ out, const double *__restrict__ zlo, const double *__restrict__ zhi)
+                double *__restrict__ out, const double *__restrict__ zlo, const double *__restrict__ zhi,
+                double *__restrict__ pdn, double *__restrict__ pup)
 {
     const int nx = lv.nx, ny = lv.ny, nz = lv.nz;
     const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
@@ -88,13 +89,18 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
             double sz = lv.cx * (c2 - zim[u] - zip[u]);
             sz = fma(lv.cy, c2 - zjm[u] - zjp[u], sz);
             sz = fma(lv.cz, c2 - zc[u] - zc[u + 2], sz);
+            double val;
             if (MODE == 2) {
                 const double rb = centre - m;
-                out[col + plane * (k0 + u)] = lv.wd * (rb + fma(-lv.wd, sz, rb));
+                val = lv.wd * (rb + fma(-lv.wd, sz, rb));
             } else {
                 const double res = (rr[u] - m) - sz;
-                out[col + plane * (k0 + u)] = MODE == 0 ? fma(lv.wd, res, centre) : res;
+                val = MODE == 0 ? fma(lv.wd, res, centre) : res;
             }
+            out[col + plane * (k0 + u)] = val;
+            // slabs: my bottom / top plane goes straight into the neighbours' halo buffers as well
+            if (pdn && k0 + u == 0) pdn[col] = val;
+            if (pup && k0 + u == nz - 1) pup[col] = val;
         }
     }
 }
@@ -102,12 +108,17 @@ mg_sweep_kernel(const __grid_constant__ Lv lv, const double *__restrict__ z,
 // out = wd (r - m): the first Jacobi sweep from a zero guess
 __global__ void __launch_bounds__(256)
 mg_scale_kernel(size_t n, double wd, const double *__restrict__ r, const double *__restrict__ mean,
-                double *__restrict__ out)
+                double *__restrict__ out, size_t plane, double *__restrict__ pdn, double *__restrict__ pup)
 {
     const double m = mean ? *mean : 0.0;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t st = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += st) out[i] = wd * (r[i] - m);
+    for (; i < n; i += st) {
+        const double val = wd * (r[i] - m);
+        out[i] = val;
+        if (pdn && i < plane) pdn[i] = val;
+        if (pup && i >= n - plane) pup[i - (n - plane)] = val;
+    }
 }
 
 // coarse(I,J,K) = sum over the 4x4x4 fine cells 2I-1 .. 2I+2 (periodic) with weights
@@ -115,7 +126,8 @@ mg_scale_kernel(size_t n, double wd, const double *__restrict__ r, const double 
 // coarse cells of plane blockIdx.z.
 __global__ void __launch_bounds__(MBX * MBY)
 mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fine,
-                   double *__restrict__ coarse, const double *__restrict__ flo, const double *__restrict__ fhi)
+                   double *__restrict__ coarse, const double *__restrict__ flo, const double *__restrict__ fhi,
+                   double *__restrict__ pdn, double *__restrict__ pup)
 {
     const int cnx = lv.nx / 2, cny = lv.ny / 2;
     const int I = blockIdx.x * MBX + threadIdx.x, J = blockIdx.y * MBY + threadIdx.y, K = blockIdx.z;
@@ -143,6 +155,8 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
         s = fma(w[c], sk, s);
     }
     coarse[I + (size_t)cnx * (J + (size_t)cny * K)] = s;
+    if (pdn && K == 0) pdn[I + (size_t)cnx * J] = s;
+    if (pup && K == (int)gridDim.z - 1) pup[I + (size_t)cnx * J] = s;
 }
 
 // fine += Pr coarse: fine cell 2I takes 3/4 c(I) + 1/4 c(I-1), cell 2I+1 takes 3/4 c(I) + 1/4 c(I+1),
@@ -151,7 +165,8 @@ mg_restrict_kernel(const __grid_constant__ Lv lv, const double *__restrict__ fin
 // first (16 loads issued together), then along z.
 __global__ void __launch_bounds__(MBX * MBY)
 mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coarse,
-                  double *__restrict__ fine, const double *__restrict__ clo, const double *__restrict__ chi)
+                  double *__restrict__ fine, const double *__restrict__ clo, const double *__restrict__ chi,
+                  double *__restrict__ pdn, double *__restrict__ pup)
 {
     const int i = blockIdx.x * MBX + threadIdx.x, j = blockIdx.y * MBY + threadIdx.y;
     if (i >= lv.nx || j >= lv.ny) return;
@@ -181,7 +196,10 @@ mg_prolong_kernel(const __grid_constant__ Lv lv, const double *__restrict__ coar
         const int k = 2 * K0 + u;                     // fine plane; parent K0 + u / 2
         if (k < lv.nz) {
             const double par = q[1 + u / 2], oth = (u & 1) ? q[2 + u / 2] : q[u / 2];
-            fine[col + plane * k] += fma(0.25, oth, 0.75 * par);
+            const double val = fine[col + plane * k] + fma(0.25, oth, 0.75 * par);
+            fine[col + plane * k] = val;
+            if (pdn && k == 0) pdn[col] = val;
+            if (pup && k == lv.nz - 1) pup[col] = val;
         }
     }
 }
@@ -219,71 +237,103 @@ struct MgState {
 
 namespace {
 
+// where a producer kernel publishes its bottom / top plane (the neighbours' halo buffers), and where a
+// consumer finds the planes next to its slab
+struct Pub {
+    double *dn = nullptr, *up = nullptr;
+};
+struct Nb {
+    const double *lo = nullptr, *hi = nullptr;
+};
+
 int sweep(pbx_handle_s *h, int mode, const Lv &lv, const double *z, const double *r, const double *mean,
-          double *out, const double *zlo = nullptr, const double *zhi = nullptr)
+          double *out, Nb nb, Pub pub)
 {
     dim3 block(MBX, MBY), grid((lv.nx + MBX - 1) / MBX, (lv.ny + MBY - 1) / MBY, (lv.nz + MKZ - 1) / MKZ);
     if (mode == 0)
-        mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
+        mg_sweep_kernel<0><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, nb.lo, nb.hi, pub.dn, pub.up);
     else if (mode == 1)
-        mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
+        mg_sweep_kernel<1><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, nb.lo, nb.hi, pub.dn, pub.up);
     else
-        mg_sweep_kernel<2><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, zlo, zhi);
+        mg_sweep_kernel<2><<<grid, block, 0, h->stream>>>(lv, z, r, mean, out, nb.lo, nb.hi, pub.dn, pub.up);
     ++h->launches;
     return PBX_OK;
 }
 
-int restrict_to(pbx_handle_s *h, const Lv &fine, const double *res, double *coarse_r,
-                const double *flo = nullptr, const double *fhi = nullptr)
+int restrict_to(pbx_handle_s *h, const Lv &fine, const double *res, double *coarse_r, Nb nb, Pub pub)
 {
     const int cnx = fine.nx / 2, cny = fine.ny / 2, cnz = fine.nz / 2;
     mg_restrict_kernel<<<dim3((cnx + MBX - 1) / MBX, (cny + MBY - 1) / MBY, cnz), dim3(MBX, MBY), 0, h->stream>>>(
-        fine, res, coarse_r, flo, fhi);
+        fine, res, coarse_r, nb.lo, nb.hi, pub.dn, pub.up);
     ++h->launches;
     return PBX_OK;
 }
 
-int prolong_add(pbx_handle_s *h, const Lv &fine, const double *coarse_z, double *fine_z,
-                const double *clo = nullptr, const double *chi = nullptr)
+int prolong_add(pbx_handle_s *h, const Lv &fine, const double *coarse_z, double *fine_z, Nb nb, Pub pub)
 {
     mg_prolong_kernel<<<dim3((fine.nx + MBX - 1) / MBX, (fine.ny + MBY - 1) / MBY, (fine.nz + 3) / 4),
-                        dim3(MBX, MBY), 0, h->stream>>>(fine, coarse_z, fine_z, clo, chi);
+                        dim3(MBX, MBY), 0, h->stream>>>(fine, coarse_z, fine_z, nb.lo, nb.hi, pub.dn, pub.up);
     ++h->launches;
     return PBX_OK;
 }
 
 unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
-// the planes next to my slab of `field` (slab = true), or nothing (periodic brick)
-int halo(pbx_handle_s *h, bool slab, const Lv &lv, const double *field, const double **lo, const double **hi)
-{
-    *lo = *hi = nullptr;
-    if (!slab) return PBX_OK;
-    return dist_halo_planes(h, field, (size_t)lv.nx * lv.ny, lv.nz, lo, hi);
-}
+// The halo protocol of a slab cycle.  A kernel whose output the next kernel needs WITH its neighbour
+// planes publishes its own bottom and top plane into the neighbours' buffers while it writes them
+// (begin: the buffers of the next exchange round); the consumer is launched after the barrier of that
+// round (end) with the planes that arrived.  One round is in flight at a time; the receive buffers
+// alternate, so a kernel may read the planes of round e while it publishes for round e + 1.
+struct Halo {
+    pbx_handle_s *h;
+    bool slab;
+    int begin(Pub *p) const
+    {
+        *p = Pub();
+        return slab ? dist_halo_begin(h, &p->dn, &p->up) : PBX_OK;
+    }
+    int end(Nb *n) const
+    {
+        *n = Nb();
+        return slab ? dist_halo_end(h, &n->lo, &n->hi) : PBX_OK;
+    }
+    // a field no kernel of the cycle produced (the right-hand side of the finest level)
+    int planes(const Lv &lv, const double *field, Nb *n) const
+    {
+        *n = Nb();
+        return slab ? dist_halo_planes(h, field, (size_t)lv.nx * lv.ny, lv.nz, &n->lo, &n->hi) : PBX_OK;
+    }
+};
 
-// `count` Jacobi sweeps on S z = r - mean from a zero guess; the result ends in *cur (the spare in *alt)
-int smooth_from_zero(pbx_handle_s *h, bool slab, const MgLevel &L, const double *r, const double *mean,
-                     int count, double **cur, double **alt)
+// `count` Jacobi sweeps on S z = r - mean from a zero guess; the result ends in *cur (the spare in
+// *alt) and has been published (Halo::begin) if `publish`.  r_nb: the planes next to r (count >= 2).
+int smooth_from_zero(const Halo &H, const MgLevel &L, const double *r, Nb r_nb, const double *mean, int count,
+                     double **cur, double **alt, bool publish)
 {
-    const double *lo, *hi;
+    pbx_handle_s *h = H.h;
+    Pub pub;
     int done = 1;
     if (count >= 2) {
         // two sweeps in one pass; the caller's buffer parity counts sweeps, so the result goes where
         // the second sweep would have put it
-        PBX_TRY(halo(h, slab, L.lv, r, &lo, &hi));
-        PBX_TRY(sweep(h, 2, L.lv, r, r, mean, *alt, lo, hi));
+        if (count > 2 || publish) PBX_TRY(H.begin(&pub));
+        PBX_TRY(sweep(h, 2, L.lv, r, r, mean, *alt, r_nb, pub));
         std::swap(*cur, *alt);
         done = 2;
     } else {
         unsigned nb = blocks_for(L.n);
         if (nb > 148 * 16) nb = 148 * 16;
-        mg_scale_kernel<<<nb, 256, 0, h->stream>>>(L.n, L.lv.wd, r, mean, *cur);
+        if (publish) PBX_TRY(H.begin(&pub));
+        mg_scale_kernel<<<nb, 256, 0, h->stream>>>(L.n, L.lv.wd, r, mean, *cur, (size_t)L.lv.nx * L.lv.ny, pub.dn,
+                                                   pub.up);
         ++h->launches;
     }
     for (int s = done; s < count; ++s) {
-        PBX_TRY(halo(h, slab, L.lv, *cur, &lo, &hi));
-        PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt, lo, hi));
+        Nb nbp;
+        PBX_TRY(H.end(&nbp));
+        pub = Pub();
+        if (s + 1 < count || publish) PBX_TRY(H.begin(&pub));
+        PBX_TRY(sweep(h, 0, L.lv, *cur, r, mean, *alt, nbp, pub));
         std::swap(*cur, *alt);
     }
     return PBX_OK;
@@ -344,49 +394,65 @@ int build_hier(MgHier &H, const int n0[3], const double hh0[3], int zdiv, int ma
 // One V(nu, nu) cycle on hierarchy H (lev[0].r and lev[0].z set by the caller).  slab: the levels are
 // my planes of a z-decomposed box.  `below`: called when the downward leg has produced the right-hand
 // side `next_r` of the level under H's last one (nullptr: H ends with the coarsest grid); it returns
-// that level's solution as (coarse, clo, chi).
+// that level's solution as (coarse, planes next to my part of it).
 template <class Below>
-int cycle(pbx_handle_s *h, MgHier &H, bool slab, int nu, const double *mean, double *next_r, Below below)
+int cycle(pbx_handle_s *h, MgHier &Hi, bool slab, int nu, const double *mean, double *next_r, Below below)
 {
-    const int nl = (int)H.lev.size();
+    const Halo H{h, slab};
+    const int nl = (int)Hi.lev.size();
     std::vector<double *> cur(nl), alt(nl);
-    const double *lo, *hi;
     const int ndown = next_r ? nl : nl - 1;        // levels that smooth, form a residual and restrict it
     for (int l = 0; l < nl; ++l) {
-        MgLevel &L = H.lev[l];
+        MgLevel &L = Hi.lev[l];
         const double *mp = l == 0 ? mean : nullptr;
+        const int count = l == ndown ? MG_COARSE_SWEEPS : nu;
+        // the planes next to r: published by the restriction that produced it, or (finest level) fetched
+        Nb r_nb;
+        if (count >= 2) PBX_TRY(l == 0 ? H.planes(L.lv, L.r, &r_nb) : H.end(&r_nb));
         if (l == ndown) {
             // coarsest grid: a fixed number of sweeps, ending in L.z
             cur[l] = (MG_COARSE_SWEEPS & 1) ? L.z : L.t;
             alt[l] = (MG_COARSE_SWEEPS & 1) ? L.t : L.z;
-            PBX_TRY(smooth_from_zero(h, slab, L, L.r, mp, MG_COARSE_SWEEPS, &cur[l], &alt[l]));
+            PBX_TRY(smooth_from_zero(H, L, L.r, r_nb, mp, count, &cur[l], &alt[l], l > 0));
             break;
         }
         // nu pre-sweeps (the first from the zero guess) + nu post-sweeps = 2 nu - 1 buffer swaps: start
         // in the spare so that the result ends in L.z
         cur[l] = L.t;
         alt[l] = L.z;
-        PBX_TRY(smooth_from_zero(h, slab, L, L.r, mp, nu, &cur[l], &alt[l]));
-        PBX_TRY(halo(h, slab, L.lv, cur[l], &lo, &hi));
-        PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l], lo, hi));          // residual into the spare
-        PBX_TRY(halo(h, slab, L.lv, alt[l], &lo, &hi));
-        PBX_TRY(restrict_to(h, L.lv, alt[l], l + 1 < nl ? H.lev[l + 1].r : next_r, lo, hi));
+        PBX_TRY(smooth_from_zero(H, L, L.r, r_nb, mp, count, &cur[l], &alt[l], true));
+        Nb nb;
+        Pub pub;
+        PBX_TRY(H.end(&nb));
+        PBX_TRY(H.begin(&pub));
+        PBX_TRY(sweep(h, 1, L.lv, cur[l], L.r, mp, alt[l], nb, pub));          // residual into the spare
+        PBX_TRY(H.end(&nb));
+        pub = Pub();
+        // the next level's first sweeps read the planes next to its right-hand side (two or more sweeps)
+        const bool next_in_h = l + 1 < nl;
+        const int next_count = (l + 1 == ndown) ? MG_COARSE_SWEEPS : nu;
+        if (next_in_h && next_count >= 2) PBX_TRY(H.begin(&pub));
+        PBX_TRY(restrict_to(h, L.lv, alt[l], next_in_h ? Hi.lev[l + 1].r : next_r, nb, pub));
     }
     for (int l = ndown - 1; l >= 0; --l) {
-        MgLevel &L = H.lev[l];
+        MgLevel &L = Hi.lev[l];
         const double *mp = l == 0 ? mean : nullptr;
         const double *coarse = nullptr;
+        Nb nb;
         if (l + 1 < nl) {
-            coarse = H.lev[l + 1].z;
-            MgLevel &C = H.lev[l + 1];
-            PBX_TRY(halo(h, slab, C.lv, coarse, &lo, &hi));
+            coarse = Hi.lev[l + 1].z;       // published by the last sweep of the level below
+            PBX_TRY(H.end(&nb));
         } else {
-            PBX_TRY(below(&coarse, &lo, &hi));
+            PBX_TRY(below(&coarse, &nb.lo, &nb.hi));
         }
-        PBX_TRY(prolong_add(h, L.lv, coarse, cur[l], lo, hi));
+        Pub pub;
+        PBX_TRY(H.begin(&pub));
+        PBX_TRY(prolong_add(h, L.lv, coarse, cur[l], nb, pub));
         for (int s = 0; s < nu; ++s) {
-            PBX_TRY(halo(h, slab, L.lv, cur[l], &lo, &hi));
-            PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l], lo, hi));
+            PBX_TRY(H.end(&nb));
+            pub = Pub();
+            if (s + 1 < nu || l > 0) PBX_TRY(H.begin(&pub));   // the finest level's last sweep feeds the CG
+            PBX_TRY(sweep(h, 0, L.lv, cur[l], L.r, mp, alt[l], nb, pub));
             std::swap(cur[l], alt[l]);
         }
         if (cur[l] != L.z) {

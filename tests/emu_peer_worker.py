@@ -114,6 +114,12 @@ xw, itw, _, whyw, histw = whole_p.cg_solve(bu, rtol=1e-8, maxit=40)
 xq, itq, _, whyq, histq = h_p.cg_solve(np.asfortranarray(bu[:, :, mine]), rtol=1e-8, maxit=40)
 errs["pcg_x"] = float(np.max(np.abs(xq - xw[:, :, mine])) / np.max(np.abs(xw)))
 cg_ok = cg_ok and whyq == whyw == 2 and itq == itw and itq <= 20
+for nu_ in (1, 3):   # one and three smoothing sweeps take other branches of the halo protocol
+    whole_p.set_pc(_lib.PC_MG, nu_)
+    h_p.set_pc(_lib.PC_MG, nu_)
+    zw = whole_p.pc_apply(bu)
+    zs = h_p.pc_apply(np.asfortranarray(bu[:, :, mine]))
+    errs[f"mg_vcycle_nu{nu_}"] = float(np.max(np.abs(zs - zw[:, :, mine])) / np.max(np.abs(zw)))
 h_p.close()
 whole_p.close()
 del bufs_p
@@ -132,7 +138,7 @@ its_all = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
 dist.all_gather(its_all, torch.tensor([its], dtype=torch.int64))
 cg_ok = cg_ok and all(int(t) == its for t in its_all)
 
-tol = {"mg_vcycle": 1e-14, "pcg_x": 1e-9, "star": 0.0, "dot": 1e-12, "allreduce": 1e-15, "cg_x": 1e-6, "cg_hist": 1e-9}
+tol = {"mg_vcycle": 1e-14, "mg_vcycle_nu1": 1e-14, "mg_vcycle_nu3": 1e-14, "pcg_x": 1e-9, "star": 0.0, "dot": 1e-12, "allreduce": 1e-15, "cg_x": 1e-6, "cg_hist": 1e-9}
 ok = all(e <= tol.get(k, 1e-13) for k, e in errs.items()) and same_bits and cg_ok
 dist.barrier()
 h.close()
