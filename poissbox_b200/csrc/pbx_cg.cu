@@ -8,9 +8,13 @@
 // algorithm; the test-side CPU restatement of the same loop lives under oracle/.
 //
 // Per iteration (PC none) the vector work is two fused kernels,
-//   update   x += a p ; r -= a w ; partial sums of (r - m0), (r - m0)^2        48 B/DoF
-//   pupdate  p = (r - m) + b p                                                 24 B/DoF
-// and p.w comes out of the Laplacian's z pass, so an iteration moves 80 + 72 = 152 B/DoF.
+//   update   r -= a w ; partial sums of (r - m0), (r - m0)^2                    24 B/DoF
+//   pupdate  x += a p ; p = (r - m) + b p                                      40 B/DoF
+// and p.w comes out of the Laplacian's z pass, so an iteration moves 80 + 64 = 144 B/DoF.  (x += a p
+// rides with the p update, which reads p anyway, instead of with the r update: 8 B/DoF less than the
+// textbook grouping.  The iteration that converges still owes x its update when the status word is
+// already set; k_pupdate_x recognises it by the iteration stamp SC_XIT that the scalar step leaves
+// whenever it computes a new step length.)
 // All scalars (a, b, mean, norms, status) stay in a device block; the host only reads back the
 // status word, one iteration late, so there is no host synchronisation on the critical path.
 // Reductions are two-stage with a fixed shape (per-CTA partials, then one CTA), so the iteration
@@ -32,7 +36,9 @@ enum {
     SC_M0 = 0, SC_S1, SC_S2, SC_PW, SC_BETA, SC_BETAOLD, SC_A, SC_B, SC_DP, SC_DP0, SC_TTOL,
     SC_PWOLD, SC_STATUS, SC_IT, SC_RTOL, SC_ABSTOL, SC_MEAN, SC_MAXIT, SC_NTOT,
     // preconditioned CG: sums of z, z^2, z (r - m0), (r - m0) (contiguous: one reduction), mean of z
-    SC_SZ, SC_SZZ, SC_SZR, SC_SR, SC_MZ, SC_COUNT
+    SC_SZ, SC_SZZ, SC_SZR, SC_SR, SC_MZ,
+    SC_XIT,   // number of the iteration whose step length SC_A is (x += a p of that iteration pending)
+    SC_COUNT
 };
 
 constexpr int VT = 256;
@@ -150,23 +156,74 @@ k_update(size_t N, double *__restrict__ x, double *__restrict__ r, const double 
     }
 }
 
-// p = (r - mean) + b p
+// r -= a w ; partial sums of r - m0   (PC none: x is updated together with p, k_pupdate_x)
 __global__ void __launch_bounds__(VT)
-k_pupdate(size_t N, const double *__restrict__ r, double *__restrict__ p,
-          const double *__restrict__ sc)
+k_update_r(size_t N, double *__restrict__ r, const double *__restrict__ w, const double *__restrict__ sc,
+           double *__restrict__ part, int np)
 {
+    __shared__ double sh[VT / 32];
     if (sc[SC_STATUS] != 0.0) return;
-    const double m = sc[SC_MEAN], b = sc[SC_B];
-    size_t st = (size_t)gridDim.x * VT * 2;
+    size_t lo, hi;
+    slice(N, &lo, &hi);
+    const double a = sc[SC_A], m0 = sc[SC_M0];
+    double s1 = 0.0, s2 = 0.0;
+    size_t i = lo + 2 * (size_t)threadIdx.x;
+    for (; i + 1 < hi; i += 2 * VT) {
+        double2 rv = *reinterpret_cast<const double2 *>(r + i);
+        const double2 wv = *reinterpret_cast<const double2 *>(w + i);
+        rv.x = fma(-a, wv.x, rv.x);
+        rv.y = fma(-a, wv.y, rv.y);
+        *reinterpret_cast<double2 *>(r + i) = rv;
+        const double t0 = rv.x - m0, t1 = rv.y - m0;
+        s1 += t0 + t1;
+        s2 = fma(t0, t0, fma(t1, t1, s2));
+    }
+    if (i < hi) {
+        const double rv = fma(-a, w[i], r[i]);
+        r[i] = rv;
+        const double t = rv - m0;
+        s1 += t;
+        s2 = fma(t, t, s2);
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = s1;
+        part[np + blockIdx.x] = s2;
+    }
+}
+
+// x += a p (iteration `itag`, if its step length was computed: also when that iteration converged or
+// hit a limit) ; p = (r - mean) + b p (while the solve is still running)
+__global__ void __launch_bounds__(VT)
+k_pupdate_x(size_t N, const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x,
+            const double *__restrict__ sc, int itag)
+{
+    const bool dox = sc[SC_XIT] == (double)itag, dop = sc[SC_STATUS] == 0.0;
+    if (!dox && !dop) return;
+    const double a = sc[SC_A], m = sc[SC_MEAN], b = sc[SC_B];
+    const size_t st = (size_t)gridDim.x * VT * 2;
     size_t i = ((size_t)blockIdx.x * VT + threadIdx.x) * 2;
     for (; i + 1 < N; i += st) {
-        double2 rv = *reinterpret_cast<const double2 *>(r + i);
         double2 pv = *reinterpret_cast<const double2 *>(p + i);
-        pv.x = fma(b, pv.x, rv.x - m);
-        pv.y = fma(b, pv.y, rv.y - m);
-        *reinterpret_cast<double2 *>(p + i) = pv;
+        if (dox) {
+            double2 xv = *reinterpret_cast<const double2 *>(x + i);
+            xv.x = fma(a, pv.x, xv.x);
+            xv.y = fma(a, pv.y, xv.y);
+            *reinterpret_cast<double2 *>(x + i) = xv;
+        }
+        if (dop) {
+            const double2 rv = *reinterpret_cast<const double2 *>(r + i);
+            pv.x = fma(b, pv.x, rv.x - m);
+            pv.y = fma(b, pv.y, rv.y - m);
+            *reinterpret_cast<double2 *>(p + i) = pv;
+        }
     }
-    if (i < N) p[i] = fma(b, p[i], r[i] - m);
+    if (i < N) {
+        const double pv = p[i];
+        if (dox) x[i] = fma(a, pv, x[i]);
+        if (dop) p[i] = fma(b, pv, r[i] - m);
+    }
 }
 
 // sum `cnt` partials of each of `narr` arrays (`stride` apart) into dst[0..narr) (one CTA, fixed order)
@@ -333,6 +390,7 @@ __device__ void scalar_phase(double *__restrict__ sc, int phase, double *__restr
         }
         sc[SC_PWOLD] = dpi;
         sc[SC_A] = beta / dpi;
+        sc[SC_XIT] = i + 1;
         return;
     }
     // phases 1 and 3: S1, S2 are sums of (r - m0), (r - m0)^2
@@ -695,10 +753,10 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
         const int slot = issued & 1;
         rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2);
         if (rc != PBX_OK) break;
-        k_update<<<nb, VT, 0, s>>>(N, x, r, p, w, sc, part, np);
+        k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np);
         ++h->launches;
         if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;
-        k_pupdate<<<vec_grid(N), VT, 0, s>>>(N, r, p, sc);
+        k_pupdate_x<<<vec_grid(N), VT, 0, s>>>(N, r, p, x, sc, issued + 1);
         ++h->launches;
         cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double),
                         cudaMemcpyDeviceToHost, s);

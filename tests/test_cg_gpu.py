@@ -195,3 +195,23 @@ def test_cg_edge_cases():
     x2, its2, *_ = cg_host(b + 1.0e3, dx, 1e-8, pbx.MODE_FAST)
     assert abs(its1 - its2) <= 1
     assert np.linalg.norm(x1 - x2) <= 1e-5 * np.linalg.norm(x1)
+
+
+@pytest.mark.parametrize("rtol,maxit", [(1e-2, 10000), (1e-8, 3), (1e-8, 1), (0.5, 10000)])
+def test_cg_last_step_reaches_x(rtol, maxit):
+    """x += a p rides with the p update; the iteration that converges or hits max_it must still apply its
+    step although the status word is already set: x equals the oracle CG's to rounding"""
+    import torch
+
+    n = 32
+    dx = (2 * np.pi / n,) * 3
+    rng = np.random.default_rng(5)
+    b = orc.lapl(np.asfortranarray(rng.uniform(-1, 1, (n, n, n))), dx)
+    xo, ito, _, whyo, _ = orc.cg_solve(b, dx, rtol=rtol, maxit=maxit)
+    h = pbx.Handle(n, n, n, dx)
+    for _ in range(2):
+        x, it, _, why, _ = h.cg_solve(pbx.fortran_to_torch(b), rtol=rtol, maxit=maxit)
+        torch.cuda.synchronize()
+        assert (it, why) == (ito, whyo)
+        assert np.max(np.abs(pbx.torch_to_fortran(x) - xo)) <= 1e-12 * np.max(np.abs(xo))
+    h.close()

@@ -383,3 +383,19 @@ def test_emu_yz_rot_bit_identical(shape, monkeypatch):
     assert np.array_equal(g.lapl(f), ref)
     h.close()
     g.close()
+
+
+@pytest.mark.parametrize("rtol,maxit", [(1e-2, 10000), (1e-8, 3), (1e-8, 1), (0.5, 10000)])
+def test_emu_cg_last_step_reaches_x(rtol, maxit):
+    """x += a p rides with the p update (k_pupdate_x); the iteration that converges or hits max_it must
+    still apply its step although the status word is already set: x equals the oracle CG's to rounding"""
+    n = 16
+    dx = (2 * np.pi / n,) * 3
+    b = orc.lapl(field((n, n, n), 5), dx)
+    xo, ito, _, whyo, _ = orc.cg_solve(b, dx, rtol=rtol, maxit=maxit)
+    h = handle((n, n, n), dx)
+    for _ in range(2):   # a second solve on the same handle starts from a clean iteration stamp
+        x, it, _, why, _ = h.cg_solve(b, rtol=rtol, maxit=maxit)
+        assert (it, why) == (ito, whyo)
+        assert np.max(np.abs(x - xo)) <= 1e-12 * np.max(np.abs(xo))
+    h.close()
