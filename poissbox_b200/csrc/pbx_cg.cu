@@ -10,9 +10,9 @@
 // Per iteration (PC none) the vector work is two fused kernels,
 //   update   r -= a w ; partial sums of (r - m0), (r - m0)^2                    24 B/DoF
 //   pupdate  x += a p ; p = (r - m) + b p                                      40 B/DoF
-// and p.w comes out of the Laplacian's z pass, so an iteration moves 80 + 64 = 144 B/DoF.  (x += a p
-// rides with the p update, which reads p anyway, instead of with the r update: 8 B/DoF less than the
-// textbook grouping.  The iteration that converges still owes x its update when the status word is
+// and p.w comes out of the Laplacian's z pass (which reads p for it: 8 B/DoF), so an iteration moves
+// 88 + 64 = 152 B/DoF.  (x += a p rides with the p update, which reads p anyway, instead of with the
+// r update: 8 B/DoF less than the textbook grouping.  The iteration that converges still owes x its update when the status word is
 // already set; k_pupdate_x recognises it by the iteration stamp SC_XIT that the scalar step leaves
 // whenever it computes a new step length.)
 // All scalars (a, b, mean, norms, status) stay in a device block; the host only reads back the
