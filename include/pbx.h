@@ -249,7 +249,8 @@ int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, d
  * geometric V(nu, nu) cycle on the same star (damped Jacobi, cell-centred trilinear transfer,
  * symmetric positive definite; pbx_mg.cu).  It is not PETSc's GAMG: iteration counts are its own.
  * KSPCG semantics with a preconditioner: z = M^-1 r with the constant removed, preconditioned norm
- * ||z||, beta = z.r, KSP_DIVERGED_INDEFINITE_PC (-8) if beta < 0.  Single rank only.
+ * ||z||, beta = z.r, KSP_DIVERGED_INDEFINITE_PC (-8) if beta < 0.  On z slabs the same cycle runs
+ * with halo exchanges on the distributed levels and gathered coarse levels.
  *   pbx_set_pc(h, PBX_PC_NONE, 0)  (default)   |   pbx_set_pc(h, PBX_PC_MG, nu)  nu = 0 -> 2
  *   pbx_pc_apply_device            z = M^-1 (r - mean r), mean-free: one application, for tests */
 #define PBX_PC_NONE 0
@@ -257,6 +258,21 @@ int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, d
 #define PBX_DIVERGED_INDEFINITE_PC (-8)
 int pbx_set_pc(pbx_handle h, int pc, int nu);
 int pbx_pc_apply_device(pbx_handle h, const double *r, double *z);
+
+/* The solve configured the way the reference configures it: by PETSc option names.  solve() calls
+ * KSPSetFromOptions (src/poissbox.f90:295) and the README runs
+ *     -ksp_type cg -pc_type gamg -ksp_rtol ... -ksp_monitor -ksp_converged_reason   (README.md:43-49);
+ * a host without PETSc passes the same string here.  Understood (PETSc's defaults where absent):
+ *     -ksp_type cg                      anything else: PBX_ERR_UNSUPPORTED
+ *     -ksp_rtol r  -ksp_atol a  -ksp_max_it n          (1e-5, 1e-50, 10000)
+ *     -pc_type none | mg | gamg         gamg selects the geometric multigrid stand-in (PBX_PC_MG)
+ *     -pc_mg_smoothup n / -pc_mg_smoothdown n / -mg_levels_ksp_max_it n    sweeps of the V(n, n) cycle
+ *     -ksp_monitor                      "  k KSP Residual norm x" per iteration on stdout, after the solve
+ *     -ksp_converged_reason             "Linear solve converged due to CONVERGED_RTOL iterations k"
+ * Other options are ignored, as PETSc ignores options nobody queries.  The handle's preconditioner
+ * setting is changed only if -pc_type is given. */
+int pbx_ksp_solve_device(pbx_handle h, const char *options, const double *b, double *x, int *its,
+                         double *rnorm, int *reason);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-pointer convenience variants (what the Fortran module bodies call).

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pbx_fwd_sweep_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbx_bwd_sweep_batch_device": (c_int, [c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pbx_cg_solve_device": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, _ip, _dp, _ip, _dp, c_int]),
+    "pbx_ksp_solve_device": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, _ip, _dp, _ip]),
     "pbx_set_pc": (c_int, [c_void_p, c_int, c_int]),
     "pbx_pc_apply_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pbx_lapl_host": (c_int, [c_int, c_int, c_int, _dp, _d3, _dp, c_int]),

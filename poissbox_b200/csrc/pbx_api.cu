@@ -1,5 +1,6 @@
 // pbx_api.cu -- the C ABI (include/pbx.h): handle lifecycle, operator drivers for both schedules,
 // host-pointer convenience variants.
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -727,6 +728,117 @@ int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, d
     if (!h || !b || !x || maxit < 0) return PBX_ERR_ARG;
     PBX_CUDA(cudaSetDevice(h->device));
     return cg_solve(h, b, x, rtol, abstol, maxit, its, rnorm, reason, hist, nhist);
+}
+
+static const char *reason_name(int r)
+{
+    switch (r) {
+    case PBX_CONVERGED_RTOL: return "CONVERGED_RTOL";
+    case PBX_CONVERGED_ATOL: return "CONVERGED_ATOL";
+    case PBX_DIVERGED_ITS: return "DIVERGED_ITS";
+    case PBX_DIVERGED_DTOL: return "DIVERGED_DTOL";
+    case PBX_DIVERGED_INDEFINITE_MAT: return "DIVERGED_INDEFINITE_MAT";
+    case PBX_DIVERGED_INDEFINITE_PC: return "DIVERGED_INDEFINITE_PC";
+    case PBX_DIVERGED_NANORINF: return "DIVERGED_NANORINF";
+    default: return "UNKNOWN";
+    }
+}
+
+// PETSc option names of the reference's solve (README.md:43-49, src/poissbox.f90:295)
+int pbx_ksp_solve_device(pbx_handle h, const char *options, const double *b, double *x, int *its,
+                         double *rnorm, int *reason)
+{
+    if (!h || !b || !x) return PBX_ERR_ARG;
+    double rtol = 1e-5, atol = 1e-50;
+    int maxit = 10000, nu = 0, pc = -1;
+    bool monitor = false, why = false;
+    std::vector<std::string> tok;
+    if (options) {
+        std::string cur;
+        for (const char *c = options;; ++c) {
+            if (*c == 0 || *c == ' ' || *c == '\t' || *c == '\n') {
+                if (!cur.empty()) tok.push_back(cur);
+                cur.clear();
+                if (*c == 0) break;
+            } else {
+                cur += *c;
+            }
+        }
+    }
+    auto value = [&](size_t i, std::string *v) {
+        if (i + 1 >= tok.size() || (tok[i + 1].size() > 1 && tok[i + 1][0] == '-' && !isdigit((unsigned char)tok[i + 1][1]) && tok[i + 1][1] != '.')) {
+            set_last_error("option " + tok[i] + " needs a value");
+            return false;
+        }
+        *v = tok[i + 1];
+        return true;
+    };
+    for (size_t i = 0; i < tok.size(); ++i) {
+        const std::string &o = tok[i];
+        std::string v;
+        char *end = nullptr;
+        if (o == "-ksp_monitor") {
+            monitor = true;
+        } else if (o == "-ksp_converged_reason") {
+            why = true;
+        } else if (o == "-ksp_type") {
+            if (!value(i, &v)) return PBX_ERR_ARG;
+            if (v != "cg") {
+                set_last_error("-ksp_type " + v + ": only cg is built");
+                return PBX_ERR_UNSUPPORTED;
+            }
+            ++i;
+        } else if (o == "-pc_type") {
+            if (!value(i, &v)) return PBX_ERR_ARG;
+            if (v == "none")
+                pc = PBX_PC_NONE;
+            else if (v == "mg" || v == "gamg")
+                pc = PBX_PC_MG;
+            else {
+                set_last_error("-pc_type " + v + ": none, mg (and gamg as its stand-in) are built");
+                return PBX_ERR_UNSUPPORTED;
+            }
+            ++i;
+        } else if (o == "-ksp_rtol" || o == "-ksp_atol") {
+            if (!value(i, &v)) return PBX_ERR_ARG;
+            const double d = strtod(v.c_str(), &end);
+            if (end == v.c_str() || *end || !(d >= 0)) {
+                set_last_error(o + " " + v + ": not a tolerance");
+                return PBX_ERR_ARG;
+            }
+            (o == "-ksp_rtol" ? rtol : atol) = d;
+            ++i;
+        } else if (o == "-ksp_max_it" || o == "-pc_mg_smoothup" || o == "-pc_mg_smoothdown" ||
+                   o == "-mg_levels_ksp_max_it") {
+            if (!value(i, &v)) return PBX_ERR_ARG;
+            const long n = strtol(v.c_str(), &end, 10);
+            if (end == v.c_str() || *end || n < 0 || n > 1000000000L) {
+                set_last_error(o + " " + v + ": not a count");
+                return PBX_ERR_ARG;
+            }
+            if (o == "-ksp_max_it")
+                maxit = (int)n;
+            else
+                nu = (int)n;
+            ++i;
+        }
+    }
+    if (pc >= 0) PBX_TRY(pbx_set_pc(h, pc, pc == PBX_PC_MG ? nu : 0));
+    else if (nu > 0 && h->pc == PBX_PC_MG) PBX_TRY(pbx_set_pc(h, PBX_PC_MG, nu));
+    std::vector<double> hist(monitor ? (size_t)maxit + 1 : 0);
+    int k = 0, r = 0;
+    double rn = 0.0;
+    PBX_TRY(pbx_cg_solve_device(h, b, x, rtol, atol, maxit, &k, &rn, &r, monitor ? hist.data() : nullptr,
+                                (int)hist.size()));
+    if (monitor && h->rank == 0)
+        for (int i = 0; i <= k && i < (int)hist.size(); ++i) printf("%3d KSP Residual norm %14.12e\n", i, hist[i]);
+    if (why && h->rank == 0)
+        printf("Linear solve %s due to %s iterations %d\n", r > 0 ? "converged" : "did not converge", reason_name(r), k);
+    if (monitor || why) fflush(stdout);
+    if (its) *its = k;
+    if (rnorm) *rnorm = rn;
+    if (reason) *reason = r;
+    return PBX_OK;
 }
 
 }  // extern "C"

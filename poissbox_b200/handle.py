@@ -221,6 +221,17 @@ class Handle:
         return z
 
     # -- solve ----------------------------------------------------------------------------------
+    def ksp_solve(self, b, options="", x=None):
+        """The reference's solve() (src/poissbox.f90:269-298) configured the way the reference configures
+        it, by PETSc option names (KSPSetFromOptions :295; README.md:43-49), e.g.
+        "-ksp_type cg -pc_type gamg -ksp_rtol 1e-8 -ksp_monitor -ksp_converged_reason".
+        Returns (x, its, rnorm, reason)."""
+        x = self.empty() if x is None else x
+        its, reason, rnorm = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        check(LIB.pbx_ksp_solve_device(self._h, options.encode(), self._field(b), self._field(x),
+                                       ctypes.byref(its), ctypes.byref(rnorm), ctypes.byref(reason)))
+        return x, its.value, rnorm.value, reason.value
+
     def cg_solve(self, b, x=None, rtol=1e-5, abstol=1e-50, maxit=10000):
         """KSPSolve with -ksp_type cg -pc_type none (src/poissbox.f90:293-296).
         Returns (x, its, rnorm, reason, history)."""

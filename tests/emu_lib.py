@@ -150,6 +150,14 @@ class EmuHandle:
                                                      len(hist)))
         return x, its.value, rnorm.value, reason.value, hist[: its.value + 1]
 
+    def ksp_solve(self, b, options=""):
+        b = aligned(b)
+        x = new_field(self.shape)
+        its, reason, rnorm = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        check(self.lib, self.lib.pbx_ksp_solve_device(self._h, options.encode(), ptr(b), ptr(x), ctypes.byref(its),
+                                                      ctypes.byref(rnorm), ctypes.byref(reason)))
+        return x, its.value, rnorm.value, reason.value
+
     def slab_phase1(self, f):
         self._f = aligned(f)
         check(self.lib, self.lib.pbx_slab_phase1(self._h, ptr(self._f)))

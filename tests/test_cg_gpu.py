@@ -215,3 +215,27 @@ def test_cg_last_step_reaches_x(rtol, maxit):
         assert (it, why) == (ito, whyo)
         assert np.max(np.abs(pbx.torch_to_fortran(x) - xo)) <= 1e-12 * np.max(np.abs(xo))
     h.close()
+
+
+def test_ksp_options(capfd):
+    """pbx_ksp_solve_device: the reference's README options (-ksp_type cg -pc_type gamg -ksp_rtol ...
+    -ksp_monitor -ksp_converged_reason) drive the in-library solve"""
+    import torch
+
+    n = 32
+    dx = (2 * np.pi / n,) * 3
+    rng = np.random.default_rng(5)
+    b = pbx.fortran_to_torch(orc.lapl(np.asfortranarray(rng.uniform(-1, 1, (n, n, n))), dx))
+    h = pbx.Handle(n, n, n, dx)
+    x0, it0, rn0, why0, _ = h.cg_solve(b, rtol=1e-3)
+    x, it, rn, why = h.ksp_solve(b, "-ksp_type cg -pc_type none -ksp_rtol 1e-3 -ksp_monitor -ksp_converged_reason")
+    torch.cuda.synchronize()
+    out = capfd.readouterr().out
+    assert (it, rn, why) == (it0, rn0, why0) and torch.equal(x, x0)
+    assert sum("KSP Residual norm" in ln for ln in out.splitlines()) == it + 1
+    assert f"Linear solve converged due to CONVERGED_RTOL iterations {it}" in out
+    xm, itm, _, whym = h.ksp_solve(b, "-pc_type gamg -ksp_rtol 1e-6")
+    assert whym == 2 and itm < it0 * 4
+    with pytest.raises(pbx.PbxError):
+        h.ksp_solve(b, "-ksp_type gmres")
+    h.close()

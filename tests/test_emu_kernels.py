@@ -399,3 +399,36 @@ def test_emu_cg_last_step_reaches_x(rtol, maxit):
         assert (it, why) == (ito, whyo)
         assert np.max(np.abs(x - xo)) <= 1e-12 * np.max(np.abs(xo))
     h.close()
+
+
+def test_emu_ksp_options(capfd):
+    """pbx_ksp_solve_device: the solve configured by the PETSc option names of the reference's README
+    (-ksp_type cg -pc_type ... -ksp_rtol ... -ksp_monitor -ksp_converged_reason)"""
+    from poissbox_b200 import _lib
+
+    n = 16
+    dx = (2 * np.pi / n,) * 3
+    b = orc.lapl(field((n, n, n), 5), dx)
+    h = handle((n, n, n), dx)
+    x0, it0, rn0, why0, hist0 = h.cg_solve(b, rtol=1e-3)
+    x, it, rn, why = h.ksp_solve(b, "-ksp_type cg -pc_type none -ksp_rtol 1e-3 -ksp_monitor -ksp_converged_reason")
+    out = capfd.readouterr().out
+    assert (it, rn, why) == (it0, rn0, why0) and np.array_equal(x, x0)
+    lines = [ln for ln in out.splitlines() if "KSP Residual norm" in ln]
+    assert len(lines) == it + 1 and lines[0].split()[0] == "0" and float(lines[-1].split()[-1]) == pytest.approx(rn, rel=1e-11)
+    assert f"Linear solve converged due to CONVERGED_RTOL iterations {it}" in out
+    # PETSc's defaults when nothing is said; unknown options are ignored
+    assert h.ksp_solve(b, "-log_view -da_grid_x 16")[1:] == h.cg_solve(b)[1:4]
+    # -pc_type gamg selects the multigrid stand-in and stays selected; -ksp_max_it bounds the solve
+    xm, itm, _, whym = h.ksp_solve(b, "-pc_type gamg -ksp_rtol 1e-6 -mg_levels_ksp_max_it 2")
+    h2 = handle((n, n, n), dx)
+    h2.set_pc(_lib.PC_MG, 2)
+    assert (itm, whym) == h2.cg_solve(b, rtol=1e-6)[1:4:2]
+    assert h.ksp_solve(b, "-ksp_max_it 2 -ksp_rtol 1e-12")[1::2] == (2, -3)
+    for bad, code in (("-ksp_type gmres", 4), ("-pc_type ilu", 4), ("-ksp_rtol", 1), ("-ksp_rtol abc", 1),
+                      ("-ksp_max_it -3", 1)):
+        with pytest.raises(_lib.PbxError) as e:
+            h.ksp_solve(b, bad)
+        assert e.value.code == code
+    h.close()
+    h2.close()
