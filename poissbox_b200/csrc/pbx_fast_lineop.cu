@@ -10,74 +10,19 @@
 // operator, against three global-memory sweeps for the REFERENCE schedule's thread-per-line Thomas.
 // Used by the FAST schedule of grad / div / interp (8 + 8 + 3 line operators, reference stage
 // order); results agree with the REFERENCE schedule to rounding (tests/test_parity_gpu.py).
-#include "pbx_fast_common.cuh"
+#include <cstdlib>
+
+#include "pbx_fast_lineop.cuh"
 
 namespace pbx {
 
 using namespace fast;
+using namespace lineop;
 
 namespace {
 
 constexpr int XW = 8;
 constexpr int CPAD = LC + 2;
-
-struct LineOp {
-    CompositeCoef cc;     // only r, pw, look, nlook are used
-    double a, b;          // right-hand-side coefficients times (1 + r^2)
-    int deriv;            // 1: opsign -1 (differences), 0: opsign +1 (sums)
-    int shift;            // 0: stagger -1 (cell -> vertex), 1: stagger +1 (vertex -> cell)
-};
-
-// rhs_k = a (f_{k+sh} +- f_{k-1+sh}) + b (f_{k+1+sh} +- f_{k-2+sh}),  e[k+3] = f_k
-__device__ __forceinline__ void stencil4(const LineOp &op, const double (&e)[LC + 6], double (&o)[LC])
-{
-#pragma unroll
-    for (int k = 0; k < LC; ++k) {
-        const double f0 = op.shift ? e[k + 4] : e[k + 3], f1 = op.shift ? e[k + 3] : e[k + 2];
-        const double f2 = op.shift ? e[k + 5] : e[k + 4], f3 = op.shift ? e[k + 2] : e[k + 1];
-        const double t1 = op.deriv ? f0 - f1 : f0 + f1;
-        const double t2 = op.deriv ? f2 - f3 : f2 + f3;
-        o[k] = fma(op.b, t2, op.a * t1);
-    }
-}
-
-// single-pole look-back: S = sum_m r^(16 (m-1)) E_(t -+ m)
-__device__ __forceinline__ double lookback1(const CompositeCoef &c, const Xchg &x, int slot, int dir)
-{
-    double S = x.get(slot, x.nb(dir));
-#pragma unroll
-    for (int m = 2; m <= MAXLOOK; ++m)
-        if (m <= c.nlook) S = fma(c.look[m - 1], x.get(slot, x.nb(dir * m)), S);
-    return S;
-}
-
-// v <- A^-1 v (up to the folded factor); slots s0, s0+1; two barriers
-template <class Bar>
-__device__ __forceinline__ void solve1_chunk(const CompositeCoef &c, const Xchg &x, int s0,
-                                             double (&v)[LC], Bar bar)
-{
-    double y = 0.0;
-#pragma unroll
-    for (int k = 0; k < LC; ++k) {
-        y = fma(c.r, y, v[k]);
-        v[k] = y;
-    }
-    x.put(s0, y);
-    bar();
-    const double S = lookback1(c, x, s0, -1);
-    double w = 0.0;
-#pragma unroll
-    for (int k = LC - 1; k >= 0; --k) {
-        const double yk = fma(c.pw[k], S, v[k]);   // corrected causal value
-        w = fma(c.r, w, yk);
-        v[k] = w;
-    }
-    x.put(s0 + 1, w);
-    bar();
-    const double W = lookback1(c, x, s0 + 1, +1);
-#pragma unroll
-    for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[LC - 1 - k], W, v[k]);
-}
 
 // ---- one slab of a z-decomposed box (pbx_dist.cu) ------------------------------------------------
 // The slab is an open line.  Per z line each neighbour sends three numbers (LINE_MSG):
@@ -323,6 +268,9 @@ lineop_boundary_kernel(long long nlines, int nzl, int bm, const __grid_constant_
     }
 }
 
+}  // namespace
+
+namespace lineop {
 LineOp make_line_op(OpKind kind, int stagger, double dx)
 {
     LineOp op;
@@ -336,8 +284,7 @@ LineOp make_line_op(OpKind kind, int stagger, double dx)
     op.shift = stagger == PBX_STAGGER_BACKWARD ? 0 : 1;
     return op;
 }
-
-}  // namespace
+}  // namespace lineop
 
 // boundary sweep of a z line operator on a slab: three planes of nx*ny numbers for either neighbour
 int fast_line_boundary(cudaStream_t s, const Brick &g, OpKind kind, int stagger, double dx,
@@ -367,6 +314,10 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
     const LineOp op = make_line_op(kind, stagger, dx);
     if (from_lo && (dir != 2 || !from_up)) return PBX_ERR_ARG;
     if (addend && (dir == 0 || addend == out || (reinterpret_cast<uintptr_t>(addend) & 15))) return PBX_ERR_ARG;
+    if (!from_lo) {
+        const int rc = fast_line_op_tma(s, g, dir, kind, stagger, dx, in, out, addend, launches);
+        if (rc != PBX_ERR_UNSUPPORTED) return rc;
+    }
     if (dir == 0) {
         LX p;
         p.op = op;

@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "pbx_fast_common.cuh"
+#include "pbx_fast_lineop.cuh"
 
 namespace pbx {
 
@@ -431,6 +432,218 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
     if (tid == 0) tma_wait_all0();
 }
 
+// ---------------------------------------------------------------------------------------------
+// ONE compact line operator per launch (grad / div / interp of the FAST schedule, pbx_fast_lineop.cu)
+// with the data movement of the Laplacian passes.  A single input field leaves room for TWO tile
+// stages, so the tile after next is in flight while the current one is computed.  Arithmetic from
+// pbx_fast_lineop.cuh: same bits as the generic line-operator kernels.  Opt-in (PBX_LINEOP_TMA=1)
+// until measured.
+// ---------------------------------------------------------------------------------------------
+struct LYZShared {
+    double tile[2][YZ_TILE_DOUBLES];
+    double xchg[NGRP][4 * NT];
+    uint64_t full[2], empty[2];
+};
+
+__device__ __forceinline__ void lyz_issue_tile(LYZShared &S, int stage, const YZT &p, const CUtensorMap *map,
+                                               int tile)
+{
+    const TileId id = tile_id(p, tile);
+    const int x0 = id.xt * XWT, g0 = id.gt * p.G;
+    mbar_expect_tx(&S.full[stage], YZ_TILE_BYTES);
+    for (int b = 0; b < p.nbox; ++b) {
+        const int i0 = b * p.RB;
+        const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
+        tma_load_3d(&S.tile[stage][b * p.RB * p.se], map, &S.full[stage], x0, c1, c2);
+    }
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(NTHR_YZ, 1)
+lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ lineop::LineOp op,
+                     const __grid_constant__ CUtensorMap map, const double *__restrict__ addend,
+                     double *__restrict__ out)
+{
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    LYZShared &S = *reinterpret_cast<LYZShared *>(smraw);
+    const int tid = threadIdx.x;
+    if ((smem_u32(smraw) & 127u) != 0) __trap();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], NTHR_YZ);
+        }
+        fence_mbar_init();
+        for (int s = 0; s < 2; ++s)
+            if ((int)blockIdx.x + s * (int)gridDim.x < p.ntiles)
+                lyz_issue_tile(S, s, p, &map, blockIdx.x + s * gridDim.x);
+    }
+    __syncthreads();
+    const int grp = tid >> 8, lt = tid & (NT - 1);
+    const int tx = lt & (XW - 1);
+    const int t = (lt >> 3) % p.T;
+    const int tz = lt / (XW * p.T);
+    const BarGroup bar{1 + grp};
+    const Xchg xc{S.xchg[grp], lt, t, p.T, XW, 0};
+    const int soff = tz * p.sgm + grp * XW + tx;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t par = (uint32_t)((it >> 1) & 1);
+        const int xt8 = (tile % p.ntx) * NGRP + grp, gt = tile / p.ntx;
+        const int x = xt8 * XW + tx, g = gt * p.G + tz;
+        const bool live = (x < p.nx) && (g < p.ng);
+        const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+        mbar_wait(&S.full[st], par);
+        double e[LC + 6], v[LC];
+        {
+            const double *tb = S.tile[st] + soff;
+            const int i0 = t * LC;
+#pragma unroll
+            for (int k = 0; k < LC; ++k) e[k + 3] = tb[(i0 + k) * p.se];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                int il = i0 - 3 + k, ir = i0 + LC + k;
+                if (il < 0) il += p.n;
+                if (ir >= p.n) ir -= p.n;
+                e[k] = tb[il * p.se];
+                e[LC + 3 + k] = tb[ir * p.se];
+            }
+        }
+        mbar_arrive(&S.empty[st]);
+        if (tid == 0 && tile + 2 * (int)gridDim.x < p.ntiles) {
+            mbar_wait(&S.empty[st], par);
+            lyz_issue_tile(S, st, p, &map, tile + 2 * gridDim.x);
+        }
+        lineop::stencil4(op, e, v);
+        lineop::solve1_chunk(op.cc, xc, 0, v, bar);
+        if (live) {
+            if (ADD) {
+#pragma unroll
+                for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k] + __ldg(addend + base + k * p.sl);
+            } else {
+#pragma unroll
+                for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
+            }
+        }
+    }
+}
+
+struct LXShared {
+    double tin[2][TILE_DOUBLES];
+    double sta[TILE_DOUBLES];
+    uint64_t full[2], empty[2];
+};
+
+// single-pole look-back by shuffle: the order of lineop::lookback1
+__device__ __forceinline__ double lookback1_shfl(const CompositeCoef &c, double e, int lane, int T, int dir)
+{
+    const int seg = lane & ~(T - 1), t = lane & (T - 1);
+    double S = shfl_d(e, seg | ((t + dir) & (T - 1)));
+#pragma unroll
+    for (int m = 2; m <= MAXLOOK; ++m)
+        if (m <= c.nlook) S = fma(c.look[m - 1], shfl_d(e, seg | ((t + dir * m) & (T - 1))), S);
+    return S;
+}
+
+struct LXT {
+    lineop::LineOp op;
+    int T, ntiles;
+};
+
+__global__ void __launch_bounds__(NT, 2)
+lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUtensorMap mapIn,
+                    const __grid_constant__ CUtensorMap mapOut)
+{
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    LXShared &S = *reinterpret_cast<LXShared *>(smraw);
+    const int tid = threadIdx.x;
+    if ((smem_u32(smraw) & 1023u) != 0) __trap();
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], NT);
+        }
+        fence_mbar_init();
+        for (int s = 0; s < 2; ++s) {
+            const int tl = (int)blockIdx.x + s * (int)gridDim.x;
+            if (tl < p.ntiles) {
+                mbar_expect_tx(&S.full[s], TILE_BYTES);
+                tma_load_2d(S.tin[s], &mapIn, &S.full[s], 0, tl * NT);
+            }
+        }
+    }
+    __syncthreads();
+    const int lane = tid & 31, T = p.T;
+    const int seg = lane & ~(T - 1), t = lane & (T - 1);
+    const int ql = (tid & ~31) | seg | ((t - 1) & (T - 1)), qr = (tid & ~31) | seg | ((t + 1) & (T - 1));
+    const CompositeCoef &c = p.op.cc;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t par = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&S.full[st], par);
+        double e[LC + 6], v[LC];
+        const double *tin = S.tin[st];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v2 = *reinterpret_cast<const double2 *>(tin + swz(tid, j));
+            e[3 + 2 * j] = v2.x;
+            e[4 + 2 * j] = v2.y;
+        }
+        {
+            const double2 l6 = *reinterpret_cast<const double2 *>(tin + swz(ql, 6));
+            const double2 l7 = *reinterpret_cast<const double2 *>(tin + swz(ql, 7));
+            const double2 r0 = *reinterpret_cast<const double2 *>(tin + swz(qr, 0));
+            const double2 r1 = *reinterpret_cast<const double2 *>(tin + swz(qr, 1));
+            e[0] = l6.y;
+            e[1] = l7.x;
+            e[2] = l7.y;
+            e[LC + 3] = r0.x;
+            e[LC + 4] = r0.y;
+            e[LC + 5] = r1.x;
+        }
+        mbar_arrive(&S.empty[st]);
+        if (tid == 0 && tile + 2 * (int)gridDim.x < p.ntiles) {
+            mbar_wait(&S.empty[st], par);
+            mbar_expect_tx(&S.full[st], TILE_BYTES);
+            tma_load_2d(S.tin[st], &mapIn, &S.full[st], 0, (tile + 2 * (int)gridDim.x) * NT);
+        }
+        lineop::stencil4(p.op, e, v);
+        // lineop::solve1_chunk with the chunk states travelling by shuffle
+        double y = 0.0;
+#pragma unroll
+        for (int k = 0; k < LC; ++k) {
+            y = fma(c.r, y, v[k]);
+            v[k] = y;
+        }
+        const double Sc = lookback1_shfl(c, y, lane, T, -1);
+        double w = 0.0;
+#pragma unroll
+        for (int k = LC - 1; k >= 0; --k) {
+            const double yk = fma(c.pw[k], Sc, v[k]);
+            w = fma(c.r, w, yk);
+            v[k] = w;
+        }
+        const double Wc = lookback1_shfl(c, w, lane, T, +1);
+#pragma unroll
+        for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[LC - 1 - k], Wc, v[k]);
+        // staging tile: the previous tile's TMA store must have read it
+        if (tid == 0) tma_wait_read0();
+        BarCompute()();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<double2 *>(S.sta + swz(tid, j)) = make_double2(v[2 * j], v[2 * j + 1]);
+        fence_proxy_async();
+        BarCompute()();
+        if (tid == 0) {
+            tma_store_2d(&mapOut, S.sta, 0, tile * NT);
+            tma_commit();
+        }
+    }
+    if (tid == 0) tma_wait_all0();
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -642,6 +855,55 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
         yz_tma_kernel<true, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
     else
         yz_tma_kernel<true, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+    if (launches) ++*launches;
+    PBX_CUDA(cudaGetLastError());
+    return PBX_OK;
+}
+
+// one compact line operator along dir with the TMA-pipelined kernels; PBX_ERR_UNSUPPORTED: use the
+// generic kernel (not asked for with PBX_LINEOP_TMA=1, slab, segmented line, unsupported shape)
+int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
+                     const double *in, double *out, const double *addend, long long *launches)
+{
+    const char *en = getenv("PBX_LINEOP_TMA");
+    if (!(en && en[0] == '1') || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    const lineop::LineOp op = lineop::make_line_op(kind, stagger, dx);
+    static bool attr_set[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
+        const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel, a, (int)sizeof(LXShared)));
+        attr_set[dev_ & 63] = true;
+    }
+    if (dir == 0) {
+        const int T = g.nx / LC;
+        const size_t nchunks = g.N() / LC;
+        if (addend || g.nx % LC || T > 32 || (T & (T - 1)) || nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
+        LXT p;
+        p.op = op;
+        p.T = T;
+        p.ntiles = (int)((nchunks + NT - 1) / NT);
+        CUtensorMap mi, mo;
+        if (!make_map_x(&mi, in, nchunks) || !make_map_x(&mo, out, nchunks)) return PBX_ERR_UNSUPPORTED;
+        int grid = 2 * sm_count();
+        if (grid > p.ntiles) grid = p.ntiles;
+        lineop_x_tma_kernel<<<grid, NT, sizeof(LXShared), s>>>(p, mi, mo);
+    } else {
+        YZT p;
+        if (!yz_geometry_tma(g, dir, &p) || p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;
+        p.rev = 0;
+        CUtensorMap m;
+        if (!make_map_yz(&m, in, g, p)) return PBX_ERR_UNSUPPORTED;
+        int grid = sm_count();
+        if (grid > p.ntiles) grid = p.ntiles;
+        if (addend)
+            lineop_yz_tma_kernel<true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+        else
+            lineop_yz_tma_kernel<false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
+    }
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -57,6 +57,18 @@ def main():
     h.set_pc(_lib.PC_MG, 2)
     x, its, _, _, _ = h.cg_solve(b, rtol=1e-6)
     res.append(f"{its}:{digest(x)}")
+    # grad / div through the TMA-pipelined line operators, and the swizzled y/z tiles of the Laplacian
+    os.environ["PBX_LINEOP_TMA"] = "1"
+    os.environ["PBX_YZ_ROT"] = "1"
+    shape = (64, 32, 64)
+    f = np.asfortranarray(rng.uniform(-1, 1, shape))
+    v = np.asfortranarray(rng.uniform(-1, 1, shape + (3,)))
+    h = emu_lib.EmuHandle(*shape, tuple(1.0 / m for m in shape))
+    res += [digest(h.grad(f)), digest(h.div(v)), digest(h.lapl(f))]
+    h.close()
+    os.environ.pop("PBX_LINEOP_TMA")
+    os.environ.pop("PBX_YZ_ROT")
+    h = emu_lib.EmuHandle(16, 16, 16, (0.1,) * 3)
     # line-major tridiagonal batches through the TMA tiles (pbx_tdma_tma.cu)
     os.environ["PBX_TDMA_TMA"] = "1"
     n, nl = 40, 45

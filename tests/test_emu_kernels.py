@@ -432,3 +432,22 @@ def test_emu_ksp_options(capfd):
         assert e.value.code == code
     h.close()
     h2.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 64), (32, 512, 16), (16, 16, 512), (512, 16, 16), (48, 64, 32), (16, 256, 16)])
+def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
+    """PBX_LINEOP_TMA=1: grad / div / interp through the TMA-pipelined line-operator kernels (two tile
+    stages, x direction by shuffles) -- the same bits as the generic line-operator kernels"""
+    dx = tuple(0.7 / n for n in shape)
+    f = field(shape, 31)
+    vec = np.asfortranarray(np.random.default_rng(32).uniform(-1, 1, shape + (3,)))
+    lib = emu_lib.load()
+    h = handle(shape, dx)
+    want = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
+    monkeypatch.setenv("PBX_LINEOP_TMA", "1")
+    maps0 = lib.pbx_emu_tensor_maps_total()
+    got = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
+    assert lib.pbx_emu_tensor_maps_total() > maps0, "the TMA line operators did not run"
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    h.close()

@@ -173,6 +173,27 @@ def test_yz_rot_bit_identical(shape, monkeypatch):
     h.close()
 
 
+@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
+                    reason="PBX_LINEOP_TMA (TMA-pipelined line operators) was written after the round's GPU budget "
+                           "was spent: CPU-harness tested only (test_emu_lineop_tma_bit_identical)")
+@pytest.mark.parametrize("shape", [(256, 256, 256), (64, 512, 32), (48, 64, 512)])
+def test_lineop_tma_bit_identical(shape, monkeypatch):
+    import torch
+
+    nx, ny, nz = shape
+    g = torch.Generator(device="cuda").manual_seed(4)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    v = torch.rand((3, nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    h = pbx.Handle(nx, ny, nz, (0.7 / nx, 0.7 / ny, 0.7 / nz))
+    want = [h.grad(f), h.div(v), h.interp(f), h.interp(f, +1)]
+    monkeypatch.setenv("PBX_LINEOP_TMA", "1")
+    got = [h.grad(f), h.div(v), h.interp(f), h.interp(f, +1)]
+    torch.cuda.synchronize()
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    h.close()
+
+
 # ------------------------------------------------------------------------------------ 1-D operators
 @pytest.mark.parametrize("n", [3, 4, 5, 37, 128, 1000])
 def test_lines_bit_exact(n):

@@ -22,6 +22,12 @@ for mode, name in ((pbx.MODE_FAST, "FAST"), (pbx.MODE_REFERENCE, "REFERENCE")):
     h.mode = mode
     tg, td, ti, tl = tm(lambda: h.grad(f, g3)), tm(lambda: h.div(v, s1)), tm(lambda: h.interp(f, -1, s1)), tm(lambda: h.lapl(f, s1))
     print(f"{name:9s} {n}^3: grad {tg:.3f} ms ({N/tg/1e6:.1f} GDoF/s)  div {td:.3f} ms ({N/td/1e6:.1f})  interp {ti:.3f} ms ({N/ti/1e6:.1f})  lapl {tl:.3f} ms ({N/tl/1e6:.1f})")
+# FAST grad / div / interp through the TMA-pipelined line operators (PBX_LINEOP_TMA=1, read per call)
+os.environ["PBX_LINEOP_TMA"] = "1"
+h.mode = pbx.MODE_FAST
+tg, td, ti = tm(lambda: h.grad(f, g3)), tm(lambda: h.div(v, s1)), tm(lambda: h.interp(f, -1, s1))
+print(f"FAST+TMA  {n}^3: grad {tg:.3f} ms ({N/tg/1e6:.1f} GDoF/s)  div {td:.3f} ms ({N/td/1e6:.1f})  interp {ti:.3f} ms ({N/ti/1e6:.1f})")
+os.environ.pop("PBX_LINEOP_TMA")
 # batched general-coefficient tridiagonal solves: n-point lines, element-major layout (coalesced)
 for ln in (64, 512, 2048):
     nl = (1 << 24) // ln

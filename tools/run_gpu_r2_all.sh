@@ -8,7 +8,7 @@ timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2_test
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/r2_smoke.log; cat gpurun_out/r2_smoke.log
 timeout 300 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; cat gpurun_out/r2_bench_default.json
 # 2. the gated tests (peer boards on one GPU, TMA line-major tridsol, host batch, swizzled y/z tiles)
-for K in peer_boards line_major_tma host_batch yz_rot; do
+for K in peer_boards line_major_tma host_batch yz_rot lineop_tma; do
   PBX_TEST_ROUND2=1 timeout 300 python -m pytest tests -m gpu -k $K -q -x 2>&1 | tail -4 > gpurun_out/r2_gated_$K.log
   cat gpurun_out/r2_gated_$K.log
 done
