@@ -114,7 +114,9 @@ def test_slab_needs_64_to_512_planes():
 def test_peer_boards_one_gpu(P):
     """P slab handles of one process on one GPU, each on its own stream and host thread, linked by
     pbx_slab_link_peers: boundary messages by direct stores, flag barrier, all-reduce inside the CG's
-    reduction kernel -- against one handle on the whole brick"""
+    reduction kernel -- against one handle on the whole brick.  (A rank's barrier kernel spins on the
+    device until its neighbours' boundary sweeps have run, so the ranks' streams must not share a
+    hardware queue: P + 2 streams stay below the default CUDA_DEVICE_MAX_CONNECTIONS of 8.)"""
     import threading
 
     import torch
