@@ -104,8 +104,10 @@ struct Xchg {
     double *sm;
     int q, t, T, tstride;
     int open = 0;
+    int dead = 0;   // a thread without a chunk (tiles whose lines do not fill the CTA): reads zeros
     __device__ __forceinline__ int nb(int dt) const
     {
+        if (dead) return -1;
         int tt = t + dt;
         if (open) {
             if (tt < 0 || tt >= T) return -1;

@@ -56,6 +56,7 @@ struct YZT {
     long long sl, sg;         // global strides along the line / between lines of a group
     int se, sgm;              // shared-memory strides (doubles) along the line / between lines
     int nbox, RB;             // boxes per field per tile, line points per box
+    unsigned tbytes;          // bytes of one field's tile (64 KiB when the lines fill the CTA)
     int ntx, ntx8, ntiles;    // tiles along x (16 wide), 8-wide sub-tiles along x, total tiles
     int zdir;                 // 0: y pass (box = (16, RB, G)), 1: z pass (box = (16, G, RB))
     int rev;                  // 1: walk the tiles from the last to the first (L2 reuse, see lapl_fast)
@@ -94,7 +95,7 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
     // first line point of the tile: 0, or hlo chunks in front of the segment's interior; the boxes
     // of a segment tile wrap around the periodic line one by one (n is a multiple of RB)
     const int start = p.seg.nseg > 1 ? (id.s * p.seg.iseg - p.seg.hlo) * LC : 0;
-    mbar_expect_tx(&S.full, 2 * YZ_TILE_BYTES);
+    mbar_expect_tx(&S.full, 2 * p.tbytes);
     for (int b = 0; b < p.nbox; ++b) {
         int i0 = (start + b * p.RB) % p.n;
         if (i0 < 0) i0 += p.n;
@@ -112,7 +113,10 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
 // a half-warp differ in bit 2 of (row & 7), the swizzle sends them to different halves of the 128-byte
 // bank line, and 16 register swaps put the values back in order.  Whole lines in one CTA only (no
 // segments, no slab), and for the z pass one line per tile row (G == 1: lines of 512 points).
-template <bool ZPASS, bool SLAB, bool SEG, bool ROT>
+// ANYT (opt-in, PBX_TMA_ANY_T=1): line lengths whose chunk count does not divide 32 -- the lines that
+// fit into a compute group leave threads without a chunk (`dead`); a compile-time switch, so that the
+// measured kernels do not carry the test.
+template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT = false>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -140,7 +144,8 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     const BarGroup bar{1 + grp};
     constexpr bool segd = SEG;                               // tiles are segments of longer lines
     const int npts = SEG ? SEG_T * LC : p.n;                 // line points in a tile
-    Xchg xc{S.xchg[grp], lt, t, p.T, XW, (SLAB || segd) ? 1 : 0};
+    const bool dead = ANYT && tz >= p.G;                     // T does not divide 32: threads without a chunk
+    Xchg xc{S.xchg[grp], lt, t, p.T, XW, (SLAB || segd) ? 1 : 0, dead ? 1 : 0};
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
     int it = 0;
@@ -156,7 +161,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         const int gt = id.gt;
         const int x = xt8 * XW + tx;
         const int g = gt * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng) && sc.interior;
+        const bool live = (x < p.nx) && (g < p.ng) && sc.interior && !dead;
         const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
         double lo9[DIST_MSG], up9[DIST_MSG];
@@ -269,9 +274,10 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
 // ---------------------------------------------------------------------------------------------
 struct XT {
     CompositeCoef M, D;
-    int T;                    // chunks per line (power of two, <= 32)
-    int ntiles;               // tiles of 256 chunks
+    int T;                    // chunks per line (power of two; ANYT: any number up to 256)
+    int ntiles;               // tiles of 256 chunks (ANYT: of `rows` chunks)
     int rev;                  // 1: walk the tiles from the last to the first
+    int rows;                 // ANYT: chunks per tile = the whole lines that fit into 256
 };
 
 struct XShared {
@@ -325,11 +331,16 @@ __device__ __forceinline__ void solve_shfl(const CompositeCoef &c, double (&v)[L
 // WIDE = true:  T = 64, 128 or 256 chunks (lines of 1024 - 4096 points): a line spans several warps
 //               of the CTA, and the chunk states and solved halos go through shared memory
 //               (xpass_body, the arithmetic of the generic x kernel) -- same TMA data movement.
-template <bool WIDE>
+// ANYT (opt-in, PBX_TMA_ANY_T=1; with WIDE): any number of chunks per line up to 256 -- a tile holds
+//               the whole lines that fit into 256 chunks, the remaining threads idle.
+template <bool WIDE, bool ANYT = false>
 __global__ void __launch_bounds__(NT, 2)
 x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap mapF,
              const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB)
 {
+    static_assert(WIDE || !ANYT, "ANYT runs on the shared-memory exchange of the WIDE kernel");
+    const int rows = ANYT ? p.rows : NT;
+    const uint32_t tile_bytes = ANYT ? (uint32_t)p.rows * 128u : TILE_BYTES;
     extern __shared__ __align__(1024) unsigned char smraw[];
     XShared &S = *reinterpret_cast<XShared *>(smraw);
     const int tid = threadIdx.x;
@@ -339,8 +350,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         mbar_init(&S.empty, NT);
         fence_mbar_init();
         if ((int)blockIdx.x < p.ntiles) {
-            mbar_expect_tx(&S.full, TILE_BYTES);
-            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * NT);
+            mbar_expect_tx(&S.full, tile_bytes);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * rows);
         }
     }
     __syncthreads();
@@ -348,9 +359,13 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
     const int lane = tid & 31;
     const int T = p.T;
     const int seg = lane & ~(T - 1), t = lane & (T - 1);
-    // rows of the previous / next chunk of the same line
-    const int ql = WIDE ? ((tid & ~(T - 1)) | ((tid - 1) & (T - 1))) : ((tid & ~31) | seg | ((t - 1) & (T - 1)));
-    const int qr = WIDE ? ((tid & ~(T - 1)) | ((tid + 1) & (T - 1))) : ((tid & ~31) | seg | ((t + 1) & (T - 1)));
+    // chunk of the line and first row of the line (WIDE), rows of the previous / next chunk of the line
+    const int tw = ANYT ? tid % T : (tid & (T - 1)), lb = tid - tw;
+    const bool dead = ANYT && tid >= rows;
+    const int ql = ANYT ? lb + (tw == 0 ? T - 1 : tw - 1)
+                        : WIDE ? ((tid & ~(T - 1)) | ((tid - 1) & (T - 1))) : ((tid & ~31) | seg | ((t - 1) & (T - 1)));
+    const int qr = ANYT ? lb + (tw == T - 1 ? 0 : tw + 1)
+                        : WIDE ? ((tid & ~(T - 1)) | ((tid + 1) & (T - 1))) : ((tid & ~31) | seg | ((t + 1) & (T - 1)));
     int it = 0;
     for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
         const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
@@ -363,6 +378,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             ef[4 + 2 * j] = v2.y;
         }
         {
+            // (an idle ANYT thread's neighbours lie inside the tile buffer too: lb + T - 1 < 256 + T <= 512 rows
+            //  of tin + sta, never beyond the shared-memory block)
             double2 l6 = *reinterpret_cast<const double2 *>(S.tin + swz(ql, 6));
             double2 l7 = *reinterpret_cast<const double2 *>(S.tin + swz(ql, 7));
             double2 r0 = *reinterpret_cast<const double2 *>(S.tin + swz(qr, 0));
@@ -378,8 +395,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             const int nxt = tile0 + (int)gridDim.x;
             mbar_wait(&S.empty, (uint32_t)(it & 1));
-            mbar_expect_tx(&S.full, TILE_BYTES);
-            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - nxt : nxt) * NT);
+            mbar_expect_tx(&S.full, tile_bytes);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - nxt : nxt) * rows);
         }
 
         double va[LC], vb[LC];
@@ -388,7 +405,7 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             // read them
             if (tid == 0) tma_wait_read0();
             BarCompute()();
-            const Xchg xc{S.sta, tid, tid & (T - 1), T, 1};
+            const Xchg xc{S.sta, tid, tw, T, 1, 0, dead ? 1 : 0};
             xpass_body(p.M, p.D, xc, ef, va, vb, BarCompute());
         } else {
         stencil<true>(p.D, ef, va);
@@ -424,8 +441,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         fence_proxy_async();
         BarCompute()();
         if (tid == 0) {
-            tma_store_2d(&mapA, S.sta, 0, tile * NT);
-            tma_store_2d(&mapB, S.stb, 0, tile * NT);
+            tma_store_2d(&mapA, S.sta, 0, tile * rows);
+            tma_store_2d(&mapB, S.stb, 0, tile * rows);
             tma_commit();
         }
     }
@@ -450,7 +467,7 @@ __device__ __forceinline__ void lyz_issue_tile(LYZShared &S, int stage, const YZ
 {
     const TileId id = tile_id(p, tile);
     const int x0 = id.xt * XWT, g0 = id.gt * p.G;
-    mbar_expect_tx(&S.full[stage], YZ_TILE_BYTES);
+    mbar_expect_tx(&S.full[stage], p.tbytes);
     for (int b = 0; b < p.nbox; ++b) {
         const int i0 = b * p.RB;
         const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
@@ -484,15 +501,16 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
     const int t = (lt >> 3) % p.T;
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
-    const Xchg xc{S.xchg[grp], lt, t, p.T, XW, 0};
-    const int soff = tz * p.sgm + grp * XW + tx;
+    const bool dead = tz >= p.G;
+    const Xchg xc{S.xchg[grp], lt, t, p.T, XW, 0, dead ? 1 : 0};
+    const int soff = (dead ? 0 : tz * p.sgm) + grp * XW + tx;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t par = (uint32_t)((it >> 1) & 1);
         const int xt8 = (tile % p.ntx) * NGRP + grp, gt = tile / p.ntx;
         const int x = xt8 * XW + tx, g = gt * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng);
+        const bool live = (x < p.nx) && (g < p.ng) && !dead;
         const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
         mbar_wait(&S.full[st], par);
         double e[LC + 6], v[LC];
@@ -684,13 +702,13 @@ bool make_map_yz(CUtensorMap *m, const double *base, const Brick &g, const YZT &
 }
 
 // 2-D map [chunks][16] with the 128-byte swizzle for the x pass
-bool make_map_x(CUtensorMap *m, const double *base, size_t nchunks)
+bool make_map_x(CUtensorMap *m, const double *base, size_t nchunks, int rows = NT)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {16, (cuuint64_t)nchunks};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {16, (cuuint32_t)NT};
+    cuuint32_t box[2] = {16, (cuuint32_t)rows};
     cuuint32_t es[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box,
               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -717,7 +735,12 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     p->n = n;
     p->seg = seg_geometry(n / LC);
     p->T = p->seg.T;
-    if (NT % (XW * p->T)) return false;          // T must divide 32
+    // T must divide 32 -- or, opt-in (PBX_TMA_ANY_T=1, unmeasured), the lines that fit leave some
+    // threads of the group without a chunk (any multiple of 16 up to 512 points)
+    if (NT % (XW * p->T)) {
+        const char *e = getenv("PBX_TMA_ANY_T");
+        if (!(e && e[0] == '1') || p->seg.nseg > 1) return false;
+    }
     p->G = NT / (XW * p->T);
     p->ng = dir == 1 ? g.nz : g.ny;
     p->sl = dir == 1 ? (long long)g.nx : (long long)g.nx * g.ny;
@@ -734,6 +757,8 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
         p->RB = n / p->nbox;
     }
     if (p->nbox > 1 && p->G != 1) return false;
+    p->tbytes = (unsigned)(XWT * npts * p->G * 8);
+    if (p->tbytes > YZ_TILE_BYTES) return false;
     if (p->zdir) {          // smem layout [i][g][16]
         p->se = p->G * XWT;
         p->sgm = XWT;
@@ -774,7 +799,12 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
                    double *B, int rev, long long *launches)
 {
     const int T = g.nx / LC;
-    if (g.nx % LC || T > NT || (T & (T - 1)) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    if (g.nx % LC || T > NT || T < 1 || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    const bool anyT = (T & (T - 1)) != 0;   // opt-in: chunk counts that are not a power of two
+    if (anyT) {
+        const char *e = getenv("PBX_TMA_ANY_T");
+        if (!(e && e[0] == '1')) return PBX_ERR_UNSUPPORTED;
+    }
     const bool wide = T > 32;
     const size_t nchunks = g.N() / LC;
     if (nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
@@ -782,10 +812,12 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     p.M = fc.M;
     p.D = fc.D[0];
     p.T = T;
-    p.ntiles = (int)((nchunks + NT - 1) / NT);
+    p.rows = anyT ? (NT / T) * T : NT;
+    p.ntiles = (int)((nchunks + p.rows - 1) / p.rows);
     p.rev = rev;
     CUtensorMap mf, ma, mb;
-    if (!make_map_x(&mf, f, nchunks) || !make_map_x(&ma, A, nchunks) || !make_map_x(&mb, B, nchunks))
+    if (!make_map_x(&mf, f, nchunks, p.rows) || !make_map_x(&ma, A, nchunks, p.rows) ||
+        !make_map_x(&mb, B, nchunks, p.rows))
         return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(XShared);
     static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
@@ -796,11 +828,15 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
                                       (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(x_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = 2 * sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    if (wide)
+    if (anyT)
+        x_tma_kernel<true, true><<<grid, NT, smem, s>>>(p, mf, ma, mb);
+    else if (wide)
         x_tma_kernel<true><<<grid, NT, smem, s>>>(p, mf, ma, mb);
     else
         x_tma_kernel<false><<<grid, NT, smem, s>>>(p, mf, ma, mb);
@@ -816,12 +852,15 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
     if (zo.open && p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;   // the generic launcher reports it
+    const bool anyT = NT % (XW * p.T) != 0;
+    if (zo.open && anyT) return PBX_ERR_UNSUPPORTED;             // the slab look-back indexes directly
     p.rev = rev;
     p.M = fc.M;
     p.D = fc.D[dir];
     const bool segd = p.seg.nseg > 1;
     const char *re = getenv("PBX_YZ_ROT");
-    const bool rot = re && re[0] == '1' && !segd && !zo.open && (dir == 1 || p.G == 1) && p.T >= 2 && g.nx % XWT == 0;
+    const bool rot = re && re[0] == '1' && !segd && !zo.open && !anyT && (dir == 1 || p.G == 1) && p.T >= 2 &&
+                     g.nx % XWT == 0;
     CUtensorMap m0, m1;
     if (!make_map_yz(&m0, in0, g, p, rot) || !make_map_yz(&m1, in1, g, p, rot)) return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(YZShared);
@@ -837,11 +876,17 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, true, false>, (cudaFuncAttribute)a, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    if (rot && dir == 1)
+    if (anyT && dir == 1)
+        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    else if (anyT)
+        yz_tma_kernel<true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+    else if (rot && dir == 1)
         yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
     else if (rot)
         yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);

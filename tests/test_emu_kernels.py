@@ -451,3 +451,32 @@ def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
     h.close()
+
+
+@pytest.mark.parametrize("shape", [(16, 48, 192), (32, 384, 16), (16, 320, 48), (16, 96, 80), (32, 16, 272),
+                                   (48, 16, 16), (192, 32, 16), (1600, 16, 16), (96, 48, 80)])
+def test_emu_tma_any_chunk_count(shape, monkeypatch):
+    """PBX_TMA_ANY_T=1: lines whose chunk count is not a power of two (x: any multiple of 16 up to 4096;
+    y / z: 48 ... 384 points) on the TMA kernels -- a tile holds the whole lines that fit, the remaining
+    threads idle; the same bits as the generic kernels, Laplacian with its fused dot and the line
+    operators"""
+    dx = tuple(0.9 / n for n in shape)
+    f = field(shape, 41)
+    lib = emu_lib.load()
+    g = handle(shape, dx, no_tma="1")
+    ref, dref = g.lapl_dot(f)
+    gref = g.grad(f)
+    monkeypatch.setenv("PBX_TMA_ANY_T", "1")
+    h = handle(shape, dx)
+    maps0 = lib.pbx_emu_tensor_maps_total()
+    out, dot = h.lapl_dot(f)
+    nmaps = lib.pbx_emu_tensor_maps_total() - maps0
+    odd = lambda n: (n // 16) & (n // 16 - 1) != 0
+    assert nmaps >= 3 * odd(shape[0]) + 2 * odd(shape[1]) + 2 * odd(shape[2]), "the TMA kernels did not run"
+    # the field carries the same bits; the fused dot is summed over 256 threads (idle ones adding zeros)
+    # instead of the generic kernel's 8 T G, i.e. in another association
+    assert np.array_equal(out, ref) and abs(dot - dref) <= 1e-13 * abs(dref)
+    monkeypatch.setenv("PBX_LINEOP_TMA", "1")
+    assert np.array_equal(h.grad(f), gref)
+    h.close()
+    g.close()

@@ -8,7 +8,7 @@ timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2_test
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/r2_smoke.log; cat gpurun_out/r2_smoke.log
 timeout 300 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; cat gpurun_out/r2_bench_default.json
 # 2. the gated tests (peer boards on one GPU, TMA line-major tridsol, host batch, swizzled y/z tiles)
-for K in peer_boards line_major_tma host_batch yz_rot lineop_tma; do
+for K in peer_boards line_major_tma host_batch yz_rot lineop_tma any_chunk; do
   PBX_TEST_ROUND2=1 timeout 300 python -m pytest tests -m gpu -k $K -q -x 2>&1 | tail -4 > gpurun_out/r2_gated_$K.log
   cat gpurun_out/r2_gated_$K.log
 done
@@ -19,3 +19,7 @@ cat gpurun_out/r2_bench_rot.json
 timeout 200 python tools/prof_ops.py 256 > gpurun_out/r2_prof_ops.log 2>&1; tail -8 gpurun_out/r2_prof_ops.log
 # 5. counters of the y / z passes (planes, bank conflicts, with and without PBX_YZ_ROT)
 bash tools/run_gpu_r2_zpass.sh
+# 6. extents that are not 16 x a power of two: generic kernels against the TMA kernels (PBX_TMA_ANY_T=1)
+for anyt in 0 1; do
+  PBX_TMA_ANY_T=$anyt timeout 120 python tools/prof_lapl.py --n 384 > gpurun_out/r2_anyt${anyt}_384.log 2>&1; tail -1 gpurun_out/r2_anyt${anyt}_384.log
+done

@@ -6,7 +6,7 @@ set -x
 mkdir -p gpurun_out
 # 0. everything that is gated because it has never run on a GPU (peer boards on one GPU, TMA line-major
 #    tridsol, host batch), each in its own process so that a trap cannot poison the next
-for K in peer_boards line_major_tma host_batch yz_rot lineop_tma; do
+for K in peer_boards line_major_tma host_batch yz_rot lineop_tma any_chunk; do
   PBX_TEST_ROUND2=1 timeout 600 python -m pytest tests -m gpu -k $K -q -x 2>&1 | tail -4 > gpurun_out/r2_gated_$K.log
   cat gpurun_out/r2_gated_$K.log
 done
