@@ -550,6 +550,7 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
 struct LXShared {
     double tin[2][TILE_DOUBLES];
     double sta[TILE_DOUBLES];
+    double xchg[2 * NT];          // WIDE: chunk states of lines that span several warps
     uint64_t full[2], empty[2];
 };
 
@@ -569,6 +570,9 @@ struct LXT {
     int T, ntiles;
 };
 
+// WIDE: lines of 1024 - 4096 points (64 - 256 chunks) span several warps; their chunk states go through
+// shared memory (lineop::solve1_chunk) instead of shuffles.
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 2)
 lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUtensorMap mapIn,
                     const __grid_constant__ CUtensorMap mapOut)
@@ -594,7 +598,8 @@ lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUten
     __syncthreads();
     const int lane = tid & 31, T = p.T;
     const int seg = lane & ~(T - 1), t = lane & (T - 1);
-    const int ql = (tid & ~31) | seg | ((t - 1) & (T - 1)), qr = (tid & ~31) | seg | ((t + 1) & (T - 1));
+    const int ql = WIDE ? ((tid & ~(T - 1)) | ((tid - 1) & (T - 1))) : ((tid & ~31) | seg | ((t - 1) & (T - 1)));
+    const int qr = WIDE ? ((tid & ~(T - 1)) | ((tid + 1) & (T - 1))) : ((tid & ~31) | seg | ((t + 1) & (T - 1)));
     const CompositeCoef &c = p.op.cc;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -628,6 +633,11 @@ lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUten
             tma_load_2d(S.tin[st], &mapIn, &S.full[st], 0, (tile + 2 * (int)gridDim.x) * NT);
         }
         lineop::stencil4(p.op, e, v);
+        if (WIDE) {
+            // (two barriers per tile order the exchange slots between consecutive tiles)
+            const Xchg xc{S.xchg, tid, tid & (T - 1), T, 1};
+            lineop::solve1_chunk(c, xc, 0, v, BarCompute());
+        } else {
         // lineop::solve1_chunk with the chunk states travelling by shuffle
         double y = 0.0;
 #pragma unroll
@@ -646,6 +656,7 @@ lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUten
         const double Wc = lookback1_shfl(c, w, lane, T, +1);
 #pragma unroll
         for (int k = 0; k < LC; ++k) v[k] = fma(c.pw[LC - 1 - k], Wc, v[k]);
+        }
         // staging tile: the previous tile's TMA store must have read it
         if (tid == 0) tma_wait_read0();
         BarCompute()();
@@ -920,13 +931,14 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
         const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
         PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false>, a, (int)sizeof(LYZShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true>, a, (int)sizeof(LYZShared)));
-        PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel, a, (int)sizeof(LXShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<false>, a, (int)sizeof(LXShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<true>, a, (int)sizeof(LXShared)));
         attr_set[dev_ & 63] = true;
     }
     if (dir == 0) {
         const int T = g.nx / LC;
         const size_t nchunks = g.N() / LC;
-        if (addend || g.nx % LC || T > 32 || (T & (T - 1)) || nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
+        if (addend || g.nx % LC || T > NT || (T & (T - 1)) || nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
         LXT p;
         p.op = op;
         p.T = T;
@@ -935,7 +947,10 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
         if (!make_map_x(&mi, in, nchunks) || !make_map_x(&mo, out, nchunks)) return PBX_ERR_UNSUPPORTED;
         int grid = 2 * sm_count();
         if (grid > p.ntiles) grid = p.ntiles;
-        lineop_x_tma_kernel<<<grid, NT, sizeof(LXShared), s>>>(p, mi, mo);
+        if (T > 32)
+            lineop_x_tma_kernel<true><<<grid, NT, sizeof(LXShared), s>>>(p, mi, mo);
+        else
+            lineop_x_tma_kernel<false><<<grid, NT, sizeof(LXShared), s>>>(p, mi, mo);
     } else {
         YZT p;
         if (!yz_geometry_tma(g, dir, &p) || p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;
