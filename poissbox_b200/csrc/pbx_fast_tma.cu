@@ -467,15 +467,19 @@ __device__ __forceinline__ void lyz_issue_tile(LYZShared &S, int stage, const YZ
 {
     const TileId id = tile_id(p, tile);
     const int x0 = id.xt * XWT, g0 = id.gt * p.G;
+    // a segment of a longer line starts hlo chunks in front of its interior; its boxes wrap around the
+    // periodic line one by one (yz_issue_tile)
+    const int start = p.seg.nseg > 1 ? (id.s * p.seg.iseg - p.seg.hlo) * LC : 0;
     mbar_expect_tx(&S.full[stage], p.tbytes);
     for (int b = 0; b < p.nbox; ++b) {
-        const int i0 = b * p.RB;
+        int i0 = (start + b * p.RB) % p.n;
+        if (i0 < 0) i0 += p.n;
         const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
         tma_load_3d(&S.tile[stage][b * p.RB * p.se], map, &S.full[stage], x0, c1, c2);
     }
 }
 
-template <bool ADD>
+template <bool ADD, bool SEG>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ lineop::LineOp op,
                      const __grid_constant__ CUtensorMap map, const double *__restrict__ addend,
@@ -502,16 +506,23 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
     const int tz = lt / (XW * p.T);
     const BarGroup bar{1 + grp};
     const bool dead = tz >= p.G;
-    const Xchg xc{S.xchg[grp], lt, t, p.T, XW, 0, dead ? 1 : 0};
+    const Xchg xc{S.xchg[grp], lt, t, p.T, XW, SEG ? 1 : 0, dead ? 1 : 0};
     const int soff = (dead ? 0 : tz * p.sgm) + grp * XW + tx;
+    const int npts = SEG ? SEG_T * LC : p.n;     // line points in a tile
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t par = (uint32_t)((it >> 1) & 1);
-        const int xt8 = (tile % p.ntx) * NGRP + grp, gt = tile / p.ntx;
+        TileId id{0, tile % p.ntx, tile / p.ntx};
+        SegChunk sc{t, true};
+        if (SEG) {
+            id = tile_id(p, tile);
+            sc = seg_chunk(p.seg, id.s, t);
+        }
+        const int xt8 = id.xt * NGRP + grp, gt = id.gt;
         const int x = xt8 * XW + tx, g = gt * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng) && !dead;
-        const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
+        const bool live = (x < p.nx) && (g < p.ng) && !dead && sc.interior;
+        const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
         mbar_wait(&S.full[st], par);
         double e[LC + 6], v[LC];
         {
@@ -522,10 +533,12 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 int il = i0 - 3 + k, ir = i0 + LC + k;
-                if (il < 0) il += p.n;
-                if (ir >= p.n) ir -= p.n;
-                e[k] = tb[il * p.se];
-                e[LC + 3 + k] = tb[ir * p.se];
+                const bool lo = il < 0, hi = ir >= npts;
+                if (lo) il += npts;
+                if (hi) ir -= npts;
+                const double vl = tb[il * p.se], vr = tb[ir * p.se];
+                e[k] = (SEG && lo) ? 0.0 : vl;            // a segment is an open line
+                e[LC + 3 + k] = (SEG && hi) ? 0.0 : vr;
             }
         }
         mbar_arrive(&S.empty[st]);
@@ -929,8 +942,10 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
         const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false>, a, (int)sizeof(LYZShared)));
-        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false, false>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true, false>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false, true>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true, true>, a, (int)sizeof(LYZShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<false>, a, (int)sizeof(LXShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<true>, a, (int)sizeof(LXShared)));
         attr_set[dev_ & 63] = true;
@@ -953,16 +968,21 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
             lineop_x_tma_kernel<false><<<grid, NT, sizeof(LXShared), s>>>(p, mi, mo);
     } else {
         YZT p;
-        if (!yz_geometry_tma(g, dir, &p) || p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;
+        if (!yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
+        const bool segd = p.seg.nseg > 1;
         p.rev = 0;
         CUtensorMap m;
         if (!make_map_yz(&m, in, g, p)) return PBX_ERR_UNSUPPORTED;
         int grid = sm_count();
         if (grid > p.ntiles) grid = p.ntiles;
-        if (addend)
-            lineop_yz_tma_kernel<true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+        if (addend && segd)
+            lineop_yz_tma_kernel<true, true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+        else if (addend)
+            lineop_yz_tma_kernel<true, false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+        else if (segd)
+            lineop_yz_tma_kernel<false, true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
         else
-            lineop_yz_tma_kernel<false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
+            lineop_yz_tma_kernel<false, false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
     }
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
