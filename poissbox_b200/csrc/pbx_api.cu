@@ -78,6 +78,22 @@ int line_op(pbx_handle_s *h, int dir, OpKind kind, int stagger, const double *in
                        h->ref[dir][kind], in, out, &h->launches);
 }
 
+// interpolation and derivative of the SAME field along dir (grad's z and y stages): one launch that
+// reads the input once where the TMA line operators are in use, else two line operators
+int line_op_pair(pbx_handle_s *h, int dir, int stagger, const double *in, double *out_interp,
+                 double *out_deriv, bool fast, int zslot_interp, int zslot_deriv)
+{
+    if (fast && dir != 0 && !(h->nranks > 1 && dir == 2) && in != out_interp && in != out_deriv &&
+        !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out_interp) |
+           reinterpret_cast<uintptr_t>(out_deriv)) & 15)) {
+        const int rc = fast_line_op_tma(h->stream, Brick{h->nx, h->ny, h->nz}, dir, OP_INTERP, stagger, h->dx[dir],
+                                        in, out_interp, nullptr, &h->launches, out_deriv);
+        if (rc != PBX_ERR_UNSUPPORTED) return rc;
+    }
+    PBX_TRY(line_op(h, dir, OP_INTERP, stagger, in, out_interp, fast, zslot_interp));
+    return line_op(h, dir, OP_DERIV, stagger, in, out_deriv, fast, zslot_deriv);
+}
+
 }  // namespace
 
 // src/compact_schemes.f90:42-88 (Z -> Y -> X, backward stagger).  S = 5 scratch fields.
@@ -87,10 +103,8 @@ static int grad_stages(pbx_handle_s *h, const double *f, double *o1, double *o2,
     PBX_TRY(ensure_scratch(h, 5));
     double **S = h->scratch;
     const int B = PBX_STAGGER_BACKWARD;
-    PBX_TRY(line_op(h, 2, OP_INTERP, B, f, S[0], fast, 0));   // dff1 (= dff2, :63)
-    PBX_TRY(line_op(h, 2, OP_DERIV, B, f, S[1], fast, 1));    // dff3
-    PBX_TRY(line_op(h, 1, OP_INTERP, B, S[0], S[2], fast));   // dfe1
-    PBX_TRY(line_op(h, 1, OP_DERIV, B, S[0], S[3], fast));    // dfe2
+    PBX_TRY(line_op_pair(h, 2, B, f, S[0], S[1], fast, 0, 1));      // dff1 (= dff2, :63), dff3
+    PBX_TRY(line_op_pair(h, 1, B, S[0], S[2], S[3], fast, 0, 0));   // dfe1, dfe2
     PBX_TRY(line_op(h, 1, OP_INTERP, B, S[1], S[4], fast));   // dfe3
     PBX_TRY(line_op(h, 0, OP_DERIV, B, S[2], o1, fast));      // df1
     PBX_TRY(line_op(h, 0, OP_INTERP, B, S[3], o2, fast));     // df2

@@ -479,12 +479,16 @@ __device__ __forceinline__ void lyz_issue_tile(LYZShared &S, int stage, const YZ
     }
 }
 
-template <bool ADD, bool SEG>
+// DUAL: two operators on the same input per tile (grad's interpolation and derivative of one field along
+// z, resp. y: the input is read once, 24 instead of 32 B/point for the pair); second result to out2.
+template <bool ADD, bool SEG, bool DUAL = false>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ lineop::LineOp op,
                      const __grid_constant__ CUtensorMap map, const double *__restrict__ addend,
-                     double *__restrict__ out)
+                     double *__restrict__ out, const __grid_constant__ lineop::LineOp op2,
+                     double *__restrict__ out2)
 {
+    static_assert(!(ADD && DUAL), "the dual kernel has no addend");
     extern __shared__ __align__(1024) unsigned char smraw[];
     LYZShared &S = *reinterpret_cast<LYZShared *>(smraw);
     const int tid = threadIdx.x;
@@ -555,6 +559,14 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
             } else {
 #pragma unroll
                 for (int k = 0; k < LC; ++k) out[base + k * p.sl] = v[k];
+            }
+        }
+        if (DUAL) {
+            lineop::stencil4(op2, e, v);
+            lineop::solve1_chunk(op2.cc, xc, 2, v, bar);
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < LC; ++k) out2[base + k * p.sl] = v[k];
             }
         }
     }
@@ -930,13 +942,17 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
 }
 
 // one compact line operator along dir with the TMA-pipelined kernels; PBX_ERR_UNSUPPORTED: use the
-// generic kernel (not asked for with PBX_LINEOP_TMA=1, slab, segmented line, unsupported shape)
+// generic kernel (not asked for with PBX_LINEOP_TMA=1, slab, unsupported shape).  out2 (y, z only):
+// the other kind of operator (interpolation <-> derivative) on the same input goes there, in the same
+// launch.
 int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
-                     const double *in, double *out, const double *addend, long long *launches)
+                     const double *in, double *out, const double *addend, long long *launches, double *out2)
 {
     const char *en = getenv("PBX_LINEOP_TMA");
     if (!(en && en[0] == '1') || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    if (out2 && (dir == 0 || addend)) return PBX_ERR_UNSUPPORTED;
     const lineop::LineOp op = lineop::make_line_op(kind, stagger, dx);
+    const lineop::LineOp op2 = lineop::make_line_op(kind == OP_DERIV ? OP_INTERP : OP_DERIV, stagger, dx);
     static bool attr_set[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -946,6 +962,8 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
         PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true, false>, a, (int)sizeof(LYZShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false, true>, a, (int)sizeof(LYZShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<true, true>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false, false, true>, a, (int)sizeof(LYZShared)));
+        PBX_CUDA(cudaFuncSetAttribute(lineop_yz_tma_kernel<false, true, true>, a, (int)sizeof(LYZShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<false>, a, (int)sizeof(LXShared)));
         PBX_CUDA(cudaFuncSetAttribute(lineop_x_tma_kernel<true>, a, (int)sizeof(LXShared)));
         attr_set[dev_ & 63] = true;
@@ -975,14 +993,19 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
         if (!make_map_yz(&m, in, g, p)) return PBX_ERR_UNSUPPORTED;
         int grid = sm_count();
         if (grid > p.ntiles) grid = p.ntiles;
-        if (addend && segd)
-            lineop_yz_tma_kernel<true, true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+        const size_t sm = sizeof(LYZShared);
+        if (out2 && segd)
+            lineop_yz_tma_kernel<false, true, true><<<grid, NTHR_YZ, sm, s>>>(p, op, m, nullptr, out, op2, out2);
+        else if (out2)
+            lineop_yz_tma_kernel<false, false, true><<<grid, NTHR_YZ, sm, s>>>(p, op, m, nullptr, out, op2, out2);
+        else if (addend && segd)
+            lineop_yz_tma_kernel<true, true><<<grid, NTHR_YZ, sm, s>>>(p, op, m, addend, out, op2, nullptr);
         else if (addend)
-            lineop_yz_tma_kernel<true, false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, addend, out);
+            lineop_yz_tma_kernel<true, false><<<grid, NTHR_YZ, sm, s>>>(p, op, m, addend, out, op2, nullptr);
         else if (segd)
-            lineop_yz_tma_kernel<false, true><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
+            lineop_yz_tma_kernel<false, true><<<grid, NTHR_YZ, sm, s>>>(p, op, m, nullptr, out, op2, nullptr);
         else
-            lineop_yz_tma_kernel<false, false><<<grid, NTHR_YZ, sizeof(LYZShared), s>>>(p, op, m, nullptr, out);
+            lineop_yz_tma_kernel<false, false><<<grid, NTHR_YZ, sm, s>>>(p, op, m, nullptr, out, op2, nullptr);
     }
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
