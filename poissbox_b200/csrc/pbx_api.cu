@@ -129,11 +129,19 @@ static int div_stages_xy(pbx_handle_s *h, const double *i1, const double *i2, co
     PBX_TRY(line_op(h, 0, OP_INTERP, F, i2, S[4], fast));     // dfe2
     double *e3 = S[0];                                  // i1 (possibly S[0]) is consumed by now
     PBX_TRY(line_op(h, 0, OP_INTERP, F, i3, e3, fast));       // dfe3
-    PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));   // dff1
     if (fast) {
-        PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast, 0, S[1]));   // dff1 + dff2 (:249)
+        // dff1 + dff2 (:249): in one launch where the TMA line operators are in use (the first summand stays
+        // in registers), else the interpolation to S[1] and the derivative with S[1] as its addend
+        int rc = fast_line_op_sum_tma(h->stream, Brick{h->nx, h->ny, h->nz}, 1, OP_INTERP, OP_DERIV, F, h->dx[1],
+                                      S[3], S[4], S[2], &h->launches);
+        if (rc == PBX_ERR_UNSUPPORTED) {
+            PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));            // dff1
+            rc = line_op(h, 1, OP_DERIV, F, S[4], S[2], fast, 0, S[1]);
+        }
+        PBX_TRY(rc);
         return line_op(h, 1, OP_INTERP, F, e3, S[3], fast);              // dff3
     }
+    PBX_TRY(line_op(h, 1, OP_INTERP, F, S[3], S[1], fast));   // dff1
     PBX_TRY(line_op(h, 1, OP_DERIV, F, S[4], S[2], fast));    // dff2
     PBX_TRY(line_op(h, 1, OP_INTERP, F, e3, S[3], fast));     // dff3
     return ref_add(h->stream, N, S[1], S[2], S[4], &h->launches);   // :249
@@ -144,6 +152,11 @@ static int div_stages_z(pbx_handle_s *h, double *out, bool fast = false)
     double **S = h->scratch;
     const int F = PBX_STAGGER_FORWARD;
     const size_t N = (size_t)h->nx * h->ny * h->nz;
+    if (fast && h->nranks == 1) {   // dfc + df (:251) in one launch where the TMA line operators are in use
+        const int rc = fast_line_op_sum_tma(h->stream, Brick{h->nx, h->ny, h->nz}, 2, OP_INTERP, OP_DERIV, F, h->dx[2],
+                                            S[div_zi(fast)], S[3], out, &h->launches);
+        if (rc != PBX_ERR_UNSUPPORTED) return rc;
+    }
     PBX_TRY(line_op(h, 2, OP_INTERP, F, S[div_zi(fast)], S[0], fast, 0));   // dfc
     if (fast) return line_op(h, 2, OP_DERIV, F, S[3], out, fast, 1, S[0]);    // df + dfc (:251)
     // the z derivative goes to a scratch field first: the sum is a separate, reference-order step

@@ -242,6 +242,8 @@ bool fast_tma_available();
 int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
                      const double *in, double *out, const double *addend, long long *launches,
                      double *out2 = nullptr);
+int fast_line_op_sum_tma(cudaStream_t s, const Brick &g, int dir, OpKind kindA, OpKind kindB, int stagger,
+                         double dx, const double *inA, const double *inB, double *out, long long *launches);
 bool tma_make_map_2d(CUtensorMap_st *m, const double *base, unsigned long long dim0, unsigned long long dim1,
                      unsigned long long stride1_bytes, unsigned box0, unsigned box1, bool swizzle128);
 // line-major batches by TMA tiles (pbx_tdma_tma.cu); PBX_ERR_UNSUPPORTED = use the generic kernel

@@ -447,8 +447,12 @@ def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
     want = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
     monkeypatch.setenv("PBX_LINEOP_TMA", "1")
     maps0 = lib.pbx_emu_tensor_maps_total()
+    lib.pbx_launch_count.restype = ctypes.c_longlong
+    l0 = lib.pbx_launch_count(h._h)
     got = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
     assert lib.pbx_emu_tensor_maps_total() > maps0, "the TMA line operators did not run"
+    # grad: two operator pairs share a launch; div: its two sums are formed inside a two-input launch
+    assert lib.pbx_launch_count(h._h) - l0 == 6 + 6 + 3 + 3
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
     h.close()
