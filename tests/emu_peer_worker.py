@@ -68,7 +68,7 @@ gathered = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
 dist.all_gather(gathered, torch.from_numpy(vals.copy()))
 same_bits = all(torch.equal(g, gathered[0]) for g in gathered)
 
-MAXIT = 60   # bounded: the harness runs ~10 iterations a second
+MAXIT = 30   # bounded: the harness runs ~10 iterations a second
 # the distributed CG against the single-handle CG on the whole brick: same iteration count, same
 # residual history (to rounding of the differently associated sums), same solution
 # (b = A f with a full-spectrum f: for smooth right-hand sides the history is governed by rounding

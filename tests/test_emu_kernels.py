@@ -435,7 +435,7 @@ def test_emu_ksp_options(capfd):
 
 
 @pytest.mark.parametrize("shape", [(64, 32, 64), (32, 512, 16), (16, 16, 512), (512, 16, 16), (48, 64, 32), (16, 256, 16),
-                                   (1024, 16, 16), (4096, 16, 16), (16, 1024, 16), (16, 16, 2048), (16, 576, 16)])
+                                   (1024, 16, 16), (2048, 16, 16), (16, 1024, 16), (16, 16, 2048), (16, 576, 16)])
 def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
     """PBX_LINEOP_TMA=1: grad / div / interp through the TMA-pipelined line-operator kernels (two tile
     stages, x direction by shuffles) -- the same bits as the generic line-operator kernels"""
