@@ -29,3 +29,12 @@ if [ "$N" -ge 2 ]; then
     done
   done
 fi
+# D. BASELINE configs[4]: 1024^3 over 8 B200 (1024-point x and y lines, 128-plane slabs), MatMult and a bounded CG
+if [ "$N" -ge 8 ]; then
+  for PS in 0 1; do
+    PBX_PEER_SYNC=$PS timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+      --master-port 29557 bench.py --gpus 8 --n 1024 --no-cpu --no-e2e --cg-maxit 300 \
+      > gpurun_out/r2_bench_1024_w8_ps${PS}.json 2> gpurun_out/r2_bench_1024_w8_ps${PS}.err
+    cat gpurun_out/r2_bench_1024_w8_ps${PS}.json
+  done
+fi
