@@ -282,9 +282,12 @@ int fast_pass(pbx_handle_s *h, int dir, const double *in0, const double *in1, do
     // measured on B200 at 512^3 (profiles/README.md): TMA-pipelined x / y / z passes run at
     // 90 / 85 / 76 % of the measured HBM peak against 45 / 74 / 66 % for the generic kernels.
     if (h->use_tma && (dir == 0 || h->use_tma_yz)) {
+        bool used = false;
         int rc = dir == 0 ? fast_xpass_tma(h->stream, g, h->fc, in0, out0, out1, rev, &h->launches)
                           : fast_yzpass_tma(h->stream, g, h->fc, dir, in0, in1, out0, out1, p,
-                                            partials, zo, rev, &h->launches);
+                                            partials, zo, rev, &h->launches,
+                                            (dir == 2 && p && partials) ? h->pending_tail : nullptr, &used);
+        if (used) h->pending_tail = nullptr;   // the kernel reduces its partial sums itself
         if (rc != PBX_ERR_UNSUPPORTED) return rc;
     }
     if (dir == 0) return fast_xpass(h->stream, g, h->fc, in0, out0, out1, &h->launches);

@@ -24,41 +24,15 @@
 //   mean = m0 + S1/N ,  ||z||^2 = S2 - S1^2/N   with S1 = sum(r - m0), S2 = sum (r - m0)^2,
 // which avoids the cancellation a raw sum(r^2) - N mean^2 would suffer when mean(b) != 0.
 #include <cmath>
+#include <cstdlib>
 
-#include "pbx_internal.h"
-#include "pbx_peer.cuh"
+#include "pbx_cg_dev.cuh"
 
 namespace pbx {
 
+using namespace cgdev;
+
 namespace {
-
-enum {
-    SC_M0 = 0, SC_S1, SC_S2, SC_PW, SC_BETA, SC_BETAOLD, SC_A, SC_B, SC_DP, SC_DP0, SC_TTOL,
-    SC_PWOLD, SC_STATUS, SC_IT, SC_RTOL, SC_ABSTOL, SC_MEAN, SC_MAXIT, SC_NTOT,
-    // preconditioned CG: sums of z, z^2, z (r - m0), (r - m0) (contiguous: one reduction), mean of z
-    SC_SZ, SC_SZZ, SC_SZR, SC_SR, SC_MZ,
-    SC_XIT,   // number of the iteration whose step length SC_A is (x += a p of that iteration pending)
-    SC_COUNT
-};
-
-constexpr int VT = 256;
-
-__device__ __forceinline__ double block_sum(double v, double *sh)
-{
-    // fixed-shape: warp shuffle tree, then warp 0 over the warp sums (blockDim.x == VT)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < VT / 32 ? sh[threadIdx.x] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    }
-    return s;   // valid in thread 0
-}
 
 // each CTA owns a contiguous slice so that the summation order is fixed
 __device__ __forceinline__ void slice(size_t N, size_t *lo, size_t *hi)
@@ -159,7 +133,7 @@ k_update(size_t N, double *__restrict__ x, double *__restrict__ r, const double 
 // r -= a w ; partial sums of r - m0   (PC none: x is updated together with p, k_pupdate_x)
 __global__ void __launch_bounds__(VT)
 k_update_r(size_t N, double *__restrict__ r, const double *__restrict__ w, const double *__restrict__ sc,
-           double *__restrict__ part, int np)
+           double *__restrict__ part, int np, const __grid_constant__ RedTail tail)
 {
     __shared__ double sh[VT / 32];
     if (sc[SC_STATUS] != 0.0) return;
@@ -191,6 +165,8 @@ k_update_r(size_t N, double *__restrict__ r, const double *__restrict__ w, const
         part[blockIdx.x] = s1;
         part[np + blockIdx.x] = s2;
     }
+    // PBX_FUSE_TAIL: the CTA that finishes last sums the partials, all-reduces them and runs the scalar step
+    if (tail.on) red_tail<VT>(tail);
 }
 
 // x += a p (iteration `itag`, if its step length was computed: also when that iteration converged or
@@ -305,126 +281,6 @@ k_init_pc(size_t N, const double *__restrict__ b, double *__restrict__ x, double
     }
 }
 
-// the scalar logic of the KSPCG loop; one thread
-//   phase 0: m0 = S1 / N                     (S1 = sum b)
-//   phase 1: initial residual norm / test    (S1, S2 about m0)
-//   phase 2: a = beta / (p.w), indefiniteness test
-//   phase 3: new residual norm, test, b = beta/beta_old
-// with a preconditioner (z = M^-1 r, sums SC_SZ .. SC_SR of z, z^2, z (r - m0), r - m0):
-//   phase 4: first application: mean of z, ||z||, beta = z.r, test
-//   phase 5: mean of the updated residual (S1 about m0), the right-hand side's mean for the next PC
-//   phase 6: as phase 4 after an iteration: counts it, b = beta/beta_old, tests
-//   phase 7 / 8: SC_MEAN / SC_MZ = S1 / N (stand-alone preconditioner application)
-__device__ void scalar_phase(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
-{
-    const double N = sc[SC_NTOT];
-    if (phase == 0) {
-        sc[SC_M0] = sc[SC_S1] / N;
-        sc[SC_MEAN] = sc[SC_M0];
-        return;
-    }
-    if (phase == 7 || phase == 8) {
-        sc[phase == 7 ? SC_MEAN : SC_MZ] = sc[SC_S1] / N;
-        return;
-    }
-    if (sc[SC_STATUS] != 0.0) return;
-    if (phase == 5) {
-        sc[SC_MEAN] = sc[SC_M0] + sc[SC_S1] / N;
-        return;
-    }
-    if (phase == 4 || phase == 6) {
-        const double mz = sc[SC_SZ] / N;
-        double zz = sc[SC_SZZ] - sc[SC_SZ] * mz;
-        if (zz < 0.0) zz = 0.0;
-        const double dp = sqrt(zz);
-        const double beta = sc[SC_SZR] - mz * sc[SC_SR];   // (z - mz) . r
-        sc[SC_MZ] = mz;
-        sc[SC_DP] = dp;
-        int it = (int)sc[SC_IT];
-        if (phase == 4) {
-            sc[SC_DP0] = dp;
-            sc[SC_TTOL] = fmax(sc[SC_RTOL] * dp, sc[SC_ABSTOL]);
-            sc[SC_BETA] = beta;
-            sc[SC_B] = 0.0;
-            sc[SC_PWOLD] = 0.0;
-            if (hist && nhist > 0) hist[0] = dp;
-        } else {
-            it += 1;
-            sc[SC_IT] = it;
-            sc[SC_BETAOLD] = sc[SC_BETA];
-            sc[SC_BETA] = beta;
-            sc[SC_B] = beta / sc[SC_BETAOLD];
-            if (hist && it < nhist) hist[it] = dp;
-        }
-        if (dp != dp || beta != beta)
-            sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
-        else if (dp <= sc[SC_TTOL])
-            sc[SC_STATUS] = dp < sc[SC_ABSTOL] ? PBX_CONVERGED_ATOL : PBX_CONVERGED_RTOL;
-        else if (beta < 0.0)
-            sc[SC_STATUS] = PBX_DIVERGED_INDEFINITE_PC;
-        else if (phase == 6 && dp >= 1.0e4 * sc[SC_DP0])
-            sc[SC_STATUS] = PBX_DIVERGED_DTOL;
-        else if (phase == 6 && it >= (int)sc[SC_MAXIT])
-            sc[SC_STATUS] = PBX_DIVERGED_ITS;
-        return;
-    }
-    if (phase == 2) {
-        const double dpi = sc[SC_PW], dpiold = sc[SC_PWOLD];
-        const int i = (int)sc[SC_IT];
-        const double beta = sc[SC_BETA];
-        if (beta == 0.0) {
-            sc[SC_IT] = i + 1;
-            sc[SC_STATUS] = PBX_CONVERGED_ATOL;
-            return;
-        }
-        if (dpi != dpi) {
-            sc[SC_IT] = i + 1;
-            sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
-            return;
-        }
-        const double sg = (dpi > 0) - (dpi < 0), sgo = (dpiold > 0) - (dpiold < 0);
-        if (dpi == 0.0 || (i > 0 && sg * sgo < 0.0)) {
-            sc[SC_IT] = i + 1;
-            sc[SC_STATUS] = PBX_DIVERGED_INDEFINITE_MAT;
-            return;
-        }
-        sc[SC_PWOLD] = dpi;
-        sc[SC_A] = beta / dpi;
-        sc[SC_XIT] = i + 1;
-        return;
-    }
-    // phases 1 and 3: S1, S2 are sums of (r - m0), (r - m0)^2
-    const double dm = sc[SC_S1] / N;
-    double zz = sc[SC_S2] - sc[SC_S1] * dm;
-    if (zz < 0.0) zz = 0.0;
-    const double dp = sqrt(zz);
-    sc[SC_MEAN] = sc[SC_M0] + dm;
-    sc[SC_DP] = dp;
-    int it = (int)sc[SC_IT];
-    if (phase == 1) {
-        sc[SC_DP0] = dp;
-        sc[SC_TTOL] = fmax(sc[SC_RTOL] * dp, sc[SC_ABSTOL]);
-        sc[SC_BETA] = zz;
-        sc[SC_PWOLD] = 0.0;
-        if (hist && nhist > 0) hist[0] = dp;
-    } else {
-        it += 1;
-        sc[SC_IT] = it;
-        sc[SC_BETAOLD] = sc[SC_BETA];
-        sc[SC_BETA] = zz;
-        sc[SC_B] = zz / sc[SC_BETAOLD];
-        if (hist && it < nhist) hist[it] = dp;
-    }
-    if (dp != dp)
-        sc[SC_STATUS] = PBX_DIVERGED_NANORINF;
-    else if (dp <= sc[SC_TTOL])
-        sc[SC_STATUS] = dp < sc[SC_ABSTOL] ? PBX_CONVERGED_ATOL : PBX_CONVERGED_RTOL;
-    else if (phase == 3 && dp >= 1.0e4 * sc[SC_DP0])
-        sc[SC_STATUS] = PBX_DIVERGED_DTOL;
-    else if (phase == 3 && it >= (int)sc[SC_MAXIT])
-        sc[SC_STATUS] = PBX_DIVERGED_ITS;
-}
-
 __global__ void k_scalar(double *__restrict__ sc, int phase, double *__restrict__ hist, int nhist)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -485,6 +341,8 @@ int cg_alloc(pbx_handle_s *h, int maxit)
         h->cg_npartials = np;
         PBX_CUDA(cudaMalloc(&h->cg_partials, 4 * (size_t)np * sizeof(double)));
         PBX_CUDA(cudaMalloc(&h->cg_scal, SC_COUNT * sizeof(double)));
+        PBX_CUDA(cudaMalloc(&h->cg_ticket, sizeof(unsigned)));
+        PBX_CUDA(cudaMemset(h->cg_ticket, 0, sizeof(unsigned)));
         PBX_CUDA(cudaMallocHost(&h->cg_host, 2 * SC_COUNT * sizeof(double)));
     }
     if (h->pc != PBX_PC_NONE && !h->cg_z) PBX_CUDA(cudaMalloc(&h->cg_z, N * sizeof(double)));
@@ -536,6 +394,26 @@ __global__ void k_dot_generic(size_t N, const double *__restrict__ a, const doub
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
+// PBX_FUSE_TAIL=1: the reduction of the per-CTA partial sums, its all-reduce and the scalar step run in
+// the tail of the kernel that wrote the partials (cgdev::red_tail) instead of in further launches.
+// Possible on one rank and with the peer boards (an NCCL all-reduce cannot be called from a kernel).
+bool make_tail(pbx_handle_s *h, double *dst, int guarded, int phase, RedTail *t)
+{
+    const char *e = getenv("PBX_FUSE_TAIL");
+    if (!(e && e[0] == '1') || !h->cg_ticket) return false;
+    *t = RedTail();
+    if (h->nranks > 1 && !dist_peer_next(h, &t->L, &t->seq)) return false;
+    t->on = 1;
+    t->ticket = h->cg_ticket;
+    t->sc = h->cg_scal;
+    t->dst = dst;
+    t->hist = h->cg_hist;
+    t->nhist = h->cg_hist_cap;
+    t->phase = phase;
+    t->guarded = guarded;
+    return true;
+}
+
 // w = A p and p.w (over all ranks) into dst (device), then scalar step `phase` (< 0: none)
 int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int guarded, int phase)
 {
@@ -547,11 +425,16 @@ int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int gu
         np = vec_grid(N);
         k_dot_generic<<<np, VT, 0, s>>>(N, p, w, h->cg_partials);
         ++h->launches;
-    } else if (h->nranks > 1) {
-        PBX_TRY(dist_lapl(h, p, w, p, h->cg_partials));
-        np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
-    } else if (h->mode == PBX_MODE_FAST) {
-        PBX_TRY(lapl_fast(h, p, w, p, h->cg_partials));
+    } else if (h->nranks > 1 || h->mode == PBX_MODE_FAST) {
+        // the z pass may reduce its partial sums itself (it takes h->pending_tail if it can)
+        RedTail tail;
+        const bool offered = make_tail(h, dst, guarded, phase, &tail);
+        h->pending_tail = offered ? &tail : nullptr;
+        const int rc = h->nranks > 1 ? dist_lapl(h, p, w, p, h->cg_partials) : lapl_fast(h, p, w, p, h->cg_partials);
+        const bool taken = offered && h->pending_tail == nullptr;
+        h->pending_tail = nullptr;
+        PBX_TRY(rc);
+        if (taken) return PBX_OK;
         np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
     } else {
         PBX_TRY(lapl_reference(h, p, w));
@@ -572,6 +455,8 @@ void cg_free(pbx_handle_s *h)
     if (h->cg_w) cudaFree(h->cg_w);
     if (h->cg_partials) cudaFree(h->cg_partials);
     if (h->cg_scal) cudaFree(h->cg_scal);
+    if (h->cg_ticket) cudaFree(h->cg_ticket);
+    h->cg_ticket = nullptr;
     if (h->cg_host) cudaFreeHost(h->cg_host);
     if (h->cg_hist) cudaFree(h->cg_hist);
     if (h->cg_z) cudaFree(h->cg_z);
@@ -753,9 +638,19 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
         const int slot = issued & 1;
         rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2);
         if (rc != PBX_OK) break;
-        k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np);
-        ++h->launches;
-        if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;
+        RedTail tail;
+        if (make_tail(h, sc + SC_S1, 1, 3, &tail)) {
+            tail.part = part;
+            tail.cnt = nb;
+            tail.stride = np;
+            tail.narr = 2;
+            k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np, tail);
+            ++h->launches;
+        } else {
+            k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np, RedTail());
+            ++h->launches;
+            if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;
+        }
         k_pupdate_x<<<vec_grid(N), VT, 0, s>>>(N, r, p, x, sc, issued + 1);
         ++h->launches;
         cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double),

@@ -24,6 +24,7 @@
 
 #include "pbx_fast_common.cuh"
 #include "pbx_fast_lineop.cuh"
+#include "pbx_cg_dev.cuh"
 
 namespace pbx {
 
@@ -116,12 +117,16 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
 // ANYT (opt-in, PBX_TMA_ANY_T=1): line lengths whose chunk count does not divide 32 -- the lines that
 // fit into a compute group leave threads without a chunk (`dead`); a compile-time switch, so that the
 // measured kernels do not carry the test.
-template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT = false>
+// FUSE (opt-in, PBX_FUSE_TAIL=1; z pass with the fused dot): the CTA that finishes last reduces the
+// partial sums of p.out, all-reduces them over the peer boards and runs the CG's scalar step
+// (cgdev::red_tail) -- compute and collective in ONE kernel, two launches fewer per iteration.
+template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT = false, bool FUSE = false>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
               double *__restrict__ out0, double *__restrict__ out1,
-              const double *__restrict__ pv, double *__restrict__ partials)
+              const double *__restrict__ pv, double *__restrict__ partials,
+              const __grid_constant__ RedTail tail)
 {
     extern __shared__ __align__(1024) unsigned char smraw[];
     YZShared &S = *reinterpret_cast<YZShared *>(smraw);
@@ -267,6 +272,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
             }
         }
     }
+    if (FUSE) cgdev::red_tail<NTHR_YZ>(tail);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -980,8 +986,10 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
 
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, const ZOpen &zo, int rev, long long *launches)
+                    double *partials, const ZOpen &zo, int rev, long long *launches, const RedTail *tail,
+                    bool *tail_used)
 {
+    if (tail_used) *tail_used = false;
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, dir, &p)) return PBX_ERR_UNSUPPORTED;
     if (zo.open && p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;   // the generic launcher reports it
@@ -1011,28 +1019,41 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
         attr_set[dev_ & 63] = true;
     }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    if (anyT && dir == 1)
-        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+    const bool fuse = tail && tail->on && dir == 2 && pvec && partials && !segd && !anyT && !rot;
+    if (fuse) {
+        RedTail t = *tail;
+        t.part = partials;
+        t.cnt = t.stride = p.ntx8 * p.ngt;   // one partial sum per 8-wide sub-tile (fast_zpass_max_partials)
+        t.narr = 1;
+        if (zo.open)
+            yz_tma_kernel<true, true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, t);
+        else
+            yz_tma_kernel<true, false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, t);
+        if (tail_used) *tail_used = true;
+    } else if (anyT && dir == 1)
+        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (anyT)
-        yz_tma_kernel<true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (rot && dir == 1)
-        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (rot)
-        yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (dir == 1 && !segd)
-        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (dir == 1)
-        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr);
+        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (zo.open)
-        yz_tma_kernel<true, true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (!segd)
-        yz_tma_kernel<true, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else
-        yz_tma_kernel<true, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials);
+        yz_tma_kernel<true, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

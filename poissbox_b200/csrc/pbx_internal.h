@@ -179,6 +179,22 @@ struct PeerLinks {
     int n, rank, lower, upper;
 };
 
+// Reduction tail (pbx_cg_dev.cuh): what the kernel that writes per-CTA partial sums needs in order to
+// reduce them itself, all-reduce the result over the peer boards and run the scalar step of the CG.
+struct RedTail {
+    int on = 0;                    // 0: the kernel leaves the reduction to later launches
+    unsigned *ticket = nullptr;    // device counter, zero between launches
+    double *sc = nullptr;          // the CG's scalar block
+    double *dst = nullptr;         // where the sums go (inside the scalar block)
+    double *hist = nullptr;
+    int nhist = 0;
+    const double *part = nullptr;  // the partial sums: narr arrays of cnt values, `stride` apart
+    int cnt = 0, stride = 0, narr = 0;
+    int phase = -1, guarded = 0;
+    PeerLinks L{};                 // L.n <= 1: single rank
+    unsigned long long seq = 0;
+};
+
 // Long lines.  A CTA holds at most SEG_T chunks (512 points) of a y or z line.  A longer line is cut
 // into segments of `iseg` chunks that are computed independently as OPEN lines of SEG_T chunks:
 // `hlo` halo chunks below and the rest above the segment are loaded (wrapping around the periodic
@@ -255,9 +271,12 @@ int tdma_periodic_batch_lm(cudaStream_t s, int n, long long nl, long long es, lo
                            const double *b, const double *c, double *d, double *ws);
 int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double *f, double *A,
                    double *B, int rev, long long *launches);
+// tail (z pass with a fused dot only): reduce the partial sums inside the kernel (RedTail); *tail_used
+// tells whether the launched kernel took it
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
-                    double *partials, const ZOpen &zo, int rev, long long *launches);
+                    double *partials, const ZOpen &zo, int rev, long long *launches,
+                    const RedTail *tail = nullptr, bool *tail_used = nullptr);
 
 }  // namespace pbx
 
@@ -295,6 +314,8 @@ struct pbx_handle_s {
     double *cg_host = nullptr;       // pinned host mirror of the scalar block
     double *cg_hist = nullptr;       // device residual history
     int cg_hist_cap = 0;
+    unsigned *cg_ticket = nullptr;   // ticket counter of the reduction tails (zero between launches)
+    const pbx::RedTail *pending_tail = nullptr;   // set by the CG around a MatMult: the z pass may take it
 
     // z-slab decomposition (pbx_dist.cu)
     void *dist = nullptr;

@@ -118,5 +118,12 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline long long clock64() { return 0; }
+static inline void __threadfence() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v)   // one CTA at a time, fibers switch at barriers only
+{
+    const unsigned o = *p;
+    *p = o + v;
+    return o;
+}
 [[noreturn]] static inline void __trap() { pbx_emu::die("__trap()"); }
 using std::fma;

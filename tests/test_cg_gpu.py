@@ -5,6 +5,8 @@ what is checked is that both implementations of the same KSPCG loop agree -- ite
 within +-1 (BASELINE north_star), the same convergence reason, matching residual histories --
 and that the solution solves the system.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -238,4 +240,25 @@ def test_ksp_options(capfd):
     assert whym == 2 and itm < it0 * 4
     with pytest.raises(pbx.PbxError):
         h.ksp_solve(b, "-ksp_type gmres")
+    h.close()
+
+
+@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
+                    reason="PBX_FUSE_TAIL (reduction tails inside the z pass and the residual update) was written "
+                           "after the round's GPU budget was spent: CPU-harness tested only")
+def test_fused_reduction_tails(monkeypatch):
+    import torch
+
+    n = 64
+    dx = (2 * np.pi / n,) * 3
+    rng = np.random.default_rng(5)
+    b = pbx.fortran_to_torch(orc.lapl(np.asfortranarray(rng.uniform(-1, 1, (n, n, n))), dx))
+    h = pbx.Handle(n, n, n, dx)
+    x0, it0, _, why0, hist0 = h.cg_solve(b, rtol=1e-8)
+    monkeypatch.setenv("PBX_FUSE_TAIL", "1")
+    l0 = h.launches
+    x1, it1, _, why1, hist1 = h.cg_solve(b, rtol=1e-8)
+    torch.cuda.synchronize()
+    assert (why1, why0) == (2, 2) and abs(it1 - it0) <= 1 and (h.launches - l0) / it1 < 5.5
+    assert (x1 - x0).abs().max().item() <= 1e-6 * x0.abs().max().item()
     h.close()

@@ -485,3 +485,32 @@ def test_emu_tma_any_chunk_count(shape, monkeypatch):
     assert np.array_equal(h.grad(f), gref)
     h.close()
     g.close()
+
+
+def test_emu_fused_reduction_tails(monkeypatch):
+    """PBX_FUSE_TAIL=1: the kernels that write per-CTA partial sums (z pass with its fused dot, residual
+    update) reduce them in their last CTA and run the CG's scalar step there: five launches per
+    iteration instead of nine, the same iterations and the same x"""
+    n = 16
+    dx = (2 * np.pi / n,) * 3
+    b = orc.lapl(field((n, n, n), 5), dx)
+    h = handle((n, n, n), dx)
+    lib = h.lib
+    lib.pbx_launch_count.restype = ctypes.c_longlong
+    x0, it0, rn0, why0, hist0 = h.cg_solve(b, rtol=1e-6)
+    out0, dot0 = h.lapl_dot(b)
+    monkeypatch.setenv("PBX_FUSE_TAIL", "1")
+    l0 = lib.pbx_launch_count(h._h)
+    x1, it1, rn1, why1, hist1 = h.cg_solve(b, rtol=1e-6)
+    per_it = (lib.pbx_launch_count(h._h) - l0) / it1
+    assert (it1, why1) == (it0, why0) and per_it < 5.5
+    assert np.allclose(hist1, hist0, rtol=1e-12) and np.max(np.abs(x1 - x0)) <= 1e-12 * np.max(np.abs(x0))
+    for kw in (dict(rtol=0.5), dict(rtol=1e-8, maxit=3)):      # early exits: the last step still reaches x
+        monkeypatch.delenv("PBX_FUSE_TAIL")
+        a = h.cg_solve(b, **kw)
+        monkeypatch.setenv("PBX_FUSE_TAIL", "1")
+        c = h.cg_solve(b, **kw)
+        assert a[1:4:2] == c[1:4:2] and np.max(np.abs(a[0] - c[0])) <= 1e-12 * np.max(np.abs(a[0]))
+    out1, dot1 = h.lapl_dot(b)
+    assert np.array_equal(out1, out0) and abs(dot1 - dot0) <= 1e-13 * abs(dot0)
+    h.close()

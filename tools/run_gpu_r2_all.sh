@@ -8,13 +8,15 @@ timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2_test
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/r2_smoke.log; cat gpurun_out/r2_smoke.log
 timeout 300 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; cat gpurun_out/r2_bench_default.json
 # 2. the gated tests (peer boards on one GPU, TMA line-major tridsol, host batch, swizzled y/z tiles)
-for K in peer_boards line_major_tma host_batch yz_rot lineop_tma any_chunk; do
+for K in peer_boards line_major_tma host_batch yz_rot lineop_tma any_chunk fused_reduction; do
   PBX_TEST_ROUND2=1 timeout 300 python -m pytest tests -m gpu -k $K -q -x 2>&1 | tail -4 > gpurun_out/r2_gated_$K.log
   cat gpurun_out/r2_gated_$K.log
 done
 # 3. the opt-in variants in the bench line: swizzled y/z tiles, batched end-to-end path
 PBX_YZ_ROT=1 PBX_BENCH_E2E_BATCH=1 timeout 300 python bench.py --no-cpu > gpurun_out/r2_bench_rot.json 2> gpurun_out/r2_bench_rot.err
 cat gpurun_out/r2_bench_rot.json
+PBX_FUSE_TAIL=1 timeout 300 python bench.py --no-cpu --no-e2e > gpurun_out/r2_bench_fuse.json 2> gpurun_out/r2_bench_fuse.err
+cat gpurun_out/r2_bench_fuse.json
 # 4. tridsol batches, both layouts, generic against TMA tiles
 timeout 200 python tools/prof_ops.py 256 > gpurun_out/r2_prof_ops.log 2>&1; tail -8 gpurun_out/r2_prof_ops.log
 # 5. counters of the y / z passes (planes, bank conflicts, with and without PBX_YZ_ROT)
