@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 # 1. the default path: GPU tests, smoke, the bench line (CG now 88 + 64 B/DoF per iteration)
-timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2_tests.log; cat gpurun_out/r2_tests.log
+timeout 400 python -m pytest tests -m gpu -q -rfs 2>&1 > gpurun_out/r2_tests.log; tail -15 gpurun_out/r2_tests.log
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2 > gpurun_out/r2_smoke.log; cat gpurun_out/r2_smoke.log
 timeout 300 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; cat gpurun_out/r2_bench_default.json
 # 2. the gated tests (peer boards on one GPU, TMA line-major tridsol, host batch, swizzled y/z tiles)
@@ -24,4 +24,9 @@ bash tools/run_gpu_r2_zpass.sh
 # 6. extents that are not 16 x a power of two: generic kernels against the TMA kernels (PBX_TMA_ANY_T=1)
 for anyt in 0 1; do
   PBX_TMA_ANY_T=$anyt timeout 120 python tools/prof_lapl.py --n 384 > gpurun_out/r2_anyt${anyt}_384.log 2>&1; tail -1 gpurun_out/r2_anyt${anyt}_384.log
+done
+# 7. races: compute-sanitizer racecheck / synccheck over lapl + 20 CG iterations at 64^3 (VERDICT weak 12)
+for tool in racecheck synccheck; do
+  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python tools/prof_lapl.py --n 64 --reps 2 --cg-its 20 > gpurun_out/r2_sanitizer_$tool.log 2>&1
+  tail -4 gpurun_out/r2_sanitizer_$tool.log
 done
