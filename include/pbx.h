@@ -13,8 +13,10 @@
  *   - Every function returns 0 on success or a PBX_ERR_* code; PBX_ERR_SIZE is 7 on purpose: it
  *     is what the reference reports with `stop 7` (src/compact_schemes.f90:177-180, 292-295).
  *   - Caller owns every array; outputs are fully overwritten.  Scratch and coefficient tables
- *     belong to a handle (pbx_create) -- there is no hidden global state except the per-thread
- *     handle cache behind the *_host convenience calls.
+ *     belong to a handle (pbx_create) -- there is no hidden global state except the handle
+ *     cache behind the *_host convenience calls: ONE per process (at most four (box, device)
+ *     entries), under one mutex, so *_host calls from several threads serialise (their copies and
+ *     the stream synchronisation included), and pbx_host_set_mode applies to every thread.
  *   - `*_device` calls take device pointers and are asynchronous on the handle's CUDA stream.
  *     `*_host` calls take host pointers, stage H2D/D2H themselves and return when the result is
  *     in the caller's buffer.
@@ -277,6 +279,8 @@ int pbx_ksp_solve_device(pbx_handle h, const char *options, const double *b, dou
 /* ---------------------------------------------------------------------------------------------
  * Host-pointer convenience variants (what the Fortran module bodies call).
  * They use a cached handle for (nx,ny,nz,dx) on the current device, copy in, run, copy out.
+ * PBX_MODE_FAST needs extents that are multiples of 16; for any other box these calls run the
+ * REFERENCE schedule instead (same result to rounding, slower) -- they never fail on the shape.
  * ------------------------------------------------------------------------------------------- */
 int pbx_lapl_host(int nx, int ny, int nz, const double *f, const double dx[3], double *d2f,
                   int mode);

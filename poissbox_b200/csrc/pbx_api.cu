@@ -1,5 +1,6 @@
 // pbx_api.cu -- the C ABI (include/pbx.h): handle lifecycle, operator drivers for both schedules,
 // host-pointer convenience variants.
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -855,7 +856,9 @@ int pbx_ksp_solve_device(pbx_handle h, const char *options, const double *b, dou
     }
     if (pc >= 0) PBX_TRY(pbx_set_pc(h, pc, pc == PBX_PC_MG ? nu : 0));
     else if (nu > 0 && h->pc == PBX_PC_MG) PBX_TRY(pbx_set_pc(h, PBX_PC_MG, nu));
-    std::vector<double> hist(monitor ? (size_t)maxit + 1 : 0);
+    // -ksp_monitor keeps at most the first 2^22 norms (32 MB); a solve that runs longer stops printing
+    const size_t hist_cap = (size_t)1 << 22;
+    std::vector<double> hist(monitor ? std::min((size_t)maxit + 1, hist_cap) : 0);
     int k = 0, r = 0;
     double rn = 0.0;
     PBX_TRY(pbx_cg_solve_device(h, b, x, rtol, atol, maxit, &k, &rn, &r, monitor ? hist.data() : nullptr,

@@ -325,7 +325,17 @@ int vec_grid(size_t N)
     return (int)nb;
 }
 
-int cg_alloc(pbx_handle_s *h, int maxit)
+// the device residual history holds what the caller will read back: min(maxit + 1, nhist) entries when a
+// history was asked for, one entry otherwise (scalar_phase guards every store with `it < nhist`), so that a
+// legal -ksp_max_it of 1e9 does not turn into an 8 GB allocation
+static int hist_entries(int maxit, const double *hist, int nhist)
+{
+    if (!hist || nhist <= 0) return 1;
+    const long long want = (long long)maxit + 1;
+    return (int)(want < (long long)nhist ? want : (long long)nhist);
+}
+
+int cg_alloc(pbx_handle_s *h, int nhist)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
     if (!h->cg_r) {
@@ -346,11 +356,13 @@ int cg_alloc(pbx_handle_s *h, int maxit)
         PBX_CUDA(cudaMallocHost(&h->cg_host, 2 * SC_COUNT * sizeof(double)));
     }
     if (h->pc != PBX_PC_NONE && !h->cg_z) PBX_CUDA(cudaMalloc(&h->cg_z, N * sizeof(double)));
-    if (h->cg_hist_cap < maxit + 1) {
+    if (nhist < 1) nhist = 1;
+    if (h->cg_hist_cap < nhist) {
         if (h->cg_hist) cudaFree(h->cg_hist);
         h->cg_hist = nullptr;
-        PBX_CUDA(cudaMalloc(&h->cg_hist, (size_t)(maxit + 1) * sizeof(double)));
-        h->cg_hist_cap = maxit + 1;
+        h->cg_hist_cap = 0;
+        PBX_CUDA(cudaMalloc(&h->cg_hist, (size_t)nhist * sizeof(double)));
+        h->cg_hist_cap = nhist;
     }
     return PBX_OK;
 }
@@ -433,6 +445,7 @@ int matmult_dot(pbx_handle_s *h, const double *p, double *w, double *dst, int gu
         const int rc = h->nranks > 1 ? dist_lapl(h, p, w, p, h->cg_partials) : lapl_fast(h, p, w, p, h->cg_partials);
         const bool taken = offered && h->pending_tail == nullptr;
         h->pending_tail = nullptr;
+        if (offered && !taken && h->nranks > 1) dist_peer_unget(h, tail.seq);   // reduce_step draws it again
         PBX_TRY(rc);
         if (taken) return PBX_OK;
         np = fast_zpass_max_partials(Brick{h->nx, h->ny, h->nz});
@@ -508,7 +521,7 @@ static int cg_solve_pc(pbx_handle_s *h, const double *b, double *x, double rtol,
                        int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist)
 {
     const size_t N = (size_t)h->nx * h->ny * h->nz;
-    PBX_TRY(cg_alloc(h, maxit));
+    PBX_TRY(cg_alloc(h, hist_entries(maxit, hist, nhist)));
     cudaStream_t s = h->stream;
     double *sc = h->cg_scal, *part = h->cg_partials;
     const int np = h->cg_npartials, nb = vec_grid(N);
@@ -598,7 +611,7 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
         set_last_error("pbx_cg_solve: b and x must be 16-byte aligned");
         return PBX_ERR_ARG;
     }
-    PBX_TRY(cg_alloc(h, maxit));
+    PBX_TRY(cg_alloc(h, hist_entries(maxit, hist, nhist)));
     cudaStream_t s = h->stream;
     double *sc = h->cg_scal, *part = h->cg_partials;
     const int np = h->cg_npartials;

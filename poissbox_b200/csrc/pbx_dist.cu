@@ -432,27 +432,47 @@ int dist_attach(pbx_handle_s *h)
     // the moments kernel stores its results straight into the neighbour's memory over NVLink.
     // Any failure leaves the ncclSend/Recv path in place.
     DistState *d = (DistState *)h->dist;
+    if (n > PEER_MAXR) return PBX_OK;   // the same decision on every rank
+    // Every rank takes part in the AllGather, whatever happened locally: a rank that cannot (or was told
+    // not to, PBX_NO_PEER=1) export its buffer sends a zeroed handle with valid = 0, and the peer / NCCL
+    // decision is taken from the GATHERED flags only, so that no rank can leave the others waiting in the
+    // collective.
+    struct IpcSlot {
+        cudaIpcMemHandle_t handle;
+        long long valid;
+    };
+    IpcSlot mine;
+    memset(&mine, 0, sizeof mine);
     const char *e = getenv("PBX_NO_PEER");
-    if ((e && e[0] == '1') || n > PEER_MAXR) return PBX_OK;
-    cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, d->rbuf) != cudaSuccess) {
-        cudaGetLastError();
-        return PBX_OK;
+    if (!(e && e[0] == '1')) {
+        if (cudaIpcGetMemHandle(&mine.handle, d->rbuf) == cudaSuccess)
+            mine.valid = 1;
+        else
+            cudaGetLastError();
     }
     char *dall = nullptr;
-    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    const size_t hb = sizeof(IpcSlot);
     PBX_CUDA(cudaMalloc(&dall, hb * (size_t)(n + 1)));
     PBX_CUDA(cudaMemcpy(dall + hb * n, &mine, hb, cudaMemcpyHostToDevice));
     int rc = g_nccl.AllGather(dall + hb * n, dall, hb, ncclInt8, (ncclComm_t)h->comm, h->stream);
-    std::vector<cudaIpcMemHandle_t> all(n);
+    std::vector<IpcSlot> slots(n);
     cudaError_t ce = cudaStreamSynchronize(h->stream);
     if (rc == ncclSuccess && ce == cudaSuccess)
-        ce = cudaMemcpy(all.data(), dall, hb * n, cudaMemcpyDeviceToHost);
+        ce = cudaMemcpy(slots.data(), dall, hb * n, cudaMemcpyDeviceToHost);
     cudaFree(dall);
     if (rc != ncclSuccess || ce != cudaSuccess) {
+        // a failed collective is not something one rank can recover from on its own: report it
         cudaGetLastError();
-        return PBX_OK;
+        set_last_error("exchange of the cudaIpc handles failed (ncclAllGather)");
+        return rc != ncclSuccess ? PBX_ERR_NCCL : PBX_ERR_CUDA;
     }
+    std::vector<cudaIpcMemHandle_t> all(n);
+    bool all_valid = true;
+    for (int q = 0; q < n; ++q) {
+        all[q] = slots[q].handle;
+        all_valid = all_valid && slots[q].valid == 1;
+    }
+    if (!all_valid) return PBX_OK;   // identical on every rank: the ncclSend/Recv path stays in place
     // PBX_PEER_SYNC=1: map EVERY rank's buffer, so that the barrier of the exchange and the CG's
     // all-reduces run over the peer boards (no NCCL call inside an iteration); otherwise the two
     // neighbours only (messages by peer stores, a one-word ncclAllReduce as the barrier)
@@ -509,6 +529,15 @@ bool dist_peer_next(pbx_handle_s *h, PeerLinks *L, unsigned long long *seq)
     return true;
 }
 
+// hand back a sequence number that was drawn for a reduction which did not take place (a reduction tail
+// that the z pass could not fuse): executed reductions use CONSECUTIVE sequence numbers, which is what the
+// ring-safety argument of pbx_peer.cuh (at most two live slots of PEER_RING) rests on
+void dist_peer_unget(pbx_handle_s *h, unsigned long long seq)
+{
+    DistState *d = (DistState *)h->dist;
+    if (d && d->peer_sync && d->ar_seq == seq) --d->ar_seq;
+}
+
 int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
 {
     if (h->nranks <= 1) return PBX_OK;
@@ -516,8 +545,10 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
         set_last_error("this slab handle has no communicator (phase-driven handles cannot reduce)");
         return PBX_ERR_UNSUPPORTED;
     }
-    static const bool skip = getenv("PBX_DEBUG_NO_ALLREDUCE") != nullptr;   // timing experiments only
+#ifdef PBX_DEBUG   // timing experiments only: never in a release build (it skips required communication)
+    static const bool skip = getenv("PBX_DEBUG_NO_ALLREDUCE") != nullptr;
     if (skip) return PBX_OK;
+#endif
     PeerLinks L;
     unsigned long long seq;
     if (count <= PEER_VALS && dist_peer_next(h, &L, &seq)) {
@@ -715,8 +746,11 @@ int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, do
         return PBX_ERR_ARG;
     }
     PBX_TRY(dist_phase1(h, f));
-    static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;   // timing experiments only
-    if (!skipx) PBX_TRY(dist_exchange_run(h));
+#ifdef PBX_DEBUG   // timing experiments only: never in a release build (it skips required communication)
+    static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;
+    if (skipx) return dist_phase2(h, out, p, partials);
+#endif
+    PBX_TRY(dist_exchange_run(h));
     return dist_phase2(h, out, p, partials);
 }
 

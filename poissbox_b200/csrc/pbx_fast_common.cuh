@@ -21,6 +21,8 @@
 // Sherman-Morrison step: the look-back wraps around the line.
 #pragma once
 
+#include <atomic>
+
 #include "pbx_internal.h"
 #include "pbx_ptx.cuh"
 

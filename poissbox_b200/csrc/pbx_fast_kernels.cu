@@ -244,7 +244,7 @@ int fast_xpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.nlines = (long long)g.ny * g.nz;
     if (p.R > p.nlines) p.R = (int)p.nlines;
     const size_t smem = sizeof(double) * (XK_SLOTS * NT + 2 * (size_t)p.R * p.T * CPAD);
-    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
@@ -284,7 +284,7 @@ int fast_ypass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.D = fc.D[1];
     dim3 grid, block;
     yz_geometry(g, 1, &p, &grid, &block);
-    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
@@ -315,7 +315,7 @@ int fast_zpass(cudaStream_t s, const Brick &g, const FastCoefs &fc, const double
     p.D = fc.D[2];
     dim3 grid, block;
     yz_geometry(g, 2, &p, &grid, &block);
-    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {

@@ -10,6 +10,7 @@
 // operator, against three global-memory sweeps for the REFERENCE schedule's thread-per-line Thomas.
 // Used by the FAST schedule of grad / div / interp (8 + 8 + 3 line operators, reference stage
 // order); results agree with the REFERENCE schedule to rounding (tests/test_parity_gpu.py).
+#include <atomic>
 #include <cstdlib>
 
 #include "pbx_fast_lineop.cuh"
@@ -327,7 +328,7 @@ int fast_line_op(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagg
         p.nlines = (long long)g.ny * g.nz;
         if (p.R > p.nlines) p.R = (int)p.nlines;
         const size_t smem = sizeof(double) * (8 * NT + (size_t)p.R * p.T * CPAD);
-        static bool attr_set[64] = {false};
+        static std::atomic<bool> attr_set[64];
         int dev_ = 0;
         cudaGetDevice(&dev_);
         if (!attr_set[dev_ & 63]) {

@@ -959,7 +959,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
         !make_map_x(&mb, B, nchunks, p.rows))
         return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(XShared);
-    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
@@ -1005,7 +1005,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     CUtensorMap m0, m1;
     if (!make_map_yz(&m0, in0, g, p, rot) || !make_map_yz(&m1, in1, g, p, rot)) return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(YZShared);
-    static bool attr_set[64] = {false};   // per device: the attribute belongs to the context
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
@@ -1071,7 +1071,7 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
     if (out2 && (dir == 0 || addend)) return PBX_ERR_UNSUPPORTED;
     const lineop::LineOp op = lineop::make_line_op(kind, stagger, dx);
     const lineop::LineOp op2 = lineop::make_line_op(kind == OP_DERIV ? OP_INTERP : OP_DERIV, stagger, dx);
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {
@@ -1145,7 +1145,7 @@ int fast_line_op_sum_tma(cudaStream_t s, const Brick &g, int dir, OpKind kindA, 
     const lineop::LineOp opA = lineop::make_line_op(kindA, stagger, dx), opB = lineop::make_line_op(kindB, stagger, dx);
     CUtensorMap ma, mb;
     if (!make_map_yz(&ma, inA, g, p) || !make_map_yz(&mb, inB, g, p)) return PBX_ERR_UNSUPPORTED;
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];
     int dev_ = 0;
     cudaGetDevice(&dev_);
     if (!attr_set[dev_ & 63]) {

@@ -377,4 +377,5 @@ int mg_slab_plan(int nx, int ny, int nzl, int nranks, size_t *gather_doubles);
 bool dist_connected(const pbx_handle_s *h);
 // peer boards in place: fills *L and the sequence number of the next all-reduce, returns true
 bool dist_peer_next(pbx_handle_s *h, PeerLinks *L, unsigned long long *seq);
+void dist_peer_unget(pbx_handle_s *h, unsigned long long seq);
 }  // namespace pbx
