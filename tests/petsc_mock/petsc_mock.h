@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 typedef int PetscErrorCode;
 typedef int PetscInt;
@@ -24,11 +25,23 @@ typedef int KSPConvergedReason;
 #define PETSC_SUCCESS 0
 #define PETSC_ERR_LIB 76
 #define PETSC_ERR_SUP 56
+#define PETSC_ERR_ARG_WRONGSTATE 73
 #define PETSC_COMM_SELF 1
 #define PETSC_COMM_WORLD 2
 #define PETSC_DETERMINE (-1)
 #define VECCUDA "cuda"
-typedef enum { MATOP_MULT = 3 } MatOperation;
+typedef enum { MATOP_MULT = 3, MATOP_DESTROY = 60 } MatOperation;
+
+/* PetscObject / PetscContainer: one composed object per Mat is all the glue needs */
+typedef struct _p_PetscContainer {
+    void *ptr;
+    PetscErrorCode (*destroy)(void *);
+    int refs;
+} *PetscContainer;
+typedef void *PetscObject;
+typedef struct _p_PetscDeviceContext {
+    cudaStream_t stream;
+} *PetscDeviceContext;
 
 typedef struct _p_Vec {
     double *dev;
@@ -40,6 +53,9 @@ typedef struct _p_Mat {
     PetscErrorCode (*mult)(struct _p_Mat *, Vec, Vec);
     PetscInt m, n;
     VecType vtype;
+    PetscErrorCode (*destroy)(struct _p_Mat *);
+    char key[32];            /* the one composed object */
+    PetscContainer composed;
 } *Mat;
 typedef struct _p_DM {
     PetscInt M, N, P;             /* global extents */
@@ -94,8 +110,87 @@ static inline PetscErrorCode MatShellSetVecType(Mat A, VecType t)
 }
 static inline PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void))
 {
-    if (op != MATOP_MULT) return PETSC_ERR_SUP;
-    A->mult = (PetscErrorCode (*)(struct _p_Mat *, Vec, Vec))f;
+    if (op == MATOP_MULT)
+        A->mult = (PetscErrorCode (*)(struct _p_Mat *, Vec, Vec))f;
+    else if (op == MATOP_DESTROY)
+        A->destroy = (PetscErrorCode (*)(struct _p_Mat *))f;
+    else
+        return PETSC_ERR_SUP;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscFree_(void *p)
+{
+    free(p);
+    return PETSC_SUCCESS;
+}
+#define PetscFree(p) PetscFree_((void *)(p))
+static inline PetscErrorCode PetscContainerCreate(MPI_Comm c, PetscContainer *out)
+{
+    (void)c;
+    *out = (PetscContainer)calloc(1, sizeof(**out));
+    (*out)->refs = 1;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscContainerSetPointer(PetscContainer c, void *p)
+{
+    c->ptr = p;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscContainerGetPointer(PetscContainer c, void **p)
+{
+    *p = c->ptr;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscContainerSetUserDestroy(PetscContainer c, PetscErrorCode (*d)(void *))
+{
+    c->destroy = d;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscContainerDestroy(PetscContainer *c)
+{
+    if (*c && --(*c)->refs == 0) {
+        if ((*c)->destroy) (*c)->destroy((*c)->ptr);
+        free(*c);
+    }
+    *c = NULL;
+    return PETSC_SUCCESS;
+}
+/* only Mats are composed on in the glue */
+static inline PetscErrorCode PetscObjectCompose(PetscObject obj, const char *key, PetscObject what)
+{
+    Mat A = (Mat)obj;
+    PetscContainer c = (PetscContainer)what;
+    if (A->composed) PetscContainerDestroy(&A->composed);
+    snprintf(A->key, sizeof A->key, "%s", key);
+    A->composed = c;
+    if (c) ++c->refs;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscObjectQuery(PetscObject obj, const char *key, PetscObject *what)
+{
+    Mat A = (Mat)obj;
+    *what = (A->composed && strcmp(A->key, key) == 0) ? (PetscObject)A->composed : NULL;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode MatDestroy(Mat *A)
+{
+    if (!*A) return PETSC_SUCCESS;
+    if ((*A)->destroy) (*A)->destroy(*A);
+    if ((*A)->composed) PetscContainerDestroy(&(*A)->composed);
+    free(*A);
+    *A = NULL;
+    return PETSC_SUCCESS;
+}
+/* the stream PETSc's vector kernels run on; the test switches it to a non-blocking stream */
+static struct _p_PetscDeviceContext petsc_mock_dctx = {0};
+static inline PetscErrorCode PetscDeviceContextGetCurrentContext(PetscDeviceContext *d)
+{
+    *d = &petsc_mock_dctx;
+    return PETSC_SUCCESS;
+}
+static inline PetscErrorCode PetscDeviceContextGetStreamHandle(PetscDeviceContext d, void **handle)
+{
+    *handle = &d->stream;
     return PETSC_SUCCESS;
 }
 static inline PetscErrorCode MatMult(Mat A, Vec x, Vec y) { return A->mult(A, x, y); }
