@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline legs only (no 256^3 / S3 solves, no CG through the host call)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check that precedes the timed region")
     ap.add_argument("--cg-rtol", type=float, default=1e-8)
     ap.add_argument("--cg-maxit", type=int, default=20000)
     return ap.parse_args()
@@ -184,6 +186,130 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
+def oracle_parity(pbx, torch, dist, world, rank, local, comm):
+    """Before any timing: the (distributed) operators of THIS run against the CPU oracle on a small brick,
+    64 x 64 x (64 * N) S2 field (every rank owns a 64-plane slab: the thin-slab wrap cases of
+    src/compact_schemes.f90:356-370 across every rank boundary), plus the CG iteration count on b = A x_true
+    (S3, rtol 1e-5, the north star's +-1).  The oracle is the checker here, never the thing measured."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+
+    nx = ny = 64
+    nzl = 64
+    nz = nzl * world
+    dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
+    rng = np.random.default_rng(1234)
+    f = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz)))
+    v = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz, 3)))
+    sl = slice(rank * nzl, (rank + 1) * nzl)
+    orc.set_threads(max(1, (os.cpu_count() or 1) // world))
+    try:
+        want = {"lapl": orc.lapl(f, dx), "grad": orc.grad(f, dx), "div": orc.div(v, dx), "interp": orc.interp(f, -1)}
+        its_o = None
+        if rank == 0:
+            _, its_o, _, why_o, _ = orc.cg_solve(want["lapl"], dx, rtol=1e-5)
+    finally:
+        orc.set_threads(1)
+    h = pbx.Handle(nx, ny, nzl, dx, device=local, comm=comm)
+    h.use_current_stream()
+    dev = torch.device("cuda", local)
+    t = lambda a: pbx.fortran_to_torch(a, device=dev)   # f(i,j,k[,c]) -> (c,) k, j, i: the Fortran memory layout
+    fl = t(f[:, :, sl])
+    got = {"lapl": pbx.torch_to_fortran(h.lapl(fl)), "grad": pbx.torch_to_fortran(h.grad(fl)),
+           "div": pbx.torch_to_fortran(h.div(t(v[:, :, sl, :]))), "interp": pbx.torch_to_fortran(h.interp(fl, -1))}
+    errs = {}
+    for k in want:
+        w = want[k][:, :, sl]
+        errs[k] = float(np.max(np.abs(got[k] - w)) / np.max(np.abs(want[k])))
+    x, its, _, why, _ = h.cg_solve(t(want["lapl"][:, :, sl]), rtol=1e-5)
+    torch.cuda.synchronize()
+    h.close()
+    e = torch.tensor([errs[k] for k in ("lapl", "grad", "div", "interp")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    e = e.tolist()
+    out = {"grid": [nx, ny, nz], "slab_planes": nzl, "field": "S2 U[-1,1], numpy default_rng(1234)",
+           "against": "CPU oracle (C restatement of src/compact_schemes.f90), same inputs, outside the timed region",
+           "max_abs_err_over_max_ref": {"lapl": e[0], "grad": e[1], "div": e[2], "interp": e[3]},
+           "n": nx * ny * nz, "tolerance": 1e-12,
+           "cg_its": {"ours": int(its), "oracle": its_o, "rtol": 1e-5, "rhs": "S3: b = A x_true"}, "ok": None}
+    if rank == 0:
+        out["ok"] = bool(max(e) <= 1e-12 and why == 2 and why_o == 2 and abs(its - its_o) <= 1)
+    return out
+
+
+def cg_case(pbx, torch, n, kind, rtol, local, maxit=20000):
+    """one device-resident CG solve on an n^3 box, one GPU: S3 (x_true ~ U[-1,1], L = 1, b = A x_true: the demo's
+    recipe, src/example.f90:70-72,180-183) or S4 (manufactured smooth u = exp(sin x + sin y + sin z), L = 2 pi)"""
+    import math
+
+    dev = torch.device("cuda", local)
+    if kind == "S3":
+        hh = 1.0 / n
+        g = torch.Generator(device=dev).manual_seed(1234)
+        u = torch.rand((n, n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    else:
+        hh = 2 * math.pi / n
+        c = (torch.arange(n, dtype=torch.float64, device=dev) + 0.5) * hh
+        u = torch.exp(torch.sin(c)[None, None, :] + torch.sin(c)[None, :, None] + torch.sin(c)[:, None, None]).contiguous()
+    h = pbx.Handle(n, n, n, (hh,) * 3, device=local)
+    h.use_current_stream()
+    b = h.lapl(u)
+    del u
+    x = h.empty()
+    h.cg_solve(b, x, rtol=rtol, maxit=3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, its, rnorm, reason, hist = h.cg_solve(b, x, rtol=rtol, maxit=maxit)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    r = h.lapl(x) - b
+    true_rel = float((r.norm() / b.norm()).item())
+    h.close()
+    return {"grid": [n] * 3, "rhs": kind, "rtol": rtol, "its": int(its), "reason": int(reason), "time_s": dt,
+            "ms_per_it": dt / max(1, its) * 1e3, "true_residual_rel": true_rel,
+            "frac_of_hbm_peak": 152.0 * float(n) ** 3 * its / dt / 1e9 / hbm_peak()[0]}
+
+
+def cg_vs_oracle(pbx, n, rtol):
+    """the north star's iteration criterion on the full-spectrum problem: the library's CG (through the host-pointer
+    call) and the oracle's CG (all host threads) on the SAME b = A x_true, S3, n^3"""
+    import ctypes
+
+    import numpy as np
+
+    from poissbox_b200 import _lib
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+
+    rng = np.random.default_rng(1234)
+    xt = np.asfortranarray(rng.uniform(-1, 1, (n, n, n)))
+    dx = (1.0 / n,) * 3
+    orc.set_threads(os.cpu_count() or 1)
+    try:
+        b = orc.lapl(xt, dx)
+        t0 = time.perf_counter()
+        xo, ito, _, whyo, _ = orc.cg_solve(b, dx, rtol=rtol)
+        t_orc = time.perf_counter() - t0
+    finally:
+        orc.set_threads(1)
+    x = np.zeros_like(b, order="F")
+    its, why, rn = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    t0 = time.perf_counter()
+    pbx.check(pbx.LIB.pbx_cg_solve_host(n, n, n, _lib._d3(*dx), b.ctypes.data_as(_lib._dp), x.ctypes.data_as(_lib._dp),
+                                        rtol, 1e-50, 10000, pbx.MODE_FAST, ctypes.byref(its), ctypes.byref(rn),
+                                        ctypes.byref(why), None, 0))
+    t_gpu = time.perf_counter() - t0
+    return {"grid": [n] * 3, "rhs": "S3: b = A x_true from the oracle", "rtol": rtol, "its_ours": its.value,
+            "its_oracle": int(ito), "reasons": [why.value, int(whyo)],
+            "x_rel_diff": float(np.linalg.norm(x - xo) / np.linalg.norm(xo)),
+            "oracle_cg_s": t_orc, "ours_host_call_s": t_gpu, "oracle_threads": os.cpu_count() or 1,
+            "within_one": bool(abs(its.value - int(ito)) <= 1)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -215,6 +341,13 @@ def run_ours(args):
         c = ctypes.c_void_p()
         pbx.check(pbx.LIB.pbx_comm_init_rank(raw, world, rank, local, ctypes.byref(c)))
         comm = c.value
+
+    parity = None
+    if not args.no_parity:
+        parity = oracle_parity(pbx, torch, dist, world, rank, local, comm)
+        if rank == 0 and not parity["ok"]:
+            print(json.dumps({"error": "oracle parity failed before the timed region", "parity": parity}), flush=True)
+            raise SystemExit(1)
 
     n = args.n
     if n % world or (n // world) % 16:
@@ -299,19 +432,20 @@ def run_ours(args):
 
     # end to end through the host-pointer C-ABI call (what the Fortran shim calls), pinned buffers
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         import ctypes
 
         fh = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
         oh = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
         fh.copy_(f)
         torch.cuda.synchronize()
+        ksteps = max(3, min(args.steps, 10))
+    if not args.no_e2e and world == 1:
         d3 = _lib._d3(*dx)
         pf = ctypes.cast(fh.data_ptr(), _lib._dp)
         po = ctypes.cast(oh.data_ptr(), _lib._dp)
         for _ in range(2):
             pbx.check(pbx.LIB.pbx_lapl_host(n, n, nzl, pf, d3, po, pbx.MODE_FAST))
-        ksteps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(ksteps):
             pbx.check(pbx.LIB.pbx_lapl_host(n, n, nzl, pf, d3, po, pbx.MODE_FAST))
@@ -319,27 +453,51 @@ def run_ours(args):
         assert torch.equal(oh.to(dev), out), "host-pointer path disagrees with the device path"
         e2e = {"value": ndof_total / dt / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": int(8 * ndof_total),
                "d2h_bytes_per_step": int(8 * ndof_total), "ms_per_step": dt * 1e3, "steps": ksteps,
-               "api": "pbx_lapl_host (pinned host buffers)"}
-        # several fields per call, double-buffered (copy-in / compute / copy-out of consecutive fields
-        # overlap): opt-in, PBX_BENCH_E2E_BATCH=1 -- written after round 1's GPU budget was spent; reported
-        # beside the single-call number, which stays the headline until the batch path has been measured
-        if os.environ.get("PBX_BENCH_E2E_BATCH") == "1":
-            try:
-                oh2 = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
-                pin = (ctypes.c_void_p * ksteps)(*([fh.data_ptr()] * ksteps))
-                pout = (ctypes.c_void_p * ksteps)(*[(oh if k % 2 == 0 else oh2).data_ptr() for k in range(ksteps)])
-                pbx.check(pbx.LIB.pbx_lapl_host_batch(n, n, nzl, 2, pin, d3, pout, pbx.MODE_FAST))
-                t0 = time.perf_counter()
-                pbx.check(pbx.LIB.pbx_lapl_host_batch(n, n, nzl, ksteps, pin, d3, pout, pbx.MODE_FAST))
-                dtb = (time.perf_counter() - t0) / ksteps
-                same = torch.equal(oh.to(dev), out) and torch.equal(oh2.to(dev), out)
-                e2e["batch"] = {"value": ndof_total / dtb / 1e9, "ms_per_field": dtb * 1e3, "fields": ksteps,
-                                "api": "pbx_lapl_host_batch (double-buffered, pinned host buffers)",
-                                "matches_device_path": bool(same)}
-                del oh2
-            except Exception as exc:
-                e2e["batch"] = {"error": repr(exc)}
+               "api": "pbx_lapl_host (pinned host buffers)",
+               "floor": "one apply needs the whole field before the first output plane exists (z lines), so copy-in and "
+                        "copy-out of ONE field cannot overlap: 2 x 1 GiB over the host link + 2 ms of compute"}
+        # several fields per call, double-buffered (copy-in / compute / copy-out of consecutive fields overlap:
+        # the host link runs in both directions at once)
+        try:
+            oh2 = torch.empty((nzl, n, n), dtype=torch.float64).pin_memory()
+            pin = (ctypes.c_void_p * ksteps)(*([fh.data_ptr()] * ksteps))
+            pout = (ctypes.c_void_p * ksteps)(*[(oh if k % 2 == 0 else oh2).data_ptr() for k in range(ksteps)])
+            pbx.check(pbx.LIB.pbx_lapl_host_batch(n, n, nzl, 2, pin, d3, pout, pbx.MODE_FAST))
+            t0 = time.perf_counter()
+            pbx.check(pbx.LIB.pbx_lapl_host_batch(n, n, nzl, ksteps, pin, d3, pout, pbx.MODE_FAST))
+            dtb = (time.perf_counter() - t0) / ksteps
+            same = torch.equal(oh.to(dev), out) and torch.equal(oh2.to(dev), out)
+            e2e["batch"] = {"value": ndof_total / dtb / 1e9, "ms_per_field": dtb * 1e3, "fields": ksteps,
+                            "api": "pbx_lapl_host_batch (double-buffered, pinned host buffers)",
+                            "matches_device_path": bool(same)}
+            del oh2
+        except Exception as exc:
+            e2e["batch"] = {"error": repr(exc)}
         pbx.LIB.pbx_host_cache_clear()
+    elif not args.no_e2e:
+        # N > 1: every rank stages ITS slab from pinned host memory, applies the distributed operator and reads
+        # its slab of the result back (the host-pointer C calls carry no communicator; this is the same
+        # sequence through the handle API).  Wall clock between barriers, max over ranks.
+        def one():
+            f.copy_(fh, non_blocking=True)
+            h.lapl(f, out)
+            oh.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            one()
+        dt = (time.perf_counter() - t0) / ksteps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+        e2e = {"value": ndof_total / dt / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": int(8 * ndof_total),
+               "d2h_bytes_per_step": int(8 * ndof_total), "ms_per_step": dt * 1e3, "steps": ksteps,
+               "api": "per rank: pinned slab -> device, pbx_lapl_device over the communicator, slab -> pinned host"}
+    if not args.no_e2e:
         del fh, oh
 
     # CG time-to-rtol on a manufactured smooth solution (S4), device resident
@@ -420,9 +578,51 @@ def run_ours(args):
         h2.close()
         del b, x
 
+    # BASELINE configs[2] (256^3 on one GPU) and the full-spectrum problem at scale; end-to-end time-to-solution
+    # through the host-pointer call (b in once, x out once)
+    if cg is not None and world == 1 and not args.no_cg and not args.quick:
+        cg["other_configs"] = []
+        for nn, kind in ((256, "S4"), (256, "S3"), (128, "S3")):
+            try:
+                cg["other_configs"].append(cg_case(pbx, torch, nn, kind, args.cg_rtol, local))
+            except Exception as exc:
+                cg["other_configs"].append({"grid": [nn] * 3, "rhs": kind, "error": repr(exc)})
+        if e2e is not None:
+            try:
+                import ctypes
+
+                hh = 2 * np.pi / n
+                c = (torch.arange(n, dtype=torch.float64, device=dev) + 0.5) * hh
+                u = torch.exp(torch.sin(c)[None, None, :] + torch.sin(c)[None, :, None] + torch.sin(c)[:, None, None]).contiguous()
+                hb = pbx.Handle(n, n, n, (hh,) * 3, device=local)
+                bh = hb.lapl(u).cpu().pin_memory()
+                hb.close()
+                del u, hb
+                xh = torch.empty_like(bh).pin_memory()
+                its_, why_, rn_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+                t0 = time.perf_counter()
+                pbx.check(pbx.LIB.pbx_cg_solve_host(n, n, n, _lib._d3(hh, hh, hh), ctypes.cast(bh.data_ptr(), _lib._dp),
+                                                    ctypes.cast(xh.data_ptr(), _lib._dp), args.cg_rtol, 1e-50, args.cg_maxit,
+                                                    pbx.MODE_FAST, ctypes.byref(its_), ctypes.byref(rn_), ctypes.byref(why_),
+                                                    None, 0))
+                dth = time.perf_counter() - t0
+                e2e["cg"] = {"api": "pbx_cg_solve_host (b in once, x out once, pinned host buffers; includes workspace allocation)",
+                             "time_s": dth, "its": its_.value, "reason": why_.value,
+                             "h2d_bytes": int(8 * ndof_total), "d2h_bytes": int(8 * ndof_total),
+                             "device_resident_time_s": cg["time_s"]}
+                pbx.LIB.pbx_host_cache_clear()
+                del bh, xh
+            except Exception as exc:
+                e2e["cg"] = {"error": repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_block()
+        if not args.quick:
+            try:
+                cpu["cg_iteration_parity"] = cg_vs_oracle(pbx, 128, 1e-5)
+            except Exception as exc:
+                cpu["cg_iteration_parity"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
@@ -437,7 +637,7 @@ def run_ours(args):
                                      "peer boards (flag barrier + all-reduce in the CG's reduction kernel, no NCCL per iteration)"
                                      if os.environ.get("PBX_PEER_SYNC") == "1" else
                                      "peer stores of the boundary messages + ncclAllReduce (barrier, CG scalars)")},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "parity": parity, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "cg": cg,
         }
         print(json.dumps(line), flush=True)

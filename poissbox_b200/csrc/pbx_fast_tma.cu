@@ -107,14 +107,14 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
     }
 }
 
-// ROT (opt-in, PBX_YZ_ROT=1): the tiles are fetched with the 128-byte swizzle and threads with an odd
+// ROT (default; PBX_YZ_ROT=0 turns it off; 512^3: y pass 0.807 -> 0.786 ms, z pass 0.645 -> 0.626 ms): the tiles are fetched with the 128-byte swizzle and threads with an odd
 // chunk index read the two halves of their chunk's second index bit in swapped order.  Without it the
 // four chunk rows a warp reads per instruction lie 16 rows apart, i.e. in the same banks (the profile of
 // round 1: 37-43 % of the passes' shared-memory wavefronts are bank conflicts); with it the two rows of
 // a half-warp differ in bit 2 of (row & 7), the swizzle sends them to different halves of the 128-byte
 // bank line, and 16 register swaps put the values back in order.  Whole lines in one CTA only (no
 // segments, no slab), and for the z pass one line per tile row (G == 1: lines of 512 points).
-// ANYT (opt-in, PBX_TMA_ANY_T=1): line lengths whose chunk count does not divide 32 -- the lines that
+// ANYT (default for such lengths; PBX_TMA_ANY_T=0 falls back to the generic kernels): line lengths whose chunk count does not divide 32 -- the lines that
 // fit into a compute group leave threads without a chunk (`dead`); a compile-time switch, so that the
 // measured kernels do not carry the test.
 // FUSE (opt-in, PBX_FUSE_TAIL=1; z pass with the fused dot): the CTA that finishes last reduces the
@@ -337,7 +337,7 @@ __device__ __forceinline__ void solve_shfl(const CompositeCoef &c, double (&v)[L
 // WIDE = true:  T = 64, 128 or 256 chunks (lines of 1024 - 4096 points): a line spans several warps
 //               of the CTA, and the chunk states and solved halos go through shared memory
 //               (xpass_body, the arithmetic of the generic x kernel) -- same TMA data movement.
-// ANYT (opt-in, PBX_TMA_ANY_T=1; with WIDE): any number of chunks per line up to 256 -- a tile holds
+// ANYT (default for such lengths; with WIDE): any number of chunks per line up to 256 -- a tile holds
 //               the whole lines that fit into 256 chunks, the remaining threads idle.
 template <bool WIDE, bool ANYT = false>
 __global__ void __launch_bounds__(NT, 2)
@@ -874,11 +874,11 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     p->n = n;
     p->seg = seg_geometry(n / LC);
     p->T = p->seg.T;
-    // T must divide 32 -- or, opt-in (PBX_TMA_ANY_T=1, unmeasured), the lines that fit leave some
-    // threads of the group without a chunk (any multiple of 16 up to 512 points)
+    // T divides 32 -- or the lines that fit leave some threads of the group without a chunk (any multiple
+    // of 16 up to 512 points; 384^3: 51.6 instead of 37.4 GDoF/s on the generic kernels; PBX_TMA_ANY_T=0
+    // turns it off)
     if (NT % (XW * p->T)) {
-        const char *e = getenv("PBX_TMA_ANY_T");
-        if (!(e && e[0] == '1') || p->seg.nseg > 1) return false;
+        if (!env_switch("PBX_TMA_ANY_T", true) || p->seg.nseg > 1) return false;
     }
     p->G = NT / (XW * p->T);
     p->ng = dir == 1 ? g.nz : g.ny;
@@ -939,11 +939,8 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
 {
     const int T = g.nx / LC;
     if (g.nx % LC || T > NT || T < 1 || !encode_fn()) return PBX_ERR_UNSUPPORTED;
-    const bool anyT = (T & (T - 1)) != 0;   // opt-in: chunk counts that are not a power of two
-    if (anyT) {
-        const char *e = getenv("PBX_TMA_ANY_T");
-        if (!(e && e[0] == '1')) return PBX_ERR_UNSUPPORTED;
-    }
+    const bool anyT = (T & (T - 1)) != 0;   // chunk counts that are not a power of two
+    if (anyT && !env_switch("PBX_TMA_ANY_T", true)) return PBX_ERR_UNSUPPORTED;
     const bool wide = T > 32;
     const size_t nchunks = g.N() / LC;
     if (nchunks > 0x7fffffffull) return PBX_ERR_UNSUPPORTED;
@@ -999,8 +996,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     p.M = fc.M;
     p.D = fc.D[dir];
     const bool segd = p.seg.nseg > 1;
-    const char *re = getenv("PBX_YZ_ROT");
-    const bool rot = re && re[0] == '1' && !segd && !zo.open && !anyT && (dir == 1 || p.G == 1) && p.T >= 2 &&
+    const bool rot = env_switch("PBX_YZ_ROT", true) && !segd && !zo.open && !anyT && (dir == 1 || p.G == 1) && p.T >= 2 &&
                      g.nx % XWT == 0;
     CUtensorMap m0, m1;
     if (!make_map_yz(&m0, in0, g, p, rot) || !make_map_yz(&m1, in1, g, p, rot)) return PBX_ERR_UNSUPPORTED;
@@ -1066,8 +1062,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
 int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
                      const double *in, double *out, const double *addend, long long *launches, double *out2)
 {
-    const char *en = getenv("PBX_LINEOP_TMA");
-    if (!(en && en[0] == '1') || !encode_fn()) return PBX_ERR_UNSUPPORTED;
+    if (!env_switch("PBX_LINEOP_TMA", true) || !encode_fn()) return PBX_ERR_UNSUPPORTED;
     if (out2 && (dir == 0 || addend)) return PBX_ERR_UNSUPPORTED;
     const lineop::LineOp op = lineop::make_line_op(kind, stagger, dx);
     const lineop::LineOp op2 = lineop::make_line_op(kind == OP_DERIV ? OP_INTERP : OP_DERIV, stagger, dx);
@@ -1134,8 +1129,7 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
 int fast_line_op_sum_tma(cudaStream_t s, const Brick &g, int dir, OpKind kindA, OpKind kindB, int stagger,
                          double dx, const double *inA, const double *inB, double *out, long long *launches)
 {
-    const char *en = getenv("PBX_LINEOP_TMA");
-    if (!(en && en[0] == '1') || !encode_fn() || dir == 0) return PBX_ERR_UNSUPPORTED;
+    if (!env_switch("PBX_LINEOP_TMA", true) || !encode_fn() || dir == 0) return PBX_ERR_UNSUPPORTED;
     if (out == inA || out == inB ||
         ((reinterpret_cast<uintptr_t>(inA) | reinterpret_cast<uintptr_t>(inB) | reinterpret_cast<uintptr_t>(out)) & 15))
         return PBX_ERR_UNSUPPORTED;

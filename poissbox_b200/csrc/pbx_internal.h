@@ -1,6 +1,7 @@
 // pbx_internal.h -- shared declarations of the poissbox-b200 CUDA library (not part of the ABI).
 #pragma once
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -17,6 +18,15 @@ namespace pbx {
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
+// A/B switches of kernel variants (read per call): `NAME=0` / `NAME=1` override the built-in default.
+// They exist so that a variant can be timed against the one it replaced; results are the same bits.
+inline bool env_switch(const char *name, bool dflt)
+{
+    const char *e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    return e[0] != '0';
+}
+
 void set_last_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 

@@ -371,6 +371,7 @@ def test_emu_yz_rot_bit_identical(shape, monkeypatch):
     f = field(shape, 21)
     lib = emu_lib.load()
     h = handle(shape, dx)
+    monkeypatch.setenv("PBX_YZ_ROT", "0")     # the unswizzled tile reads the (now default) rotated ones replaced
     ref, dref = h.lapl_dot(f)
     monkeypatch.setenv("PBX_YZ_ROT", "1")
     maps0 = lib.pbx_emu_tensor_maps3_swizzled_total()
@@ -444,6 +445,7 @@ def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
     vec = np.asfortranarray(np.random.default_rng(32).uniform(-1, 1, shape + (3,)))
     lib = emu_lib.load()
     h = handle(shape, dx)
+    monkeypatch.setenv("PBX_LINEOP_TMA", "0")  # the generic line-operator kernels
     want = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
     monkeypatch.setenv("PBX_LINEOP_TMA", "1")
     maps0 = lib.pbx_emu_tensor_maps_total()

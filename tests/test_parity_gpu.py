@@ -141,9 +141,6 @@ def test_tridsol_line_major_tma(n, nl, pad, monkeypatch):
             assert np.array_equal(got["0"][0], got["1"][0]) and np.array_equal(got["0"][1], got["1"][1])
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="pbx_lapl_host_batch was written after the round's GPU budget was spent: CPU-harness "
-                           "tested only (test_emu_lapl_host_batch); PBX_TEST_ROUND2=1 runs it on the GPU")
 def test_lapl_host_batch():
     rng = np.random.default_rng(8)
     n, dx = (64, 32, 48), (0.1, 0.2, 0.3)
@@ -154,9 +151,6 @@ def test_lapl_host_batch():
             assert np.array_equal(o, cs.lapl(f, dx, mode=mode))
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="PBX_YZ_ROT (swizzled y/z tiles) was written after the round's GPU budget was spent: "
-                           "CPU-harness tested only (test_emu_yz_rot_bit_identical)")
 @pytest.mark.parametrize("shape", [(512, 512, 512), (64, 256, 512), (32, 128, 64)])
 def test_yz_rot_bit_identical(shape, monkeypatch):
     import torch
@@ -165,6 +159,7 @@ def test_yz_rot_bit_identical(shape, monkeypatch):
     g = torch.Generator(device="cuda").manual_seed(3)
     f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     h = pbx.Handle(nx, ny, nz, (1.0 / nx, 1.0 / ny, 1.0 / nz))
+    monkeypatch.setenv("PBX_YZ_ROT", "0")     # the unswizzled tile reads the default replaced
     ref, dref = h.lapl_dot(f)
     monkeypatch.setenv("PBX_YZ_ROT", "1")
     out, dot = h.lapl_dot(f)
@@ -173,9 +168,6 @@ def test_yz_rot_bit_identical(shape, monkeypatch):
     h.close()
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="PBX_LINEOP_TMA (TMA-pipelined line operators) was written after the round's GPU budget "
-                           "was spent: CPU-harness tested only (test_emu_lineop_tma_bit_identical)")
 @pytest.mark.parametrize("shape", [(256, 256, 256), (64, 512, 32), (48, 64, 512)])
 def test_lineop_tma_bit_identical(shape, monkeypatch):
     import torch
@@ -185,6 +177,7 @@ def test_lineop_tma_bit_identical(shape, monkeypatch):
     f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     v = torch.rand((3, nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     h = pbx.Handle(nx, ny, nz, (0.7 / nx, 0.7 / ny, 0.7 / nz))
+    monkeypatch.setenv("PBX_LINEOP_TMA", "0")  # the generic line-operator kernels the default replaced
     want = [h.grad(f), h.div(v), h.interp(f), h.interp(f, +1)]
     monkeypatch.setenv("PBX_LINEOP_TMA", "1")
     got = [h.grad(f), h.div(v), h.interp(f), h.interp(f, +1)]
@@ -194,9 +187,6 @@ def test_lineop_tma_bit_identical(shape, monkeypatch):
     h.close()
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="PBX_TMA_ANY_T (TMA kernels for chunk counts that are not a power of two) was written "
-                           "after the round's GPU budget was spent: CPU-harness tested only")
 @pytest.mark.parametrize("shape", [(384, 384, 384), (48, 320, 192), (1600, 96, 48)])
 def test_tma_any_chunk_count(shape, monkeypatch):
     import torch
@@ -205,6 +195,7 @@ def test_tma_any_chunk_count(shape, monkeypatch):
     g = torch.Generator(device="cuda").manual_seed(6)
     f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     h = pbx.Handle(nx, ny, nz, (0.9 / nx, 0.9 / ny, 0.9 / nz))
+    monkeypatch.setenv("PBX_TMA_ANY_T", "0")
     ref, dref = h.lapl_dot(f)           # generic kernels for these extents
     monkeypatch.setenv("PBX_TMA_ANY_T", "1")
     out, dot = h.lapl_dot(f)

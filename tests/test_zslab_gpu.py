@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import poissbox_b200 as pbx
+from poissbox_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
