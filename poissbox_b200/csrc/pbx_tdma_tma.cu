@@ -18,9 +18,8 @@
 //   * lines that do not fill the last block or the last CTA need no special code: the tensor maps
 //     carry the true extents, out-of-range loads are zero-filled and out-of-range stores dropped.
 //
-// Needs es == 1, an even line stride, 16-byte aligned bases and n >= 2; everything else stays on
-// the generic kernels.  Opt-in (PBX_TDMA_TMA=1): written after the round's GPU budget was spent,
-// CPU-harness tested (bit-exact); it becomes the default once it has been measured on the B200.
+// Needs es == 1, an even n >= 2, an even line stride and 16-byte aligned bases; everything else stays
+// on the generic kernels.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -392,16 +391,16 @@ periodic_lm_kernel(int n, long long nl, long long ls, const __grid_constant__ Lm
     if (lane == 0) tma_wait_all0();
 }
 
-bool lm_enabled()
-{
-    const char *e = getenv("PBX_TDMA_TMA");
-    return e && e[0] == '1';
-}
+// default since its first B200 run (line-major batches: tdma 20 -> 51 Gpt/s, tdma_periodic 10.5 -> 20.7 Gpt/s
+// for 512-point lines); PBX_TDMA_TMA=0 selects the generic thread-per-line kernels
+bool lm_enabled() { return env_switch("PBX_TDMA_TMA", true); }
 
 bool lm_shape_ok(int n, long long nl, long long es, long long ls, const void *p0, const void *p1,
                  const void *p2, const void *p3)
 {
-    if (!lm_enabled() || es != 1 || n < 2 || nl < 1 || ls < n || (ls & 1)) return false;
+    // n even: TMA moves 16-byte units, so the last unit of an odd line would reach one element past the
+    // line (measured on the B200: the store wrote the zero fill into the caller's padding element)
+    if (!lm_enabled() || es != 1 || n < 2 || (n & 1) || nl < 1 || ls < n || (ls & 1)) return false;
     if (nl > 0x7fffffffLL - LM_LINES) return false;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) |
                          reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(p3);

@@ -328,7 +328,8 @@ def test_emu_tridsol_line_major_tma(n, nl, pad, monkeypatch):
         maps0 = lib.pbx_emu_tensor_maps_total()
         emu_lib.check(lib, lib.pbx_tdma_batch_device(n, nl, 1, ls, emu_lib.ptr(a), emu_lib.ptr(b), emu_lib.ptr(c),
                                                      emu_lib.ptr(d), None))
-        assert lib.pbx_emu_tensor_maps_total() - maps0 == 7, "the TMA kernels did not run"
+        # odd n stays on the generic kernels: TMA moves 16-byte units and would touch the element behind the line
+        assert lib.pbx_emu_tensor_maps_total() - maps0 == (7 if n % 2 == 0 else 0), "the TMA kernels did not run"
         assert np.array_equal(d[:n].T, want_t) and np.array_equal(b[:n].T, want_b)
         assert np.all(d[n:] == 73.29) and np.all(b[n:] == 73.29), "padding between the lines touched"
         a, b, c, d = (padded(i) for i in (0, 1, 2, 4))

@@ -106,11 +106,8 @@ def test_tridsol_batch_strided():
         assert np.array_equal(got, want)
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_TDMA_TMA") != "1" and os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="line-major TMA tridsol kernels (pbx_tdma_tma.cu) were written after the round's GPU "
-                           "budget was spent: CPU-harness tested only (test_emu_tridsol_line_major_tma); set "
-                           "PBX_TEST_TDMA_TMA=1 to run them on the GPU")
-@pytest.mark.parametrize("n,nl,pad", [(5, 37, 1), (64, 300, 0), (203, 70, 1), (512, 4096, 0), (2048, 33, 2)])
+@pytest.mark.parametrize("n,nl,pad", [(5, 37, 1), (6, 37, 2), (64, 300, 0), (203, 70, 1), (204, 70, 0), (512, 4096, 0),
+                                      (2048, 33, 2)])
 def test_tridsol_line_major_tma(n, nl, pad, monkeypatch):
     """PBX_TDMA_TMA=1: contiguous lines as swizzled TMA tiles, same bits as the generic kernels and the oracle"""
     import ctypes
@@ -132,7 +129,7 @@ def test_tridsol_line_major_tma(n, nl, pad, monkeypatch):
         for fn, want in ((pbx.LIB.pbx_tdma_batch_device, want_t), (pbx.LIB.pbx_tdma_periodic_batch_device, want_p)):
             got = {}
             for tma in ("0", "1"):
-                monkeypatch.setenv("PBX_TDMA_TMA", tma)
+                monkeypatch.setenv("PBX_TDMA_TMA", tma)   # "0": the generic thread-per-line kernels
                 arrs = [torch.from_numpy(v.copy()).cuda() for v in host]
                 pbx.check(fn(n, nl, 1, ls, *[ctypes.c_void_p(t.data_ptr()) for t in arrs], None))
                 torch.cuda.synchronize()
