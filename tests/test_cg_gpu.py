@@ -250,9 +250,6 @@ def test_ksp_options(capfd):
     h.close()
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="PBX_FUSE_TAIL (reduction tails inside the z pass and the residual update) was written "
-                           "after the round's GPU budget was spent: CPU-harness tested only")
 def test_fused_reduction_tails(monkeypatch):
     import torch
 

@@ -107,10 +107,6 @@ def test_slab_needs_64_to_512_planes():
         assert e.value.code == 4
 
 
-@pytest.mark.skipif(os.environ.get("PBX_TEST_PEER_BOARDS") != "1" and os.environ.get("PBX_TEST_ROUND2") != "1",
-                    reason="peer boards (device-side barrier and all-reduce) were written in a round whose GPU "
-                           "budget was already spent: CPU-harness tested only (tests/test_zslab_cpu.py::"
-                           "test_peer_boards); set PBX_TEST_PEER_BOARDS=1 to run them on the GPU")
 @pytest.mark.parametrize("P", [2, 4])
 def test_peer_boards_one_gpu(P):
     """P slab handles of one process on one GPU, each on its own stream and host thread, linked by
