@@ -1181,6 +1181,7 @@ int pbx_host_cache_clear(void)
         pbx_destroy(e.h);
     }
     g_host.clear();
+    tdma_trim_workspace();
     return PBX_OK;
 }
 

@@ -120,6 +120,7 @@ int tdma_fwd_batch(cudaStream_t s, int n, long long nl, long long es, long long 
                    double *b, const double *c, double *d);
 int tdma_bwd_batch(cudaStream_t s, int n, long long nl, long long es, long long ls, const double *b,
                    const double *c, double *d);
+void tdma_trim_workspace();
 int tdma_periodic_batch(cudaStream_t s, int n, long long nl, long long es, long long ls,
                         const double *a, const double *b, const double *c, double *d);
 

@@ -50,6 +50,33 @@ static inline cudaError_t cudaMallocAsync(T **p, size_t bytes, cudaStream_t)
 {
     return cudaMalloc(p, bytes);
 }
+// memory pools: one opaque pool, allocations as cudaMalloc
+typedef struct pbx_emu_pool *cudaMemPool_t;
+enum cudaMemAllocationType { cudaMemAllocationTypePinned = 1 };
+enum cudaMemAllocationHandleType { cudaMemHandleTypeNone = 0 };
+enum cudaMemLocationType { cudaMemLocationTypeDevice = 1 };
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+struct cudaMemLocation {
+    cudaMemLocationType type;
+    int id;
+};
+struct cudaMemPoolProps {
+    cudaMemAllocationType allocType;
+    cudaMemAllocationHandleType handleTypes;
+    cudaMemLocation location;
+};
+static inline cudaError_t cudaMemPoolCreate(cudaMemPool_t *pool, const cudaMemPoolProps *)
+{
+    *pool = (cudaMemPool_t)(uintptr_t)1;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void *) { return cudaSuccess; }
+static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaSuccess; }
+template <class T>
+static inline cudaError_t cudaMallocFromPoolAsync(T **p, size_t bytes, cudaMemPool_t, cudaStream_t)
+{
+    return cudaMalloc(p, bytes);
+}
 template <class T>
 static inline cudaError_t cudaMallocHost(T **p, size_t bytes)
 {
