@@ -362,6 +362,108 @@ __device__ __forceinline__ void slab_load_messages(const ZOpen &zo, bool first, 
     }
 }
 
+// the same behind the flag of the fused exchange: peers have just stored these numbers into my memory
+// over NVLink, so they are read at the L2 (the point of coherence), never through L1
+__device__ __forceinline__ void slab_load_messages_cg(const ZOpen &zo, bool first, bool last,
+                                                      long long line, double (&lo9)[DIST_MSG],
+                                                      double (&up9)[DIST_MSG])
+{
+#pragma unroll
+    for (int a = 0; a < DIST_MSG; ++a) {
+        lo9[a] = first ? __ldcg(zo.from_lo + a * zo.nlines + line) : 0.0;
+        up9[a] = last ? __ldcg(zo.from_up + a * zo.nlines + line) : 0.0;
+    }
+}
+
+// Fused exchange, first leg: the two messages of a z line (the eighteen numbers ZOpen lists, what k_boundary
+// computes in a sweep of its own) from the chunks the z pass holds in registers anyway.  c = raw input of
+// the interpolation composite, ed = raw input of the derivative composite with its in-slab halos (zeros
+// beyond the slab).  Every thread sums its chunk -- bottom moments sum r^k u_k, sum k r^k u_k by Horner, top
+// recursion from zero state (fwd_local) -- chunk 0 of a line assembles the message for the lower rank from
+// the nlook bottom chunks, chunk T-1 the one for the upper rank by the look-back over the chunks below it.
+// The windows are the look-back's (r^(16 nlook) < 1e-17) instead of k_boundary's 48 / 24 planes.
+// slots 0..7; ends with a barrier, so the slots are free again on return
+template <class Bar>
+__device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const CompositeCoef &D,
+                                                   const Xchg &xc, const double (&c)[LC],
+                                                   const double (&ed)[LC + 6], bool live, long long line,
+                                                   long long nlines, double *__restrict__ dst_dn,
+                                                   double *__restrict__ dst_up, Bar bar)
+{
+    const bool first = xc.t == 0, last = xc.t == xc.T - 1;
+    double s[LC];
+    stencil<true>(D, ed, s);
+    double p = 0.0, q = 0.0, pD = 0.0, qD = 0.0;
+#pragma unroll
+    for (int k = LC - 1; k >= 0; --k) {
+        q = M.r * (q + p);
+        p = fma(M.r, p, c[k]);
+        qD = D.r * (qD + pD);
+        pD = fma(D.r, pD, s[k]);
+    }
+    double v0[LC], ey, ez, eyD, ezD;
+#pragma unroll
+    for (int k = 0; k < LC; ++k) v0[k] = c[k];
+    fwd_local(M.r, v0, ey, ez);
+    fwd_local(D.r, s, eyD, ezD);       // s now holds the zero-inflow solved values of the derivative input
+    xc.put(0, p);
+    xc.put(1, q);
+    xc.put(2, pD);
+    xc.put(3, qD);
+    xc.put(4, ey);
+    xc.put(5, ez);
+    xc.put(6, eyD);
+    xc.put(7, ezD);
+    bar();
+    if (first && live) {
+        double P = p, Q = q, PD = pD, QD = qD;
+#pragma unroll
+        for (int m = 1; m < MAXLOOK; ++m) {
+            const int qm = xc.nb(m);
+            if (m < M.nlook) {
+                const double pm = xc.get(0, qm), qmv = xc.get(1, qm);
+                P = fma(M.look[m], pm, P);
+                Q = fma(M.look[m], fma((double)(LC * m), pm, qmv), Q);
+            }
+            if (m < D.nlook) {
+                const double pm = xc.get(2, qm), qmv = xc.get(3, qm);
+                PD = fma(D.look[m], pm, PD);
+                QD = fma(D.look[m], fma((double)(LC * m), pm, qmv), QD);
+            }
+        }
+        dst_dn[0 * nlines + line] = P;
+        dst_dn[1 * nlines + line] = Q;
+        dst_dn[2 * nlines + line] = PD;
+        dst_dn[3 * nlines + line] = QD;
+        dst_dn[4 * nlines + line] = ed[3];
+        dst_dn[5 * nlines + line] = ed[4];
+        dst_dn[6 * nlines + line] = ed[5];
+        dst_dn[7 * nlines + line] = c[0];
+        dst_dn[8 * nlines + line] = c[1];
+    }
+    if (last && live) {
+        double Y, Z, YD, ZD;
+        lookback(M, xc, 4, 5, -1, Y, Z);       // open line: chunks below the slab read as zero state
+        lookback(D, xc, 6, 7, -1, YD, ZD);
+        const double yt = fma(M.pw[LC - 1], Y, ey);
+        const double z0 = fma(M.pw[LC - 1], fma((double)LC, Y, Z), v0[LC - 1]);
+        const double z1 = fma(M.pw[LC - 2], fma((double)(LC - 1), Y, Z), v0[LC - 2]);
+        const double z2 = fma(M.pw[LC - 3], fma((double)(LC - 2), Y, Z), v0[LC - 3]);
+        const double yDt = fma(D.pw[LC - 1], YD, eyD);
+        const double zDt = fma(D.pw[LC - 1], fma((double)LC, YD, ZD), s[LC - 1]);
+        dst_up[0 * nlines + line] = yt;
+        dst_up[1 * nlines + line] = z0;
+        dst_up[2 * nlines + line] = z1;
+        dst_up[3 * nlines + line] = z2;
+        dst_up[4 * nlines + line] = yDt;
+        dst_up[5 * nlines + line] = zDt;
+        dst_up[6 * nlines + line] = ed[LC + 2];
+        dst_up[7 * nlines + line] = ed[LC + 1];
+        dst_up[8 * nlines + line] = ed[LC];
+    }
+    bar();
+}
+
 template <class Bar>
 __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
                                                 const ZOpen &zo, const Xchg &xc,

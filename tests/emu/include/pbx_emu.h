@@ -88,6 +88,11 @@ static inline T __ldg(const T *p)
     return *p;
 }
 template <class T>
+static inline T __ldcg(const T *p)
+{
+    return *(const volatile T *)p;
+}
+template <class T>
 static inline T __shfl_sync(unsigned, T v, int src, int = 32)
 {
     return pbx_emu::shfl_any(v, src);

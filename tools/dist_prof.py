@@ -10,7 +10,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-nzl = n // world
+NZ = int(sys.argv[2]) if len(sys.argv) > 2 else n      # optional: n x n x NZ brick (thin slabs on few GPUs)
+nzl = NZ // world
 idbuf = torch.zeros(128, dtype=torch.uint8, device=dev)
 if rank == 0:
     raw = (ctypes.c_ubyte * 128)(); check(LIB.pbx_comm_unique_id(raw))
@@ -30,10 +31,19 @@ def tm(fn, reps=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3, (time.perf_counter() - t0) / reps * 1e6
 res = {}
-res["phase1"] = tm(lambda: h.slab_phase1(f))
-res["exchange"] = tm(lambda: check(LIB.pbx_slab_exchange(h._h)))
-res["phase2"] = tm(lambda: h.slab_phase2(out))
 res["lapl"] = tm(lambda: h.lapl(f, out))
+w1 = pbx.Handle(n, n, nzl, (1.0 / n,) * 3, device=local); w1.use_current_stream()
+res["lapl, periodic brick of the same size (no exchange)"] = tm(lambda: w1.lapl(f, out))
+w1.close()
+if os.environ.get("PBX_PROF_PHASES", "1") == "1":   # the unfused pieces (they leave the epoch counters in step)
+    res["phase1 (x, y, boundary sweep)"] = tm(lambda: h.slab_phase1(f))
+    res["exchange"] = tm(lambda: check(LIB.pbx_slab_exchange(h._h)))
+    res["phase2 (slab z pass)"] = tm(lambda: h.slab_phase2(out))
+bq = h.lapl(f)
+def cgits():
+    h.cg_solve(bq, rtol=1e-30, maxit=50)
+t_dev, t_host = tm(cgits, reps=4)
+res["CG iteration (50-iteration solves)"] = (t_dev / 50, t_host / 50)
 res["allreduce_pbx(2 doubles)"] = tm(lambda: check(LIB.pbx_allreduce_sum(h._h, ctypes.c_void_p(sc.data_ptr()), 2)))
 res["allreduce_torch(2 doubles)"] = tm(lambda: dist.all_reduce(sc[:2]))
 big = torch.zeros(2 * 1024 * 1024, dtype=torch.float64, device=dev)
