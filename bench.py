@@ -413,17 +413,24 @@ def run_ours(args):
                    "achieved_GBs": ALG_BYTES_PASS[k] * ndof_total / (pm[i] * 1e-3) / 1e9}
                for i, k in enumerate(names)}
         dom = max(names, key=lambda k: per[k]["ms"])
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
-        if os.path.exists(tpath):
+        # DRAM bytes per launch and the kernel's name from the newest dated `ncu --set full` summary under
+        # profiles/ (r<round>_ncu_full_<n>.json, written from the .ncu-rep of that round's capture)
+        traffic, kname, tsrc = None, {"x": "x_tma_kernel", "y": "yz_tma_kernel (y pass)", "z": "yz_tma_kernel (z pass)"}[dom], None
+        import glob
+        import re
+
+        caps = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_{n}.json")),
+                      key=lambda q: int(re.search(r"r(\d+)_ncu", os.path.basename(q)).group(1)))
+        if caps:
             try:
-                traffic = json.load(open(tpath)).get(f"{dom}pass_{n}")
+                cap = json.load(open(caps[-1]))
+                for kk in cap["kernels"]:
+                    if kk["pass"] == dom:
+                        traffic, kname, tsrc = kk["dram_bytes_per_launch"], kk["kernel"], os.path.basename(caps[-1])
             except Exception:
                 traffic = None
-        kname = {"x": "x_tma_kernel<false> (x pass)", "y": "yz_tma_kernel<false,false,false> (y pass)",
-                 "z": "yz_tma_kernel<true,false,false> (z pass)"}[dom]
         roof = {"bound": "hbm", "kernel": kname, "achieved": per[dom]["achieved_GBs"],
-                "peak": peak, "unit": "GB/s", "frac": per[dom]["achieved_GBs"] / peak, "traffic": traffic,
+                "peak": peak, "unit": "GB/s", "frac": per[dom]["achieved_GBs"] / peak, "traffic": traffic, "traffic_source": tsrc,
                 "peak_source": peak_src, "passes": per,
                 "matmult": {"alg_bytes_per_dof": ALG_BYTES_MATMULT,
                             "achieved_GBs": ALG_BYTES_MATMULT * value,
