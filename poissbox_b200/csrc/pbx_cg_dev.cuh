@@ -161,7 +161,7 @@ __device__ __forceinline__ void scalar_phase(double *__restrict__ sc, int phase,
 }
 
 
-// The reduction tail (RedTail, pbx_internal.h; opt-in PBX_FUSE_TAIL=1).  Called by ALL NTHREADS threads
+// The reduction tail (RedTail, pbx_internal.h; PBX_FUSE_TAIL=0 turns it off).  Called by ALL NTHREADS threads
 // of EVERY CTA at the end of a kernel that has written its per-CTA partial sums: the CTA that draws the
 // last ticket sums the partials in a fixed shape, all-reduces them over the peer boards (several
 // ranks), stores them into the scalar block and runs the scalar step of the loop -- what k_reduce (+
@@ -181,8 +181,11 @@ __device__ __forceinline__ void red_tail(const RedTail &t)
     __threadfence();
     if (!(t.guarded && t.sc[SC_STATUS] != 0.0)) {  // the same verdict on every rank
         for (int a = 0; a < t.narr; ++a) {
+            // the association of k_reduce (VT threads; the other warps add exact zeros), so that a solve carries
+            // the same bits whether the sums are taken here or in a launch of their own
             double s = 0.0;
-            for (int i = threadIdx.x; i < t.cnt; i += NTHREADS) s += t.part[a * t.stride + i];
+            if (threadIdx.x < VT)
+                for (int i = threadIdx.x; i < t.cnt; i += VT) s += t.part[a * t.stride + i];
             s = block_sum_n<NTHREADS>(s, sh);
             if (threadIdx.x == 0) mine[a] = s;
             __syncthreads();

@@ -375,6 +375,20 @@ __device__ __forceinline__ void slab_load_messages_cg(const ZOpen &zo, bool firs
     }
 }
 
+// ... and from the tile-major layout of the fused exchange: the nine numbers of the `lpg` lines of a
+// (tile, compute group) are contiguous, component by component, so that the sender's stores over NVLink are
+// whole 128-byte lines (base = first double of this (tile, group), li = my line among the group's)
+__device__ __forceinline__ void slab_load_messages_tile(const ZOpen &zo, bool first, bool last, long long base,
+                                                        int lpg, int li, double (&lo9)[DIST_MSG],
+                                                        double (&up9)[DIST_MSG])
+{
+#pragma unroll
+    for (int a = 0; a < DIST_MSG; ++a) {
+        lo9[a] = first ? __ldcg(zo.from_lo + base + a * lpg + li) : 0.0;
+        up9[a] = last ? __ldcg(zo.from_up + base + a * lpg + li) : 0.0;
+    }
+}
+
 // Fused exchange, first leg: the two messages of a z line (the eighteen numbers ZOpen lists, what k_boundary
 // computes in a sweep of its own) from the chunks the z pass holds in registers anyway.  c = raw input of
 // the interpolation composite, ed = raw input of the derivative composite with its in-slab halos (zeros
@@ -382,14 +396,19 @@ __device__ __forceinline__ void slab_load_messages_cg(const ZOpen &zo, bool firs
 // recursion from zero state (fwd_local) -- chunk 0 of a line assembles the message for the lower rank from
 // the nlook bottom chunks, chunk T-1 the one for the upper rank by the look-back over the chunks below it.
 // The windows are the look-back's (r^(16 nlook) < 1e-17) instead of k_boundary's 48 / 24 planes.
-// slots 0..7; ends with a barrier, so the slots are free again on return
+// The numbers are staged in shared memory ([direction][component][line of the group], slots 8..) and leave as
+// contiguous runs written by the whole compute group: 64-byte pieces from a quarter of the lanes ran the
+// NVLink stores at a fraction of their rate (first B200 run: z pass 104 -> 476 us).
+// slots 0..7 and the staging area; ends with a barrier, so all of them are free again on return
+constexpr int ZMSG_STAGE_SLOT = 8;
 template <class Bar>
 __device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const CompositeCoef &D,
                                                    const Xchg &xc, const double (&c)[LC],
-                                                   const double (&ed)[LC + 6], bool live, long long line,
-                                                   long long nlines, double *__restrict__ dst_dn,
+                                                   const double (&ed)[LC + 6], int lpg, int li, long long base,
+                                                   double *__restrict__ dst_dn,
                                                    double *__restrict__ dst_up, Bar bar)
 {
+    double *stage = xc.sm + ZMSG_STAGE_SLOT * NT;      // 2 x DIST_MSG x lpg doubles (lpg <= 64)
     const bool first = xc.t == 0, last = xc.t == xc.T - 1;
     double s[LC];
     stencil<true>(D, ed, s);
@@ -415,7 +434,7 @@ __device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const
     xc.put(6, eyD);
     xc.put(7, ezD);
     bar();
-    if (first && live) {
+    if (first) {
         double P = p, Q = q, PD = pD, QD = qD;
 #pragma unroll
         for (int m = 1; m < MAXLOOK; ++m) {
@@ -431,17 +450,17 @@ __device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const
                 QD = fma(D.look[m], fma((double)(LC * m), pm, qmv), QD);
             }
         }
-        dst_dn[0 * nlines + line] = P;
-        dst_dn[1 * nlines + line] = Q;
-        dst_dn[2 * nlines + line] = PD;
-        dst_dn[3 * nlines + line] = QD;
-        dst_dn[4 * nlines + line] = ed[3];
-        dst_dn[5 * nlines + line] = ed[4];
-        dst_dn[6 * nlines + line] = ed[5];
-        dst_dn[7 * nlines + line] = c[0];
-        dst_dn[8 * nlines + line] = c[1];
+        stage[0 * lpg + li] = P;
+        stage[1 * lpg + li] = Q;
+        stage[2 * lpg + li] = PD;
+        stage[3 * lpg + li] = QD;
+        stage[4 * lpg + li] = ed[3];
+        stage[5 * lpg + li] = ed[4];
+        stage[6 * lpg + li] = ed[5];
+        stage[7 * lpg + li] = c[0];
+        stage[8 * lpg + li] = c[1];
     }
-    if (last && live) {
+    if (last) {
         double Y, Z, YD, ZD;
         lookback(M, xc, 4, 5, -1, Y, Z);       // open line: chunks below the slab read as zero state
         lookback(D, xc, 6, 7, -1, YD, ZD);
@@ -451,15 +470,24 @@ __device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const
         const double z2 = fma(M.pw[LC - 3], fma((double)(LC - 2), Y, Z), v0[LC - 3]);
         const double yDt = fma(D.pw[LC - 1], YD, eyD);
         const double zDt = fma(D.pw[LC - 1], fma((double)LC, YD, ZD), s[LC - 1]);
-        dst_up[0 * nlines + line] = yt;
-        dst_up[1 * nlines + line] = z0;
-        dst_up[2 * nlines + line] = z1;
-        dst_up[3 * nlines + line] = z2;
-        dst_up[4 * nlines + line] = yDt;
-        dst_up[5 * nlines + line] = zDt;
-        dst_up[6 * nlines + line] = ed[LC + 2];
-        dst_up[7 * nlines + line] = ed[LC + 1];
-        dst_up[8 * nlines + line] = ed[LC];
+        double *su = stage + DIST_MSG * lpg;
+        su[0 * lpg + li] = yt;
+        su[1 * lpg + li] = z0;
+        su[2 * lpg + li] = z1;
+        su[3 * lpg + li] = z2;
+        su[4 * lpg + li] = yDt;
+        su[5 * lpg + li] = zDt;
+        su[6 * lpg + li] = ed[LC + 2];
+        su[7 * lpg + li] = ed[LC + 1];
+        su[8 * lpg + li] = ed[LC];
+    }
+    bar();
+    const int per = DIST_MSG * lpg;
+    for (int i = xc.q; i < 2 * per; i += NT) {
+        if (i < per)
+            dst_dn[base + i] = stage[i];
+        else
+            dst_up[base + i - per] = stage[i];
     }
     bar();
 }

@@ -353,7 +353,9 @@ z_slab_fused_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen
         const int g = gt * p.G + tz;
         const bool live = (x < p.nx) && (g < p.ng);
         const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
-        const long long line = live ? (long long)x + (long long)p.nx * g : 0;
+        (void)live;   // fast_zslab_fused_ok: the brick is whole tiles, every thread owns a line
+        const int lpg = NT / p.T, li = tz * XW + tx;                         // lines of a (tile, group); mine
+        const long long mbase = ((long long)tile * NGRP + grp) * DIST_MSG * lpg;   // its messages in either array
 
         mbar_wait(&S.full, (uint32_t)(k & 1));
         double a[LC], eb[LC + 6];
@@ -384,23 +386,26 @@ z_slab_fused_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen
         }
         const unsigned long long seq = zo.seq0 + (unsigned long long)i + 1ull;
         if (leg == 0) {
-            slab_make_messages(p.M, p.D, xc, a, eb, live, line, zo.nlines, zo.dst_dn, zo.dst_up, bar);
+            slab_make_messages(p.M, p.D, xc, a, eb, lpg, li, mbase, zo.dst_dn, zo.dst_up, bar);
             // the group's stores are ordered before the barrier that ended slab_make_messages; one thread
-            // publishes them (cumulative release at system scope)
-            if (lt == 0) {
+            // publishes them: ONE fence at system scope (cumulative), then the two flags.  Not thread 0 of the
+            // CTA: it is the TMA producer, and the fence waits for the stores to be acknowledged over NVLink.
+            if (lt == 32) {
                 fence_sys();
-                st_release_sys(zo.flag_dn + fidx, seq);
-                st_release_sys(zo.flag_up + fidx, seq);
+                st_relaxed_sys_u64(zo.flag_dn + fidx, seq);
+                st_relaxed_sys_u64(zo.flag_up + fidx, seq);
             }
         } else {
-            if (lt == 0) {
+            if (lt == 32) {
                 const long long t0 = spin_start();
-                while (ld_acquire_sys(zo.flag_lo + fidx) < seq || ld_acquire_sys(zo.flag_hi + fidx) < seq)
+                while (ld_relaxed_sys_u64(zo.flag_lo + fidx) < seq || ld_relaxed_sys_u64(zo.flag_hi + fidx) < seq)
                     spin_pause(t0);
+                (void)ld_acquire_sys(zo.flag_lo + fidx);   // one acquire per flag once both are up
+                (void)ld_acquire_sys(zo.flag_hi + fidx);
             }
             bar();
             double lo9[DIST_MSG], up9[DIST_MSG];
-            slab_load_messages_cg(zo, t == 0, t == p.T - 1, line, lo9, up9);
+            slab_load_messages_tile(zo, t == 0, t == p.T - 1, mbase, lpg, li, lo9, up9);
             double o[LC];
             zpass_body_slab(p.M, p.D, zo, xc, lo9, up9, a, eb, o, bar);
             double dot = 0.0;
@@ -1076,6 +1081,7 @@ bool fast_zslab_fused_ok(const Brick &g)
     YZT p;
     if (!encode_fn() || !yz_geometry_tma(g, 2, &p)) return false;
     if (p.seg.nseg > 1 || NT % (XW * p.T) != 0 || p.T > 8 || p.T < 4) return false;
+    if (g.nx % XWT || g.ny % p.G) return false;     // whole tiles: the messages travel tile by tile
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     return 2 * grid <= ZF_FLAGS;
