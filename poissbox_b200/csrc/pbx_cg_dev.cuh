@@ -181,11 +181,10 @@ __device__ __forceinline__ void red_tail(const RedTail &t)
     __threadfence();
     if (!(t.guarded && t.sc[SC_STATUS] != 0.0)) {  // the same verdict on every rank
         for (int a = 0; a < t.narr; ++a) {
-            // the association of k_reduce (VT threads; the other warps add exact zeros), so that a solve carries
-            // the same bits whether the sums are taken here or in a launch of their own
+            // (fixed shape, but not k_reduce's: NTHREADS strides instead of VT -- a sum taken here and one taken
+            // in a launch of its own agree to rounding, not bit for bit)
             double s = 0.0;
-            if (threadIdx.x < VT)
-                for (int i = threadIdx.x; i < t.cnt; i += VT) s += t.part[a * t.stride + i];
+            for (int i = threadIdx.x; i < t.cnt; i += NTHREADS) s += t.part[a * t.stride + i];
             s = block_sum_n<NTHREADS>(s, sh);
             if (threadIdx.x == 0) mine[a] = s;
             __syncthreads();

