@@ -108,7 +108,6 @@ struct DistState {
     double *peer_lo_recv_up[2] = {nullptr, nullptr};   // where my "down" message lands in the lower rank
     // peer boards of ALL ranks mapped: barrier and all-reduce without NCCL (PeerBoard, pbx_internal.h)
     bool peer_sync = false;
-    bool zfuse = false;           // thin slab, every rank's board mapped, same grid everywhere: z pass with fused exchange
     PeerLinks links;
     unsigned long long ar_seq = 0, bar_seq = 0;
     double *sync_word = nullptr;  // device scalar all-reduced as the inter-rank barrier
@@ -122,9 +121,7 @@ struct DistState {
     unsigned long long gather_seq = 0;
     size_t per() const { return (size_t)DIST_MSG * (size_t)nlines; }
     size_t board_offset() const { return (4 * per() * sizeof(double) + 127) & ~(size_t)127; }
-    // flags of the exchange fused into the z pass: [from_lo | from_up][ZF_FLAGS] words behind the board
-    size_t flags_offset() const { return (board_offset() + sizeof(PeerBoard) + 127) & ~(size_t)127; }
-    size_t gather_offset() const { return (flags_offset() + 2 * ZF_FLAGS * sizeof(unsigned long long) + 127) & ~(size_t)127; }
+    size_t gather_offset() const { return (board_offset() + sizeof(PeerBoard) + 127) & ~(size_t)127; }
     size_t recv_bytes() const { return gather_offset() + 2 * gather_cap * sizeof(double); }
     bool peer_stores() const { return peer_up_recv_lo[0] != nullptr; }
 };
@@ -357,7 +354,6 @@ static void close_peer_maps(DistState *d)
         d->peer_map[r] = nullptr;
     }
     d->peer_sync = false;
-    d->zfuse = false;
     for (int par = 0; par < 2; ++par) d->peer_up_recv_lo[par] = d->peer_lo_recv_up[par] = nullptr;
 }
 
@@ -373,9 +369,8 @@ static void set_recv_pointers(DistState *d)
 // bufs[r]: rank r's receive buffer as addressable from this device (bufs[rank] = my own).  With
 // the two neighbours given the boundary sweep stores its messages straight into their memory;
 // with ALL ranks given and `boards` set the peer boards take over the barrier and the all-reduce.
-static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs, bool boards, bool zfuse_allowed = false)
+static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs, bool boards)
 {
-    d->zfuse = false;
     const size_t per = d->per();
     for (int par = 0; par < 2; ++par) {
         d->peer_up_recv_lo[par] = (double *)bufs[d->upper] + (size_t)(2 * par) * per;
@@ -393,7 +388,6 @@ static void set_peer_pointers(pbx_handle_s *h, DistState *d, void *const *bufs, 
     L.lower = d->lower;
     L.upper = d->upper;
     d->peer_sync = true;
-    d->zfuse = zfuse_allowed && h->fast_ok && fast_zslab_fused_ok(Brick{h->nx, h->ny, h->nz});
 }
 
 int dist_setup(pbx_handle_s *h, int rank, int nranks)
@@ -464,16 +458,9 @@ int dist_attach(pbx_handle_s *h)
     struct IpcSlot {
         cudaIpcMemHandle_t handle;
         long long valid;
-        long long nz, sms;     // the fused exchange needs the same slab and the same grid on every rank
     };
     IpcSlot mine;
     memset(&mine, 0, sizeof mine);
-    {
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        mine.nz = h->nz;
-        mine.sms = sms;
-    }
     const char *e = getenv("PBX_NO_PEER");
     if (!(e && e[0] == '1')) {
         if (cudaIpcGetMemHandle(&mine.handle, d->rbuf) == cudaSuccess)
@@ -498,11 +485,10 @@ int dist_attach(pbx_handle_s *h)
         return rc != ncclSuccess ? PBX_ERR_NCCL : PBX_ERR_CUDA;
     }
     std::vector<cudaIpcMemHandle_t> all(n);
-    bool all_valid = true, same_shape = true;
+    bool all_valid = true;
     for (int q = 0; q < n; ++q) {
         all[q] = slots[q].handle;
         all_valid = all_valid && slots[q].valid == 1;
-        same_shape = same_shape && slots[q].nz == slots[0].nz && slots[q].sms == slots[0].sms;
     }
     if (!all_valid) return PBX_OK;   // identical on every rank: the ncclSend/Recv path stays in place
     // PBX_PEER_SYNC=1: map EVERY rank's buffer, so that the barrier of the exchange and the CG's
@@ -531,7 +517,7 @@ int dist_attach(pbx_handle_s *h)
     }
     void *bufs[PEER_MAXR] = {nullptr};
     for (int r = 0; r < n; ++r) bufs[r] = r == h->rank ? (void *)d->rbuf : d->peer_map[r];
-    set_peer_pointers(h, d, bufs, want_all, same_shape && env_switch("PBX_Z_FUSED", true));
+    set_peer_pointers(h, d, bufs, want_all);
     return PBX_OK;
 }
 
@@ -600,7 +586,7 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
 }
 
 // x and y sweeps (local) and the boundary sweep that produces the two neighbour messages
-int dist_phase1(pbx_handle_s *h, const double *f, bool boundary)
+int dist_phase1(pbx_handle_s *h, const double *f)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return PBX_ERR_ARG;
@@ -612,7 +598,6 @@ int dist_phase1(pbx_handle_s *h, const double *f, bool boundary)
     PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr));
     PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr));
     ++d->epoch;
-    if (!boundary) return PBX_OK;   // the z pass produces and exchanges the messages itself (dist_phase2, fused)
     const int par = (int)(d->epoch & 1);
     // with peer mappings the messages are stored straight into the neighbours' receive arrays
     double *dst_dn = d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn;
@@ -663,7 +648,7 @@ int dist_line_msgs(pbx_handle_s *h, int slot, const double **from_lo, const doub
 }
 
 // z sweep on the slab, the neighbours' messages of this parity in place
-int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials, bool fused)
+int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return PBX_ERR_ARG;
@@ -672,20 +657,6 @@ int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials,
     ZOpen zo = d->zo;
     zo.from_lo = d->recv_lo[par];
     zo.from_up = d->recv_up[par];
-    if (fused) {
-        if (!d->zfuse) return PBX_ERR_ARG;
-        auto flags = [&](int r) {
-            return (unsigned long long *)((char *)d->links.board[r] - d->board_offset() + d->flags_offset());
-        };
-        zo.fused = 1;
-        zo.dst_dn = d->peer_lo_recv_up[par];
-        zo.dst_up = d->peer_up_recv_lo[par];
-        zo.flag_dn = flags(d->lower) + ZF_FLAGS;     // I am the lower rank's upper neighbour
-        zo.flag_up = flags(d->upper);                // ... and the upper rank's lower neighbour
-        zo.flag_lo = flags(h->rank);
-        zo.flag_hi = flags(h->rank) + ZF_FLAGS;
-        zo.seq0 = d->epoch * ZF_SEQ_STRIDE;
-    }
     return fast_pass(h, 2, S[0], S[1], out, nullptr, p, partials, &zo);
 }
 
@@ -793,11 +764,7 @@ int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, do
         set_last_error("FAST schedule needs 16-byte aligned fields");
         return PBX_ERR_ARG;
     }
-    DistState *dd = (DistState *)h->dist;
-    // thin slabs with every board mapped: boundary sweep, barrier and z pass as ONE kernel
-    const bool fz = dd->zfuse && h->use_tma && h->use_tma_yz;
-    PBX_TRY(dist_phase1(h, f, !fz));
-    if (fz) return dist_phase2(h, out, p, partials, true);
+    PBX_TRY(dist_phase1(h, f));
 #ifdef PBX_DEBUG   // timing experiments only: never in a release build (it skips required communication)
     static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;
     if (skipx) return dist_phase2(h, out, p, partials);
@@ -955,9 +922,7 @@ int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n)
         d->rbuf_owned = false;
         set_recv_pointers(d);
     }
-    // the fused exchange spins inside a grid that fills the GPU: only for ranks that own a GPU each (opt-in here,
-    // where the host may have put several ranks on one device)
-    set_peer_pointers(h, d, bufs, true, env_switch("PBX_Z_FUSED", false));
+    set_peer_pointers(h, d, bufs, true);
     return PBX_OK;
 }
 

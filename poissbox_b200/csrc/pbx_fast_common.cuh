@@ -362,136 +362,6 @@ __device__ __forceinline__ void slab_load_messages(const ZOpen &zo, bool first, 
     }
 }
 
-// the same behind the flag of the fused exchange: peers have just stored these numbers into my memory
-// over NVLink, so they are read at the L2 (the point of coherence), never through L1
-__device__ __forceinline__ void slab_load_messages_cg(const ZOpen &zo, bool first, bool last,
-                                                      long long line, double (&lo9)[DIST_MSG],
-                                                      double (&up9)[DIST_MSG])
-{
-#pragma unroll
-    for (int a = 0; a < DIST_MSG; ++a) {
-        lo9[a] = first ? __ldcg(zo.from_lo + a * zo.nlines + line) : 0.0;
-        up9[a] = last ? __ldcg(zo.from_up + a * zo.nlines + line) : 0.0;
-    }
-}
-
-// ... and from the tile-major layout of the fused exchange: the nine numbers of the `lpg` lines of a
-// (tile, compute group) are contiguous, component by component, so that the sender's stores over NVLink are
-// whole 128-byte lines (base = first double of this (tile, group), li = my line among the group's)
-__device__ __forceinline__ void slab_load_messages_tile(const ZOpen &zo, bool first, bool last, long long base,
-                                                        int lpg, int li, double (&lo9)[DIST_MSG],
-                                                        double (&up9)[DIST_MSG])
-{
-#pragma unroll
-    for (int a = 0; a < DIST_MSG; ++a) {
-        lo9[a] = first ? __ldcg(zo.from_lo + base + a * lpg + li) : 0.0;
-        up9[a] = last ? __ldcg(zo.from_up + base + a * lpg + li) : 0.0;
-    }
-}
-
-// Fused exchange, first leg: the two messages of a z line (the eighteen numbers ZOpen lists, what k_boundary
-// computes in a sweep of its own) from the chunks the z pass holds in registers anyway.  c = raw input of
-// the interpolation composite, ed = raw input of the derivative composite with its in-slab halos (zeros
-// beyond the slab).  Every thread sums its chunk -- bottom moments sum r^k u_k, sum k r^k u_k by Horner, top
-// recursion from zero state (fwd_local) -- chunk 0 of a line assembles the message for the lower rank from
-// the nlook bottom chunks, chunk T-1 the one for the upper rank by the look-back over the chunks below it.
-// The windows are the look-back's (r^(16 nlook) < 1e-17) instead of k_boundary's 48 / 24 planes.
-// The numbers are staged in shared memory ([direction][component][line of the group], slots 8..) and leave as
-// contiguous runs written by the whole compute group: 64-byte pieces from a quarter of the lanes ran the
-// NVLink stores at a fraction of their rate (first B200 run: z pass 104 -> 476 us).
-// slots 0..7 and the staging area; ends with a barrier, so all of them are free again on return
-constexpr int ZMSG_STAGE_SLOT = 8;
-template <class Bar>
-__device__ __forceinline__ void slab_make_messages(const CompositeCoef &M, const CompositeCoef &D,
-                                                   const Xchg &xc, const double (&c)[LC],
-                                                   const double (&ed)[LC + 6], int lpg, int li, long long base,
-                                                   double *__restrict__ dst_dn,
-                                                   double *__restrict__ dst_up, Bar bar)
-{
-    double *stage = xc.sm + ZMSG_STAGE_SLOT * NT;      // 2 x DIST_MSG x lpg doubles (lpg <= 64)
-    const bool first = xc.t == 0, last = xc.t == xc.T - 1;
-    double s[LC];
-    stencil<true>(D, ed, s);
-    double p = 0.0, q = 0.0, pD = 0.0, qD = 0.0;
-#pragma unroll
-    for (int k = LC - 1; k >= 0; --k) {
-        q = M.r * (q + p);
-        p = fma(M.r, p, c[k]);
-        qD = D.r * (qD + pD);
-        pD = fma(D.r, pD, s[k]);
-    }
-    double v0[LC], ey, ez, eyD, ezD;
-#pragma unroll
-    for (int k = 0; k < LC; ++k) v0[k] = c[k];
-    fwd_local(M.r, v0, ey, ez);
-    fwd_local(D.r, s, eyD, ezD);       // s now holds the zero-inflow solved values of the derivative input
-    xc.put(0, p);
-    xc.put(1, q);
-    xc.put(2, pD);
-    xc.put(3, qD);
-    xc.put(4, ey);
-    xc.put(5, ez);
-    xc.put(6, eyD);
-    xc.put(7, ezD);
-    bar();
-    if (first) {
-        double P = p, Q = q, PD = pD, QD = qD;
-#pragma unroll
-        for (int m = 1; m < MAXLOOK; ++m) {
-            const int qm = xc.nb(m);
-            if (m < M.nlook) {
-                const double pm = xc.get(0, qm), qmv = xc.get(1, qm);
-                P = fma(M.look[m], pm, P);
-                Q = fma(M.look[m], fma((double)(LC * m), pm, qmv), Q);
-            }
-            if (m < D.nlook) {
-                const double pm = xc.get(2, qm), qmv = xc.get(3, qm);
-                PD = fma(D.look[m], pm, PD);
-                QD = fma(D.look[m], fma((double)(LC * m), pm, qmv), QD);
-            }
-        }
-        stage[0 * lpg + li] = P;
-        stage[1 * lpg + li] = Q;
-        stage[2 * lpg + li] = PD;
-        stage[3 * lpg + li] = QD;
-        stage[4 * lpg + li] = ed[3];
-        stage[5 * lpg + li] = ed[4];
-        stage[6 * lpg + li] = ed[5];
-        stage[7 * lpg + li] = c[0];
-        stage[8 * lpg + li] = c[1];
-    }
-    if (last) {
-        double Y, Z, YD, ZD;
-        lookback(M, xc, 4, 5, -1, Y, Z);       // open line: chunks below the slab read as zero state
-        lookback(D, xc, 6, 7, -1, YD, ZD);
-        const double yt = fma(M.pw[LC - 1], Y, ey);
-        const double z0 = fma(M.pw[LC - 1], fma((double)LC, Y, Z), v0[LC - 1]);
-        const double z1 = fma(M.pw[LC - 2], fma((double)(LC - 1), Y, Z), v0[LC - 2]);
-        const double z2 = fma(M.pw[LC - 3], fma((double)(LC - 2), Y, Z), v0[LC - 3]);
-        const double yDt = fma(D.pw[LC - 1], YD, eyD);
-        const double zDt = fma(D.pw[LC - 1], fma((double)LC, YD, ZD), s[LC - 1]);
-        double *su = stage + DIST_MSG * lpg;
-        su[0 * lpg + li] = yt;
-        su[1 * lpg + li] = z0;
-        su[2 * lpg + li] = z1;
-        su[3 * lpg + li] = z2;
-        su[4 * lpg + li] = yDt;
-        su[5 * lpg + li] = zDt;
-        su[6 * lpg + li] = ed[LC + 2];
-        su[7 * lpg + li] = ed[LC + 1];
-        su[8 * lpg + li] = ed[LC];
-    }
-    bar();
-    const int per = DIST_MSG * lpg;
-    for (int i = xc.q; i < 2 * per; i += NT) {
-        if (i < per)
-            dst_dn[base + i] = stage[i];
-        else
-            dst_up[base + i - per] = stage[i];
-    }
-    bar();
-}
-
 template <class Bar>
 __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
                                                 const ZOpen &zo, const Xchg &xc,

@@ -276,161 +276,6 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
 }
 
 // ---------------------------------------------------------------------------------------------
-// z pass of a thin slab with the neighbour exchange fused into it.
-//
-// On eight GPUs a rank owns 64 planes of 512^3.  The separate boundary sweep (k_boundary_thin) re-reads
-// nearly both z inputs of the slab (236 MiB, 65-94 us beside 104 us of z pass), stores its 2 x 19 MB of
-// messages over NVLink in one burst, and a barrier kernel follows.  Here the z pass does all of it:
-// a CTA visits every one of its tiles TWICE, as leg A and one tile later as leg B,
-//
-//   A(i)   load tile i (HBM) -> the tile's messages from the chunks in registers (slab_make_messages)
-//          -> stored straight into the neighbours' receive arrays over NVLink -> release of the
-//          sequence number seq0 + i + 1 on the neighbours' flag of this (CTA, compute group)
-//   B(i)   load tile i again (it is in L2: the CTAs of one GPU have ~60 MB in flight between the two legs)
-//          -> acquire my two flags of this (CTA, compute group) -> the slab solve as before
-//
-// in the order A(0) A(1) B(0) A(2) B(1) ... so that a neighbour has a whole leg to deliver.  Every rank runs the
-// same grid over the same tiles (the host checks it), so my twin CTAs on the neighbours produce exactly the
-// lines I wait for; an A leg never waits on anybody, hence no cycle; the spins are bounded.  NVLink traffic is
-// spread over the whole pass and overlaps the HBM traffic; the 236 MiB of re-reads and two launches go.
-// ---------------------------------------------------------------------------------------------
-template <bool FUSE>
-__global__ void __launch_bounds__(NTHR_YZ, 1)
-z_slab_fused_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
-                    const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-                    double *__restrict__ out0, const double *__restrict__ pv, double *__restrict__ partials,
-                    const __grid_constant__ RedTail tail)
-{
-    extern __shared__ __align__(1024) unsigned char smraw[];
-    YZShared &S = *reinterpret_cast<YZShared *>(smraw);
-    const int tid = threadIdx.x;
-    if ((smem_u32(smraw) & 127u) != 0) __trap();
-    const int nmine = (int)blockIdx.x < p.ntiles ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nitems = 2 * nmine;
-    // item k of this CTA: leg (0 = A, 1 = B) and index i of the tile among mine
-    auto item = [&](int k, int &leg, int &i) {
-        if (k == 0) {
-            leg = 0;
-            i = 0;
-        } else if (k == nitems - 1) {
-            leg = 1;
-            i = nmine - 1;
-        } else if (k & 1) {
-            leg = 0;
-            i = (k + 1) >> 1;
-        } else {
-            leg = 1;
-            i = (k >> 1) - 1;
-        }
-    };
-    if (tid == 0) {
-        mbar_init(&S.full, 1);
-        mbar_init(&S.empty, NTHR_YZ);
-        fence_mbar_init();
-        if (nitems > 0) yz_issue_tile(S, p, &map0, &map1, blockIdx.x);
-    }
-    __syncthreads();
-
-    const int grp = tid >> 8, lt = tid & (NT - 1);
-    const int tx = lt & (XW - 1);
-    const int t = (lt >> 3) % p.T;
-    const int tz = lt / (XW * p.T);
-    const BarGroup bar{1 + grp};
-    const int npts = p.n;
-    Xchg xc{S.xchg[grp], lt, t, p.T, XW, 1, 0};
-    const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
-    const int fidx = (int)blockIdx.x * NGRP + grp;          // my flag on either neighbour, theirs on my board
-
-    for (int k = 0; k < nitems; ++k) {
-        int leg, i;
-        item(k, leg, i);
-        const int tile0 = (int)blockIdx.x + i * (int)gridDim.x;
-        const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
-        const TileId id{0, tile % p.ntx, tile / p.ntx};
-        const int xt8 = id.xt * NGRP + grp;
-        const int gt = id.gt;
-        const int x = xt8 * XW + tx;
-        const int g = gt * p.G + tz;
-        const bool live = (x < p.nx) && (g < p.ng);
-        const long long base = (long long)x + (long long)(t * LC) * p.sl + (long long)g * p.sg;
-        (void)live;   // fast_zslab_fused_ok: the brick is whole tiles, every thread owns a line
-        const int lpg = NT / p.T, li = tz * XW + tx;                         // lines of a (tile, group); mine
-        const long long mbase = ((long long)tile * NGRP + grp) * DIST_MSG * lpg;   // its messages in either array
-
-        mbar_wait(&S.full, (uint32_t)(k & 1));
-        double a[LC], eb[LC + 6];
-        {
-            const double *ta = S.tile[0] + soff, *tb = S.tile[1] + soff;
-            const int i0 = t * LC;
-#pragma unroll
-            for (int q = 0; q < LC; ++q) a[q] = ta[(i0 + q) * p.se];
-#pragma unroll
-            for (int q = 0; q < LC; ++q) eb[q + 3] = tb[(i0 + q) * p.se];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                int il = i0 - 3 + q, ir = i0 + LC + q;
-                const bool lo = il < 0, hi = ir >= npts;
-                if (lo) il += npts;
-                if (hi) ir -= npts;
-                const double vl = tb[il * p.se], vr = tb[ir * p.se];
-                eb[q] = lo ? 0.0 : vl;          // open line: nothing beyond the slab
-                eb[LC + 3 + q] = hi ? 0.0 : vr;
-            }
-        }
-        mbar_arrive(&S.empty);
-        if (tid == 0 && k + 1 < nitems) {
-            int leg2, i2;
-            item(k + 1, leg2, i2);
-            mbar_wait(&S.empty, (uint32_t)(k & 1));
-            yz_issue_tile(S, p, &map0, &map1, (int)blockIdx.x + i2 * (int)gridDim.x);
-        }
-        const unsigned long long seq = zo.seq0 + (unsigned long long)i + 1ull;
-        if (leg == 0) {
-            slab_make_messages(p.M, p.D, xc, a, eb, lpg, li, mbase, zo.dst_dn, zo.dst_up, bar);
-            // the group's stores are ordered before the barrier that ended slab_make_messages; one thread
-            // publishes them: ONE fence at system scope (cumulative), then the two flags.  Not thread 0 of the
-            // CTA: it is the TMA producer, and the fence waits for the stores to be acknowledged over NVLink.
-            if (lt == 32) {
-                fence_sys();
-                st_relaxed_sys_u64(zo.flag_dn + fidx, seq);
-                st_relaxed_sys_u64(zo.flag_up + fidx, seq);
-            }
-        } else {
-            if (lt == 32) {
-                const long long t0 = spin_start();
-                while (ld_relaxed_sys_u64(zo.flag_lo + fidx) < seq || ld_relaxed_sys_u64(zo.flag_hi + fidx) < seq)
-                    spin_pause(t0);
-                (void)ld_acquire_sys(zo.flag_lo + fidx);   // one acquire per flag once both are up
-                (void)ld_acquire_sys(zo.flag_hi + fidx);
-            }
-            bar();
-            double lo9[DIST_MSG], up9[DIST_MSG];
-            slab_load_messages_tile(zo, t == 0, t == p.T - 1, mbase, lpg, li, lo9, up9);
-            double o[LC];
-            zpass_body_slab(p.M, p.D, zo, xc, lo9, up9, a, eb, o, bar);
-            double dot = 0.0;
-            if (live) {
-                if (pv != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < LC; ++q) {
-                        dot = fma(__ldg(pv + base + q * p.sl), o[q], dot);
-                        out0[base + q * p.sl] = o[q];
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < LC; ++q) out0[base + q * p.sl] = o[q];
-                }
-            }
-            if (pv != nullptr) {
-                double tot = block_sum_warps(dot, S.xchg[grp] + (Y_SLOTS - 1) * NT, lt, NT, bar);
-                if (lt == 0 && xt8 < p.ntx8) partials[gt * p.ntx8 + xt8] = tot;
-            }
-        }
-    }
-    if (FUSE) cgdev::red_tail<NTHR_YZ>(tail);
-}
-
-// ---------------------------------------------------------------------------------------------
 // x pass
 // ---------------------------------------------------------------------------------------------
 struct XT {
@@ -1073,19 +918,6 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
 
 bool fast_tma_available() { return encode_fn() != nullptr; }
 
-// the fused exchange needs the TMA z kernel on whole lines, and enough flags for the grid; it pays for thin
-// slabs only (every tile is visited twice: worth it while the boundary sweep it replaces costs as much as
-// the z pass itself, i.e. up to 128 planes)
-bool fast_zslab_fused_ok(const Brick &g)
-{
-    YZT p;
-    if (!encode_fn() || !yz_geometry_tma(g, 2, &p)) return false;
-    if (p.seg.nseg > 1 || NT % (XW * p.T) != 0 || p.T > 8 || p.T < 4) return false;
-    if (g.nx % XWT || g.ny % p.G) return false;     // whole tiles: the messages travel tile by tile
-    int grid = sm_count();
-    if (grid > p.ntiles) grid = p.ntiles;
-    return 2 * grid <= ZF_FLAGS;
-}
 
 // 2-D fp64 tensor map {dim0 (contiguous), dim1} with row stride `stride1_bytes` (a multiple of 16)
 bool tma_make_map_2d(CUtensorMap_st *m, const double *base, unsigned long long dim0, unsigned long long dim1,
@@ -1191,27 +1023,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     const bool fuse = tail && tail->on && dir == 2 && pvec && partials && !segd && !anyT && !rot;
-    if (zo.fused) {
-        // the exchange inside the z pass: same grid on every rank (fast_zslab_fused_ok)
-        if (dir != 2 || !zo.open || segd || anyT || 2 * grid > ZF_FLAGS) return PBX_ERR_ARG;
-        static std::atomic<bool> fattr[64];
-        if (!fattr[dev_ & 63]) {
-            const int a = cudaFuncAttributeMaxDynamicSharedMemorySize;
-            PBX_CUDA(cudaFuncSetAttribute(z_slab_fused_kernel<false>, (cudaFuncAttribute)a, (int)smem));
-            PBX_CUDA(cudaFuncSetAttribute(z_slab_fused_kernel<true>, (cudaFuncAttribute)a, (int)smem));
-            fattr[dev_ & 63] = true;
-        }
-        if (fuse) {
-            RedTail t = *tail;
-            t.part = partials;
-            t.cnt = t.stride = p.ntx8 * p.ngt;
-            t.narr = 1;
-            z_slab_fused_kernel<true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, pvec, partials, t);
-            if (tail_used) *tail_used = true;
-        } else {
-            z_slab_fused_kernel<false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, pvec, partials, RedTail());
-        }
-    } else if (fuse) {
+    if (fuse) {
         RedTail t = *tail;
         t.part = partials;
         t.cnt = t.stride = p.ntx8 * p.ngt;   // one partial sum per 8-wide sub-tile (fast_zpass_max_partials)

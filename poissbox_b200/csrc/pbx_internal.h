@@ -160,20 +160,7 @@ struct ZOpen {
     double gw[2] = {0, 0}, gx0[2] = {0, 0};
     double kwy[2] = {0, 0}, kwz[2] = {0, 0}, kxy[2] = {0, 0}, kxz[2] = {0, 0};
     double rinv = 0;                                // 1 / r of the interpolation recursion
-    // Exchange fused into the z pass (z_slab_fused_kernel, pbx_fast_tma.cu): the kernel computes a tile's
-    // messages itself, stores them into the neighbours' receive arrays (dst_*) and raises the flag of its
-    // (CTA, compute group) on their boards (flag_dn: the lower rank's `from_up` flags, flag_up: the upper
-    // rank's `from_lo` flags); it solves a tile once its own flags (flag_lo, flag_hi) carry the tile's
-    // sequence number seq0 + i + 1.  from_lo / from_up are then read behind that acquire, never through L1.
-    int fused = 0;
-    double *dst_dn = nullptr, *dst_up = nullptr;
-    unsigned long long *flag_dn = nullptr, *flag_up = nullptr;
-    const unsigned long long *flag_lo = nullptr, *flag_hi = nullptr;
-    unsigned long long seq0 = 0;
 };
-// flags of the fused exchange: one word per (CTA, compute group) and direction, behind the peer board
-constexpr int ZF_FLAGS = 1024;                      // >= 2 x the largest grid (one CTA per SM)
-constexpr unsigned long long ZF_SEQ_STRIDE = 1ull << 20;   // sequence numbers per MatMult (> tiles per CTA)
 
 // Peer boards (pbx_dist.cu): a small block of flags and records at the end of every rank's receive
 // buffer, stored into by the other ranks over NVLink peer mappings (or, for slab handles linked by
@@ -297,8 +284,6 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
                    double *B, int rev, long long *launches);
 // tail (z pass with a fused dot only): reduce the partial sums inside the kernel (RedTail); *tail_used
 // tells whether the launched kernel took it
-// can the z pass of this slab run with the exchange fused into it (zo.fused = 1)?
-bool fast_zslab_fused_ok(const Brick &g);
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
                     double *partials, const ZOpen &zo, int rev, long long *launches,
@@ -379,8 +364,8 @@ int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);
 void cg_free(pbx_handle_s *h);
 // z-slab decomposition over an NCCL communicator (or driven phase by phase by the caller)
 int dist_setup(pbx_handle_s *h, int rank, int nranks);
-int dist_phase1(pbx_handle_s *h, const double *f, bool boundary = true);
-int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials, bool fused = false);
+int dist_phase1(pbx_handle_s *h, const double *f);
+int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials);
 int dist_attach(pbx_handle_s *h);
 void dist_free(pbx_handle_s *h);
 int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, double *partials);

@@ -129,16 +129,6 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p)
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 // bounded spin: a peer that never shows up traps the kernel (after ~2 minutes) instead of hanging
 // the GPU for good

@@ -164,8 +164,6 @@ inline unsigned long long ld_acquire_sys(const unsigned long long *p)
 }
 inline void st_relaxed_sys(double *p, double v) { *(volatile double *)p = v; }
 inline double ld_relaxed_sys(const double *p) { return *(const volatile double *)p; }
-inline void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
-inline unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long spin_start() { return (long long)time(nullptr); }
 inline void spin_pause(long long t0)

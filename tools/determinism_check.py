@@ -10,6 +10,9 @@ import torch
 import poissbox_b200 as pbx
 
 shapes = [(16, 640, 1088), (32, 16, 2048), (64, 1024, 32), (512, 512, 32)]
+if len(sys.argv) > 1:   # shapes as nx,ny,nz ...
+    shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+REPS = int(os.environ.get("REPS", "30"))
 for nx, ny, nz in shapes:
     dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -20,7 +23,7 @@ for nx, ny, nz in shapes:
         h = pbx.Handle(nx, ny, nz, dx)
         os.environ.pop("PBX_NO_TMA"); os.environ.pop("PBX_TMA_YZ")
         first, bad, worst = None, 0, 0.0
-        for rep in range(30):
+        for rep in range(REPS):
             w, dot = h.lapl_dot(f)
             torch.cuda.synchronize()
             if first is None:
@@ -29,7 +32,7 @@ for nx, ny, nz in shapes:
                 bad += 1
                 worst = max(worst, (w - first[0]).abs().max().item() / first[0].abs().max().item())
         fam[name] = first
-        print(f"{(nx, ny, nz)} {name:8s}: {bad} of 29 repeats differ from the first run (worst field diff {worst:.2e})", flush=True)
+        print(f"{(nx, ny, nz)} {name:8s}: {bad} of {REPS - 1} repeats differ from the first run (worst field diff {worst:.2e})", flush=True)
         h.close()
     same = all(torch.equal(fam["tma"][0], v[0]) for v in fam.values())
     print(f"{(nx, ny, nz)} families agree on the field: {same}", flush=True)
