@@ -50,9 +50,10 @@ def test_emu_lapl_fast_and_reference(shape, no_tma):
 
 
 @pytest.mark.parametrize("shape", [(64, 32, 64), (16, 1024, 16), (16, 16, 656), (1024, 16, 16)])
-def test_emu_tma_and_generic_bit_identical(shape):
+def test_emu_tma_and_generic_bit_identical(shape, monkeypatch):
     """includes y / z lines of more than 512 points, which run as overlapping segments, and x lines
     of 1024 points (several warps per line in the TMA x kernel)"""
+    monkeypatch.setenv("PBX_TMA_SEG", "1")   # segmented TMA tiles: off by default on the GPU (open defect), logic kept under test
     dx = tuple(1.0 / n for n in shape)
     f = field(shape, 7)
     outs = []
@@ -446,6 +447,9 @@ def test_emu_lineop_tma_bit_identical(shape, monkeypatch):
     vec = np.asfortranarray(np.random.default_rng(32).uniform(-1, 1, shape + (3,)))
     lib = emu_lib.load()
     h = handle(shape, dx)
+    # segmented y / z lines: the TMA kernels are off by default (open defect on the B200, pbx_fast_tma.cu); the
+    # harness keeps exercising their logic
+    monkeypatch.setenv("PBX_TMA_SEG", "1")
     monkeypatch.setenv("PBX_LINEOP_TMA", "0")  # the generic line-operator kernels
     want = [h.grad(f), h.div(vec), h.interp(f), h.interp(f, +1)]
     monkeypatch.setenv("PBX_LINEOP_TMA", "1")
