@@ -874,12 +874,16 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     p->n = n;
     p->seg = seg_geometry(n / LC);
     p->T = p->seg.T;
-    // OPEN DEFECT (round 2, tools/determinism_check.py on the B200): with y or z lines of more than 512 points
-    // (segment tiles: eight wrapped 64-point boxes per field) the TMA y / z kernels return a wrong field on bricks
-    // that do not fit the L2 -- (48, 640, 1088) on every run, (32, 640, 1088) on 12 of 79, (16, 640, 1088) on 2 of
-    // 29 -- while the generic kernels, which share the arithmetic, and the CPU harness running these very kernels
-    // give the same bits every time; small bricks pass.  Not root-caused, so segmented lines stay on the generic
-    // kernels (same results, 0.60 against 0.59-0.63 of the roofline); PBX_TMA_SEG=1 re-enables the path for debugging.
+    // OPEN DEFECT (round 2, tools/determinism_check.py and tools/seg_defect_probe.py on the B200): with z lines of
+    // more than 512 points (segment tiles: eight wrapped 64-point boxes per field) the TMA z kernel WITH ITS FUSED DOT
+    // returns, in 10-30 % of the runs on bricks beyond the L2, a wrong field in one (tile, compute group): always the
+    // group of the TMA producer thread, starting at the segment's first interior chunk and decaying over ~10 chunks
+    // (a wrong incoming recursion state).  Without the dot (plain lapl) 0 of 53 runs fail; with the dot's loads of p
+    // removed 0 of 24; with the loads but without the reduction 3 of 24 -- i.e. the trigger is the timing the
+    // loads of p give the group's live warps, not the reduction.  The generic kernels (same arithmetic), the CPU
+    // harness running these very kernels, whole-line tiles (512^3: 0 of 29) and small bricks give the same bits every
+    // time.  Not root-caused, so segmented lines stay on the generic kernels (same results, 0.60 against 0.59-0.63
+    // of the roofline); PBX_TMA_SEG=1 re-enables the path for debugging.
     if (p->seg.nseg > 1 && !env_switch("PBX_TMA_SEG", false)) return false;
     // T divides 32 -- or the lines that fit leave some threads of the group without a chunk (any multiple
     // of 16 up to 512 points; 384^3: 51.6 instead of 37.4 GDoF/s on the generic kernels; PBX_TMA_ANY_T=0

@@ -10,7 +10,7 @@ import torch
 import poissbox_b200 as pbx
 
 os.environ["PBX_TMA_SEG"] = "1"
-shapes = [(48, 640, 1088), (48, 640, 512), (48, 512, 1088), (48, 1024, 512), (48, 512, 2048)]
+shapes = [(48, 640, 1088), (48, 640, 512), (48, 512, 1088)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for nx, ny, nz in shapes:
@@ -23,12 +23,15 @@ for nx, ny, nz in shapes:
     ref = hg.lapl(f)
     hg.close()
     h = pbx.Handle(nx, ny, nz, dx)
-    for rep in range(3):
-        out = h.lapl(f)
+    for rep in range(int(os.environ.get("REPS", "8"))):
+        if rep < 2:
+            out = h.lapl(f)
+        else:
+            out, _ = h.lapl_dot(f)     # the z pass with its fused dot; x pass walks back to front, y pass front to back
         torch.cuda.synchronize()
         bad = (out != ref)
         nbad = int(bad.sum().item())
-        line = f"{(nx, ny, nz)} rep {rep}: {nbad} of {out.numel()} values differ"
+        line = f"{(nx, ny, nz)} rep {rep} ({'lapl' if rep < 2 else 'lapl_dot'}): {nbad} of {out.numel()} values differ"
         if nbad:
             zc = bad.reshape(nz // 16, 16, ny, nx).any(dim=1).any(dim=1).any(dim=1).nonzero().flatten().tolist()
             yc = bad.reshape(nz, ny // 16, 16, nx).any(dim=2).any(dim=0).any(dim=1).nonzero().flatten().tolist()
