@@ -579,10 +579,34 @@ def run_ours(args):
                 true_rel = float(torch.sqrt(num / den).item())
                 del rres
                 cg["multigrid_pc"] = {"pc": "V(2,2) geometric multigrid on the 2nd-order star, damped Jacobi",
+                                      "stopping": "PETSc's default: preconditioned norm ||M^-1 r|| <= rtol ||M^-1 b||",
                                       "time_s": dtp, "its": its, "reason": reason,
                                       "rnorm_rel": rnorm / hist[0] if hist[0] else 0.0,
                                       "true_residual_rel": true_rel, "ms_per_it": dtp / max(1, its) * 1e3,
-                                      "speedup_vs_pc_none": dt / dtp, "gpu_launches": h2.launches - l1}
+                                      "gpu_launches": h2.launches - l1}
+                # the like-for-like figure: the same solve carried on until the TRUE residual ||A x - b|| / ||b|| is
+                # below the tolerance the unpreconditioned solve reaches (M ~ P^-1 weights smooth error, so the
+                # preconditioned norm is 2-3 orders of magnitude ahead of the true residual)
+                for rt in (1e-10, 3e-11, 1e-11, 3e-12):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    x, its, rnorm, reason, hist = h2.cg_solve(b, x, rtol=rt, maxit=args.cg_maxit)
+                    torch.cuda.synchronize()
+                    dte = time.perf_counter() - t0
+                    rres = h2.lapl(x) - b
+                    num = (rres * rres).sum()
+                    if world > 1:
+                        t = torch.tensor([dte], dtype=torch.float64, device=dev)
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                        dte = t.item()
+                        dist.all_reduce(num)
+                    tr = float(torch.sqrt(num / den).item())
+                    del rres
+                    if tr <= args.cg_rtol or rt == 3e-12:
+                        cg["multigrid_pc"]["equal_true_residual"] = {
+                            "rtol_on_preconditioned_norm": rt, "its": its, "reason": reason, "time_s": dte,
+                            "true_residual_rel": tr, "speedup_vs_pc_none": dt / dte}
+                        break
             except Exception as exc:   # the optional leg must never cost the headline line
                 cg["multigrid_pc"] = {"error": repr(exc)}
         h2.close()
