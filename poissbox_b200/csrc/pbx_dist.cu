@@ -228,44 +228,11 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
 {
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
-    double P = 0.0, Q = 0.0, rj = 1.0, c0 = 0.0, c1 = 0.0;
-    double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
-    const int top0 = nzl - BM;
-    // planes in blocks of eight, all loads of a block issued before its (serial) recurrences: one load
-    // in flight per thread left the sweep latency-bound (65 us for 236 MiB on a 64-plane slab of 512^2 lines)
-    constexpr int KB = 8;
-    double cb[KB], cn[KB];
-#pragma unroll
-    for (int u = 0; u < KB; ++u) cn[u] = __ldg(C + (long long)u * nlines + l);   // nzl >= 64
-    for (int j0 = 0; j0 < nzl; j0 += KB) {
-#pragma unroll
-        for (int u = 0; u < KB; ++u) {
-            cb[u] = cn[u];
-            const int jn = j0 + KB + u;
-            cn[u] = jn < nzl ? __ldg(C + (long long)jn * nlines + l) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < KB; ++u) {
-            const int j = j0 + u;
-            const double c = cb[u];
-            if (j < nzl) {
-                if (j < BM) {
-                    const double t = rj * c;
-                    P += t;
-                    Q = fma((double)j, t, Q);
-                    rj *= M.r;
-                    if (j == 0) c0 = c;
-                    if (j == 1) c1 = c;
-                }
-                if (j >= top0) {
-                    y = fma(M.r, y, c);
-                    z2 = z1;
-                    z1 = z;
-                    z = fma(M.r, z, y);
-                }
-            }
-        }
-    }
+    // Order of the work: the messages travel over NVLink (2 x 9 numbers per line, 38 MB per apply at 512^2 lines)
+    // and the link, not HBM, bounds this kernel when they all leave at the end of the sweep (round 2: 52 us on one
+    // GPU, 94 us with the peer stores).  So everything that does not need the long walk over C goes out FIRST --
+    // the derivative part (27 planes either side) and the raw planes, 12 of the 18 numbers -- and is in flight
+    // while the planes of C stream in; the bottom moments follow as soon as plane BM - 1 is through.
     {
         double w[BD + 3];
 #pragma unroll
@@ -277,15 +244,11 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
             QD = D.r * (QD + PD);
             PD = fma(D.r, PD, sj);
         }
-        msg_dn[0 * nlines + l] = P;
-        msg_dn[1 * nlines + l] = Q;
         msg_dn[2 * nlines + l] = PD;
         msg_dn[3 * nlines + l] = QD;
         msg_dn[4 * nlines + l] = w[0];
         msg_dn[5 * nlines + l] = w[1];
         msg_dn[6 * nlines + l] = w[2];
-        msg_dn[7 * nlines + l] = c0;
-        msg_dn[8 * nlines + l] = c1;
     }
     {
         double w[BD + 3];
@@ -298,16 +261,61 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
             yD = fma(D.r, yD, sj);
             zD = fma(D.r, zD, yD);
         }
-        msg_up[0 * nlines + l] = y;
-        msg_up[1 * nlines + l] = z;
-        msg_up[2 * nlines + l] = z1;
-        msg_up[3 * nlines + l] = z2;
         msg_up[4 * nlines + l] = yD;
         msg_up[5 * nlines + l] = zD;
         msg_up[6 * nlines + l] = w[BD + 2];
         msg_up[7 * nlines + l] = w[BD + 1];
         msg_up[8 * nlines + l] = w[BD];
     }
+    double P = 0.0, Q = 0.0, rj = 1.0;
+    double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
+    const int top0 = nzl - BM;
+    // planes in blocks of eight, all loads of a block issued before its (serial) recurrences: one load
+    // in flight per thread left the sweep latency-bound (65 us for 236 MiB on a 64-plane slab of 512^2 lines)
+    constexpr int KB = 8;
+    static_assert(BM % KB == 0, "the bottom moments are stored after a whole block of planes");
+    double cb[KB], cn[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) cn[u] = __ldg(C + (long long)u * nlines + l);   // nzl >= 64
+    for (int j0 = 0; j0 < nzl; j0 += KB) {
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            cb[u] = cn[u];
+            const int jn = j0 + KB + u;
+            cn[u] = jn < nzl ? __ldg(C + (long long)jn * nlines + l) : 0.0;
+        }
+        if (j0 == 0) {
+            msg_dn[7 * nlines + l] = cb[0];
+            msg_dn[8 * nlines + l] = cb[1];
+        }
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            const int j = j0 + u;
+            const double c = cb[u];
+            if (j < nzl) {
+                if (j < BM) {
+                    const double t = rj * c;
+                    P += t;
+                    Q = fma((double)j, t, Q);
+                    rj *= M.r;
+                }
+                if (j >= top0) {
+                    y = fma(M.r, y, c);
+                    z2 = z1;
+                    z1 = z;
+                    z = fma(M.r, z, y);
+                }
+            }
+        }
+        if (j0 == BM - KB) {
+            msg_dn[0 * nlines + l] = P;
+            msg_dn[1 * nlines + l] = Q;
+        }
+    }
+    msg_up[0 * nlines + l] = y;
+    msg_up[1 * nlines + l] = z;
+    msg_up[2 * nlines + l] = z1;
+    msg_up[3 * nlines + l] = z2;
 }
 
 // Neighbour barrier of the slab exchange over the peer boards: the boundary sweep that precedes this
@@ -586,7 +594,7 @@ int dist_allreduce_sum(pbx_handle_s *h, double *dev, int count)
 }
 
 // x and y sweeps (local) and the boundary sweep that produces the two neighbour messages
-int dist_phase1(pbx_handle_s *h, const double *f)
+int dist_phase1(pbx_handle_s *h, const double *f, int in_cg)
 {
     DistState *d = (DistState *)h->dist;
     if (!d) return PBX_ERR_ARG;
@@ -595,8 +603,14 @@ int dist_phase1(pbx_handle_s *h, const double *f)
     PBX_TRY(ensure_scratch(h, yseg ? 4 : 2));
     double **S = h->scratch;
     double *A = yseg ? S[2] : S[0], *B = yseg ? S[3] : S[1];
-    PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr));
-    PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr));
+    // tile order and the L2 as in lapl_fast: every pass starts where its producer has just finished (inside the CG the
+    // p-update wrote the input front to back).  A 64-plane slab of 512^2 lines is 134 MB per field against 126 MB
+    // of L2, so on the slabs of the 8-GPU run this is worth far more than at 512^3 (PBX_SLAB_L2_ORDER=0: all
+    // passes front to back, as in round 1)
+    const bool ordered = env_switch("PBX_SLAB_L2_ORDER", true);
+    const int xrev = (ordered && in_cg) ? 1 : 0, yrev = ordered ? 1 - xrev : 0;
+    PBX_TRY(fast_pass(h, 0, f, nullptr, A, B, nullptr, nullptr, nullptr, xrev));
+    PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr, nullptr, yrev));
     ++d->epoch;
     const int par = (int)(d->epoch & 1);
     // with peer mappings the messages are stored straight into the neighbours' receive arrays
@@ -764,7 +778,7 @@ int dist_lapl(pbx_handle_s *h, const double *f, double *out, const double *p, do
         set_last_error("FAST schedule needs 16-byte aligned fields");
         return PBX_ERR_ARG;
     }
-    PBX_TRY(dist_phase1(h, f));
+    PBX_TRY(dist_phase1(h, f, p != nullptr));
 #ifdef PBX_DEBUG   // timing experiments only: never in a release build (it skips required communication)
     static const bool skipx = getenv("PBX_DEBUG_NO_EXCHANGE") != nullptr;
     if (skipx) return dist_phase2(h, out, p, partials);

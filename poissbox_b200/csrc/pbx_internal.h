@@ -27,6 +27,14 @@ inline bool env_switch(const char *name, bool dflt)
     return e[0] != '0';
 }
 
+// integer-valued switch (bit masks of measurement variants)
+inline int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    if (!e || !e[0]) return dflt;
+    return atoi(e);
+}
+
 void set_last_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
@@ -364,7 +372,7 @@ int cg_lapl_dot(pbx_handle_s *h, const double *f, double *out, double *dot_dev);
 void cg_free(pbx_handle_s *h);
 // z-slab decomposition over an NCCL communicator (or driven phase by phase by the caller)
 int dist_setup(pbx_handle_s *h, int rank, int nranks);
-int dist_phase1(pbx_handle_s *h, const double *f);
+int dist_phase1(pbx_handle_s *h, const double *f, int in_cg = 0);
 int dist_phase2(pbx_handle_s *h, double *out, const double *p, double *partials);
 int dist_attach(pbx_handle_s *h);
 void dist_free(pbx_handle_s *h);

@@ -88,6 +88,11 @@ static inline T __ldg(const T *p)
     return *p;
 }
 template <class T>
+static inline T __ldcs(const T *p)
+{
+    return *p;
+}
+template <class T>
 static inline T __ldcg(const T *p)
 {
     return *(const volatile T *)p;
