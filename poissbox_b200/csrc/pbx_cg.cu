@@ -169,51 +169,6 @@ k_update_r(size_t N, double *__restrict__ r, const double *__restrict__ w, const
     if (tail.on) red_tail<VT>(tail);
 }
 
-// The same update walking the brick as the z pass leaves it in the L2: in pieces of 16 y rows of one plane, from
-// the LAST y rows (which the z pass, whose tiles advance along y, wrote last) down to the first, planes inner; w,
-// which nobody reads again, is loaded evict-first.  On a brick of about the size of the L2 (the 64-plane slabs of
-// the 8-GPU run: 134 MB per field) most of w is then still resident.  Every thread adds its elements in a fixed
-// order and the partials are summed as before, so the sums are reproducible run to run; their association
-// differs from k_update_r's.  nx, ny multiples of 16.  (PBX_UPDR_YFRONT=1)
-__global__ void __launch_bounds__(VT)
-k_update_r_yf(int nx, int ny, int nz, double *__restrict__ r, const double *__restrict__ w,
-              const double *__restrict__ sc, double *__restrict__ part, int np, const __grid_constant__ RedTail tail)
-{
-    __shared__ double sh[VT / 32];
-    if (sc[SC_STATUS] != 0.0) return;
-    const double a = sc[SC_A], m0 = sc[SC_M0];
-    const int E = 16 * nx;                               // elements of a piece (a multiple of 256)
-    const int tpu = (E + 2 * VT - 1) / (2 * VT);         // trips of 2 * VT elements per piece
-    const int nyb = ny / 16;
-    const long long ntrips = (long long)nyb * nz * tpu;
-    const size_t plane = (size_t)nx * ny;
-    double s1 = 0.0, s2 = 0.0;
-    for (long long q = blockIdx.x; q < ntrips; q += gridDim.x) {
-        const int trip = (int)(q % tpu);
-        const long long u = q / tpu;
-        const int z = (int)(u % nz), yb = nyb - 1 - (int)(u / nz);
-        const int e = trip * 2 * VT + 2 * (int)threadIdx.x;
-        if (e < E) {
-            const size_t i = (size_t)z * plane + (size_t)yb * E + e;
-            double2 rv = *reinterpret_cast<const double2 *>(r + i);
-            const double2 wv = __ldcs(reinterpret_cast<const double2 *>(w + i));
-            rv.x = fma(-a, wv.x, rv.x);
-            rv.y = fma(-a, wv.y, rv.y);
-            *reinterpret_cast<double2 *>(r + i) = rv;
-            const double t0 = rv.x - m0, t1 = rv.y - m0;
-            s1 += t0 + t1;
-            s2 = fma(t0, t0, fma(t1, t1, s2));
-        }
-    }
-    s1 = block_sum(s1, sh);
-    s2 = block_sum(s2, sh);
-    if (threadIdx.x == 0) {
-        part[blockIdx.x] = s1;
-        part[np + blockIdx.x] = s2;
-    }
-    if (tail.on) red_tail<VT>(tail);
-}
-
 // x += a p (iteration `itag`, if its step length was computed: also when that iteration converged or
 // hit a limit) ; p = (r - mean) + b p (while the solve is still running)
 __global__ void __launch_bounds__(VT)
@@ -693,8 +648,6 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
     int rc = PBX_OK;
     bool done = hs[SC_STATUS] != 0.0;
     int issued = 0;
-    const bool yfront = env_switch("PBX_UPDR_YFRONT", false) && h->nx % 16 == 0 && h->ny % 16 == 0 &&
-                        h->op != PBX_OPERATOR_STAR && (h->nranks > 1 || h->mode == PBX_MODE_FAST);
     while (!done && issued < maxit) {
         const int slot = issued & 1;
         rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2);
@@ -709,10 +662,7 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
         } else {
             tail = RedTail();
         }
-        if (yfront)
-            k_update_r_yf<<<nb, VT, 0, s>>>(h->nx, h->ny, h->nz, r, w, sc, part, np, tail);
-        else
-            k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np, tail);
+        k_update_r<<<nb, VT, 0, s>>>(N, r, w, sc, part, np, tail);
         ++h->launches;
         if (!tailed) {
             if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;

@@ -63,9 +63,7 @@ struct YZT {
     int rev;                  // 1: walk the tiles from the last to the first (L2 reuse, see lapl_fast)
     SegGeom seg;              // long lines: tile = (segment, x tile, line group), segment fastest
     int ngt;                  // line groups (tiles in the remaining direction)
-    unsigned long long hint;  // L2 cache policy of the tile loads (0: none), see l2_hints()
-    int dbg;                  // PBX_YZ_DBG (probe of the segmented-tile defect): 1 = the release of the tile buffers
-                              // depends on the values read from them, 2 = fence.proxy.async before the release
+    int dbg;                  // PBX_YZ_DBG=3: release the tile buffers without the proxy fence (timing only)
 };
 
 struct TileId {
@@ -105,13 +103,8 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
         if (i0 < 0) i0 += p.n;
         const int c1 = p.zdir ? g0 : i0, c2 = p.zdir ? i0 : g0;
         const int off = b * p.RB * p.se;
-        if (p.hint) {
-            tma_load_3d_hint(&S.tile[0][off], map0, &S.full, x0, c1, c2, p.hint);
-            tma_load_3d_hint(&S.tile[1][off], map1, &S.full, x0, c1, c2, p.hint);
-        } else {
-            tma_load_3d(&S.tile[0][off], map0, &S.full, x0, c1, c2);
-            tma_load_3d(&S.tile[1][off], map1, &S.full, x0, c1, c2);
-        }
+        tma_load_3d(&S.tile[0][off], map0, &S.full, x0, c1, c2);
+        tma_load_3d(&S.tile[1][off], map1, &S.full, x0, c1, c2);
     }
 }
 
@@ -236,18 +229,15 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                 eb[LC + 3 + k] = (cut && hi) ? 0.0 : vr;
             }
         }
-        if (p.dbg == 1) {
-            // probe: the arrival cannot be issued before every value read from the tile has landed
-            double chk = 0.0;
-#pragma unroll
-            for (int k = 0; k < LC; ++k) chk += a[k];
-#pragma unroll
-            for (int k = 0; k < LC + 6; ++k) chk += eb[k];
-            mbar_arrive(chk == 1.2345e300 ? &S.full : &S.empty);
-        } else {
-            if (p.dbg == 2) fence_proxy_async();
-            mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
-        }
+        // The release of the tile buffers.  fence.proxy.async FIRST: the mbarrier arrival does not wait for this
+        // thread's outstanding shared-memory loads (SASS: 38 LDS, then SYNCS.ARRIVE with no scoreboard wait in
+        // between), and the TMA writes it releases belong to the async proxy, which the arrival's release semantics
+        // do not order against generic-proxy reads.  Without the fence the next tile's boxes could land under loads
+        // still queued behind bank conflicts: round 2 saw exactly that with the segment tiles (one 64-row box of a
+        // (tile, group) read as the NEXT tile's data in 3 of 40 applies, tools/seg_defect_probe2.py; 0 of 40 with the
+        // fence, 0 of 40 with an arrival made data-dependent on every value read).
+        if (p.dbg != 3) fence_proxy_async();     // PBX_YZ_DBG=3: the unfenced release, for timing the fence only
+        mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty, (uint32_t)(it & 1));       // ... and neither does anybody else
             yz_issue_tile(S, p, &map0, &map1, tile0 + gridDim.x);
@@ -303,17 +293,8 @@ struct XT {
     int ntiles;               // tiles of 256 chunks (ANYT: of `rows` chunks)
     int rev;                  // 1: walk the tiles from the last to the first
     int rows;                 // ANYT: chunks per tile = the whole lines that fit into 256
-    unsigned long long hint;  // L2 cache policy of the tile loads (0: none)
+    int dbg;                  // PBX_YZ_DBG=3: release the tile buffer without the proxy fence (timing only)
 };
-
-__device__ __forceinline__ void x_load_tile(double *dst, const CUtensorMap *map, uint64_t *bar, int row,
-                                            unsigned long long hint)
-{
-    if (hint)
-        tma_load_2d_hint(dst, map, bar, 0, row, hint);
-    else
-        tma_load_2d(dst, map, bar, 0, row);
-}
 
 struct XShared {
     double tin[TILE_DOUBLES];
@@ -386,7 +367,7 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
         fence_mbar_init();
         if ((int)blockIdx.x < p.ntiles) {
             mbar_expect_tx(&S.full, tile_bytes);
-            x_load_tile(S.tin, &mapF, &S.full, (p.rev ? p.ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * rows, p.hint);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * rows);
         }
     }
     __syncthreads();
@@ -426,12 +407,13 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             ef[LC + 4] = r0.y;
             ef[LC + 5] = r1.x;
         }
+        if (p.dbg != 3) fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
         mbar_arrive(&S.empty);
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             const int nxt = tile0 + (int)gridDim.x;
             mbar_wait(&S.empty, (uint32_t)(it & 1));
             mbar_expect_tx(&S.full, tile_bytes);
-            x_load_tile(S.tin, &mapF, &S.full, (p.rev ? p.ntiles - 1 - nxt : nxt) * rows, p.hint);
+            tma_load_2d(S.tin, &mapF, &S.full, 0, (p.rev ? p.ntiles - 1 - nxt : nxt) * rows);
         }
 
         double va[LC], vb[LC];
@@ -580,6 +562,7 @@ lineop_yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ line
                 e[LC + 3 + k] = (SEG && hi) ? 0.0 : vr;
             }
         }
+        fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
         mbar_arrive(&S.empty[st]);
         if (tid == 0 && tile + 2 * (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty[st], par);
@@ -690,6 +673,7 @@ lineop_yz_tma_sum_kernel(const __grid_constant__ YZT p, const __grid_constant__ 
         lineop::stencil4(opA, e, va);
         lineop::solve1_chunk(opA.cc, xc, 0, va, bar);
         take(S.tile[1] + soff, e);
+        fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
         mbar_arrive(&S.empty);
         if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty, (uint32_t)(it & 1));
@@ -783,6 +767,7 @@ lineop_x_tma_kernel(const __grid_constant__ LXT p, const __grid_constant__ CUten
             e[LC + 4] = r0.y;
             e[LC + 5] = r1.x;
         }
+        fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
         mbar_arrive(&S.empty[st]);
         if (tid == 0 && tile + 2 * (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty[st], par);
@@ -883,15 +868,6 @@ bool make_map_x(CUtensorMap *m, const double *base, size_t nchunks, int rows = N
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// PBX_L2_HINTS (bit mask, measurement switch; default 3): 1 = the x pass loads its input evict-first, so that the
-// y pass, which starts where the x pass ends, finds more of A and B in the L2; 2 = the z pass loads C and D evict-first
-// (the residual update reads the z pass's output next).  Matters on bricks of about the size of the 126 MB L2 --
-// the 64-plane slabs of the 8-GPU run -- and is neutral at 512^3.
-int l2_hints()
-{
-    return env_int("PBX_L2_HINTS", 3);
-}
-
 int sm_count()
 {
     static int n = 0;
@@ -910,7 +886,6 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     if (n % LC || n < LC || (g.nx & 1)) return false;
     p->nx = g.nx;
     p->n = n;
-    p->hint = 0;
     p->dbg = env_int("PBX_YZ_DBG", 0);
     p->seg = seg_geometry(n / LC);
     p->T = p->seg.T;
@@ -1003,7 +978,7 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     p.rows = anyT ? (NT / T) * T : NT;
     p.ntiles = (int)((nchunks + p.rows - 1) / p.rows);
     p.rev = rev;
-    p.hint = (l2_hints() & 1) ? L2_EVICT_FIRST : 0;   // the input is not read again before the y pass has read A and B
+    p.dbg = env_int("PBX_YZ_DBG", 0);
     CUtensorMap mf, ma, mb;
     if (!make_map_x(&mf, f, nchunks, p.rows) || !make_map_x(&ma, A, nchunks, p.rows) ||
         !make_map_x(&mb, B, nchunks, p.rows))
@@ -1046,7 +1021,6 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     const bool anyT = NT % (XW * p.T) != 0;
     if (zo.open && anyT) return PBX_ERR_UNSUPPORTED;             // the slab look-back indexes directly
     p.rev = rev;
-    p.hint = (dir == 2 && (l2_hints() & 2)) ? L2_EVICT_FIRST : 0;   // C and D are dead after the z pass: keep w
     p.M = fc.M;
     p.D = fc.D[dir];
     const bool segd = p.seg.nseg > 1;

@@ -82,29 +82,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// The same loads with an L2 cache policy (the 64-bit encodings createpolicy.fractional produces for a
-// fraction of 1.0; L2_EVICT_FIRST marks a stream that nobody reads again soon, so that it does not push the
-// lines the NEXT kernel starts on out of the L2).
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_3d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
-                                                 int c1, int c2, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
-                                                 int c1, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

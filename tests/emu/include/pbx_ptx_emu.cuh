@@ -139,17 +139,6 @@ inline void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0
     mbar_complete_tx(bar, tma_box_bytes(map));
     pbx_emu::note_progress();
 }
-// cache policies have no functional effect
-constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-inline void tma_load_3d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint64_t)
-{
-    tma_load_3d(dst, map, bar, c0, c1, c2);
-}
-inline void tma_load_2d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t)
-{
-    tma_load_2d(dst, map, bar, c0, c1);
-}
 inline void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
 {
     const int c[3] = {c0, c1, 0};

@@ -522,18 +522,3 @@ def test_emu_fused_reduction_tails(monkeypatch):
     assert np.array_equal(out1, out0) and abs(dot1 - dot0) <= 1e-13 * abs(dot0)
     h.close()
 
-
-def test_emu_update_r_yfront(monkeypatch):
-    """PBX_UPDR_YFRONT=1: the residual update walks the brick in the order the z pass leaves it in the L2 (pieces of 16
-    y rows, last rows first); same iterations, same x to rounding (the partial sums associate differently)"""
-    for shape in ((16, 32, 16), (48, 16, 32)):
-        dx = tuple(2 * np.pi / s for s in shape)
-        b = orc.lapl(field(shape, 6), dx)
-        h = handle(shape, dx)
-        x0, it0, rn0, why0, hist0 = h.cg_solve(b, rtol=1e-6)
-        monkeypatch.setenv("PBX_UPDR_YFRONT", "1")
-        x1, it1, rn1, why1, hist1 = h.cg_solve(b, rtol=1e-6)
-        monkeypatch.delenv("PBX_UPDR_YFRONT")
-        assert (it1, why1) == (it0, why0)
-        assert np.allclose(hist1, hist0, rtol=1e-10) and np.max(np.abs(x1 - x0)) <= 1e-10 * np.max(np.abs(x0))
-        h.close()

@@ -1,7 +1,9 @@
-"""one GPU: the segmented TMA z tiles (PBX_TMA_SEG=1) under the probe variants of PBX_YZ_DBG -- 0: as built, 1: the
-release of the tile buffers depends on the values read from them, 2: fence.proxy.async before the release.  The output
-field is pre-filled with NaN (a store that never happened shows as NaN) and compared with the generic kernels' (same
-arithmetic, same bits expected); the first failing z line of every variant is dumped for inspection."""
+"""one GPU: the segmented TMA z tiles under PBX_YZ_DBG -- 3: the tile buffers released WITHOUT fence.proxy.async (the
+kernels as they were until round 2: generic-proxy loads still queued when the async-proxy refill lands), 0: as built.
+(The run that found the cause, profiles/r2_seg_defect_rootcause.log, had 0 = unfenced, 1 = a release made data-dependent
+on every value read, 2 = the fence.)  The output field is pre-filled with NaN (a store that never happened would show as
+NaN) and compared with the generic kernels' (same arithmetic, same bits expected); the first failing z line of every
+variant is printed."""
 import os
 import sys
 
@@ -14,7 +16,7 @@ import poissbox_b200 as pbx
 os.environ["PBX_TMA_SEG"] = "1"
 shape = tuple(int(v) for v in sys.argv[1].split(",")) if len(sys.argv) > 1 else (48, 512, 1088)
 reps = int(os.environ.get("REPS", "40"))
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2").split(",")]
+variants = [int(v) for v in os.environ.get("VARIANTS", "3,0").split(",")]
 nx, ny, nz = shape
 dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
 g = torch.Generator(device="cuda").manual_seed(7)
@@ -57,9 +59,6 @@ for v in variants:
                     print("   ref", lr[max(0, k - 4):k + 12])
                     d = np.abs(lo - lr)
                     print("   |diff| by chunk", np.array([d[c * 16:(c + 1) * 16].max() for c in range(nz // 16)]))
-                np.savez(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", f"seg_probe2_v{v}.npz"),
-                         out=out[:, y0, (x0 // 16) * 16:(x0 // 16) * 16 + 16].cpu().numpy(),
-                         ref=ref[:, y0, (x0 // 16) * 16:(x0 // 16) * 16 + 16].cpu().numpy())
     print(f"{shape} PBX_YZ_DBG={v}: {fails} of {reps} lapl_dot runs differ from the generic kernels; {t / reps:.3f} ms per apply",
           flush=True)
     h.close()
