@@ -34,6 +34,12 @@ using namespace cgdev;
 
 namespace {
 
+// (iteration number, status) in one 8-byte word: the host must never see one without the other
+__host__ __device__ inline unsigned long long status_word(int itag, double status)
+{
+    return ((unsigned long long)(unsigned)itag << 16) | (unsigned long long)(unsigned)((int)status + 1024);
+}
+
 // each CTA owns a contiguous slice so that the summation order is fixed
 __device__ __forceinline__ void slice(size_t N, size_t *lo, size_t *hi)
 {
@@ -171,10 +177,15 @@ k_update_r(size_t N, double *__restrict__ r, const double *__restrict__ w, const
 
 // x += a p (iteration `itag`, if its step length was computed: also when that iteration converged or
 // hit a limit) ; p = (r - mean) + b p (while the solve is still running)
+// Thread 0 also posts (iteration number, status) as ONE word straight into the host's pinned status word: the host
+// follows the solve one iteration behind by reading that word, with no copy and no event in the stream (a
+// stream-ordered 200-byte cudaMemcpyAsync between two kernels cost ~5 us of idle GPU per iteration).
 __global__ void __launch_bounds__(VT)
 k_pupdate_x(size_t N, const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x,
-            const double *__restrict__ sc, int itag)
+            const double *__restrict__ sc, int itag, unsigned long long *__restrict__ host_word)
 {
+    if (host_word && blockIdx.x == 0 && threadIdx.x == 0)
+        *(volatile unsigned long long *)host_word = status_word(itag, sc[SC_STATUS]);
     const bool dox = sc[SC_XIT] == (double)itag, dop = sc[SC_STATUS] == 0.0;
     if (!dox && !dop) return;
     const double a = sc[SC_A], m = sc[SC_MEAN], b = sc[SC_B];
@@ -353,7 +364,8 @@ int cg_alloc(pbx_handle_s *h, int nhist)
         PBX_CUDA(cudaMalloc(&h->cg_scal, SC_COUNT * sizeof(double)));
         PBX_CUDA(cudaMalloc(&h->cg_ticket, sizeof(unsigned)));
         PBX_CUDA(cudaMemset(h->cg_ticket, 0, sizeof(unsigned)));
-        PBX_CUDA(cudaMallocHost(&h->cg_host, 2 * SC_COUNT * sizeof(double)));
+        // pinned and mapped: the last two doubles' worth is the status word k_pupdate_x posts into
+        PBX_CUDA(cudaHostAlloc(&h->cg_host, (2 * SC_COUNT + 2) * sizeof(double), cudaHostAllocMapped));
     }
     if (h->pc != PBX_PC_NONE && !h->cg_z) PBX_CUDA(cudaMalloc(&h->cg_z, N * sizeof(double)));
     if (nhist < 1) nhist = 1;
@@ -638,18 +650,18 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
 
     // The host runs one iteration ahead of the status it has seen: every kernel that changes
     // solver state checks the device status word first, so iterations issued after convergence
-    // are no-ops.
-    cudaEvent_t ev[2];
-    PBX_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    PBX_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    // are no-ops.  The status travels as one word that the p-update posts into pinned host memory.
     double *hs = h->cg_host;
+    volatile unsigned long long *hword = reinterpret_cast<volatile unsigned long long *>(hs + 2 * SC_COUNT);
+    unsigned long long *dword = nullptr;
+    PBX_CUDA(cudaHostGetDevicePointer((void **)&dword, (void *)(hs + 2 * SC_COUNT), 0));
+    *hword = 0;
     PBX_CUDA(cudaMemcpyAsync(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s));
     PBX_CUDA(cudaStreamSynchronize(s));
     int rc = PBX_OK;
     bool done = hs[SC_STATUS] != 0.0;
     int issued = 0;
     while (!done && issued < maxit) {
-        const int slot = issued & 1;
         rc = matmult_dot(h, p, w, sc + SC_PW, 1, 2);
         if (rc != PBX_OK) break;
         RedTail tail;
@@ -667,20 +679,30 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
         if (!tailed) {
             if ((rc = reduce_step(h, part, nb, np, 2, sc + SC_S1, 1, 3)) != PBX_OK) break;
         }
-        k_pupdate_x<<<vec_grid(N), VT, 0, s>>>(N, r, p, x, sc, issued + 1);
+        k_pupdate_x<<<vec_grid(N), VT, 0, s>>>(N, r, p, x, sc, issued + 1, dword);
         ++h->launches;
-        cudaMemcpyAsync(hs + slot * SC_COUNT, sc, SC_COUNT * sizeof(double),
-                        cudaMemcpyDeviceToHost, s);
-        cudaEventRecord(ev[slot], s);
         ++issued;
         if (issued >= 2) {
-            cudaEventSynchronize(ev[slot ^ 1]);
-            if (hs[(slot ^ 1) * SC_COUNT + SC_STATUS] != 0.0) done = true;
+            // wait for the word of iteration issued - 1 (bounded: a failed kernel ends the wait through the stream's
+            // error state, a finished stream through the word itself)
+            const unsigned long long want = (unsigned long long)(issued - 1);
+            unsigned long long wv;
+            long long spins = 0;
+            while (((wv = *hword) >> 16) < want) {
+                if ((++spins & 0xfff) == 0) {
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q != cudaErrorNotReady && ((*hword) >> 16) < want) {
+                        if (q == cudaSuccess) set_last_error("pbx_cg_solve: the status word never arrived");
+                        rc = q == cudaSuccess ? PBX_ERR_CUDA : cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+                        break;
+                    }
+                }
+            }
+            if (rc != PBX_OK) break;
+            if ((int)(wv & 0xffff) != 1024) done = true;
         }
     }
     cudaError_t e = cudaStreamSynchronize(s);
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
     if (rc != PBX_OK) return rc;
     PBX_CUDA(e);
     PBX_CUDA(cudaMemcpy(hs, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost));

@@ -221,6 +221,12 @@ k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
 // thread per z line walks the planes of C ONCE, upwards, feeding both the bottom moments (running
 // power of r instead of Horner's rule) and the top recursion: 64 planes read instead of 96.  Same
 // numbers as k_boundary to rounding; the derivative part is unchanged.
+// DOWN: the walk over C goes from the top plane to the bottom one -- the direction that starts on the planes the y
+// pass wrote last when it ran front to back (inside the CG), i.e. on what is still in the L2.  The top state is then
+// the four moment sums  y = sum r^m c(top-m),  z = sum (m+1) r^m c(top-m),  z' = sum m r^(m-1) c(top-m),
+// z'' = sum (m-1) r^(m-2) c(top-m)  over the same BM planes the recursion starts from zero state on, and the
+// bottom moments come by Horner's rule as in k_boundary: the same numbers to rounding.
+template <bool DOWN>
 __global__ void __launch_bounds__(128)
 k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
                 const __grid_constant__ CompositeCoef D, const double *__restrict__ C,
@@ -232,8 +238,8 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
     // and the link, not HBM, bounds this kernel when they all leave at the end of the sweep (round 2: 52 us on one
     // GPU, 94 us with the peer stores).  So everything that does not need the long walk over C goes out FIRST --
     // the derivative part (27 planes either side) and the raw planes, 12 of the 18 numbers -- and is in flight
-    // while the planes of C stream in; the bottom moments follow as soon as plane BM - 1 is through.
-    {
+    // while the planes of C stream in; what the walk completes half-way follows as soon as it is complete.
+    auto d_bottom = [&]() {
         double w[BD + 3];
 #pragma unroll
         for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)j * nlines + l);
@@ -249,8 +255,8 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
         msg_dn[4 * nlines + l] = w[0];
         msg_dn[5 * nlines + l] = w[1];
         msg_dn[6 * nlines + l] = w[2];
-    }
-    {
+    };
+    auto d_top = [&]() {
         double w[BD + 3];
 #pragma unroll
         for (int j = 0; j < BD + 3; ++j) w[j] = __ldg(Dd + (long long)(nzl - BD - 3 + j) * nlines + l);
@@ -266,6 +272,13 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
         msg_up[6 * nlines + l] = w[BD + 2];
         msg_up[7 * nlines + l] = w[BD + 1];
         msg_up[8 * nlines + l] = w[BD];
+    };
+    if (DOWN) {
+        d_top();
+        d_bottom();
+    } else {
+        d_bottom();
+        d_top();
     }
     double P = 0.0, Q = 0.0, rj = 1.0;
     double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
@@ -273,49 +286,95 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
     // planes in blocks of eight, all loads of a block issued before its (serial) recurrences: one load
     // in flight per thread left the sweep latency-bound (65 us for 236 MiB on a 64-plane slab of 512^2 lines)
     constexpr int KB = 8;
-    static_assert(BM % KB == 0, "the bottom moments are stored after a whole block of planes");
+    static_assert(BM % KB == 0, "the half-way messages are stored after a whole block of planes");
     double cb[KB], cn[KB];
+    if (!DOWN) {
 #pragma unroll
-    for (int u = 0; u < KB; ++u) cn[u] = __ldg(C + (long long)u * nlines + l);   // nzl >= 64
-    for (int j0 = 0; j0 < nzl; j0 += KB) {
+        for (int u = 0; u < KB; ++u) cn[u] = __ldg(C + (long long)u * nlines + l);   // nzl >= 64
+        for (int j0 = 0; j0 < nzl; j0 += KB) {
 #pragma unroll
-        for (int u = 0; u < KB; ++u) {
-            cb[u] = cn[u];
-            const int jn = j0 + KB + u;
-            cn[u] = jn < nzl ? __ldg(C + (long long)jn * nlines + l) : 0.0;
-        }
-        if (j0 == 0) {
-            msg_dn[7 * nlines + l] = cb[0];
-            msg_dn[8 * nlines + l] = cb[1];
-        }
+            for (int u = 0; u < KB; ++u) {
+                cb[u] = cn[u];
+                const int jn = j0 + KB + u;
+                cn[u] = jn < nzl ? __ldg(C + (long long)jn * nlines + l) : 0.0;
+            }
+            if (j0 == 0) {
+                msg_dn[7 * nlines + l] = cb[0];
+                msg_dn[8 * nlines + l] = cb[1];
+            }
 #pragma unroll
-        for (int u = 0; u < KB; ++u) {
-            const int j = j0 + u;
-            const double c = cb[u];
-            if (j < nzl) {
-                if (j < BM) {
-                    const double t = rj * c;
-                    P += t;
-                    Q = fma((double)j, t, Q);
-                    rj *= M.r;
-                }
-                if (j >= top0) {
-                    y = fma(M.r, y, c);
-                    z2 = z1;
-                    z1 = z;
-                    z = fma(M.r, z, y);
+            for (int u = 0; u < KB; ++u) {
+                const int j = j0 + u;
+                const double c = cb[u];
+                if (j < nzl) {
+                    if (j < BM) {
+                        const double t = rj * c;
+                        P += t;
+                        Q = fma((double)j, t, Q);
+                        rj *= M.r;
+                    }
+                    if (j >= top0) {
+                        y = fma(M.r, y, c);
+                        z2 = z1;
+                        z1 = z;
+                        z = fma(M.r, z, y);
+                    }
                 }
             }
+            if (j0 == BM - KB) {
+                msg_dn[0 * nlines + l] = P;
+                msg_dn[1 * nlines + l] = Q;
+            }
         }
-        if (j0 == BM - KB) {
-            msg_dn[0 * nlines + l] = P;
-            msg_dn[1 * nlines + l] = Q;
+        msg_up[0 * nlines + l] = y;
+        msg_up[1 * nlines + l] = z;
+        msg_up[2 * nlines + l] = z1;
+        msg_up[3 * nlines + l] = z2;
+    } else {
+        // m = nzl - 1 - j counts the planes from the top; rm = r^m, rm1 = r^(m-1), rm2 = r^(m-2)
+        double rm = 1.0, rm1 = 0.0, rm2 = 0.0;
+#pragma unroll
+        for (int u = 0; u < KB; ++u) cn[u] = __ldg(C + (long long)(nzl - 1 - u) * nlines + l);
+        for (int m0 = 0; m0 < nzl; m0 += KB) {
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                cb[u] = cn[u];
+                const int mn = m0 + KB + u;
+                cn[u] = mn < nzl ? __ldg(C + (long long)(nzl - 1 - mn) * nlines + l) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < KB; ++u) {
+                const int m = m0 + u, j = nzl - 1 - m;
+                const double c = cb[u];
+                if (m < nzl) {
+                    if (m < BM) {
+                        const double t = rm * c;
+                        y += t;
+                        z = fma((double)(m + 1), t, z);
+                        z1 = fma((double)m, rm1 * c, z1);
+                        z2 = fma((double)(m - 1), rm2 * c, z2);      // rm2 = 0 while m < 2
+                        rm2 = rm1;
+                        rm1 = rm;
+                        rm *= M.r;
+                    }
+                    if (j < BM) {
+                        Q = M.r * (Q + P);
+                        P = fma(M.r, P, c);
+                    }
+                    if (j == 1) msg_dn[8 * nlines + l] = c;
+                    if (j == 0) msg_dn[7 * nlines + l] = c;
+                }
+            }
+            if (m0 == BM - KB) {
+                msg_up[0 * nlines + l] = y;
+                msg_up[1 * nlines + l] = z;
+                msg_up[2 * nlines + l] = z1;
+                msg_up[3 * nlines + l] = z2;
+            }
         }
+        msg_dn[0 * nlines + l] = P;
+        msg_dn[1 * nlines + l] = Q;
     }
-    msg_up[0 * nlines + l] = y;
-    msg_up[1 * nlines + l] = z;
-    msg_up[2 * nlines + l] = z1;
-    msg_up[3 * nlines + l] = z2;
 }
 
 // Neighbour barrier of the slab exchange over the peer boards: the boundary sweep that precedes this
@@ -618,8 +677,11 @@ int dist_phase1(pbx_handle_s *h, const double *f, int in_cg)
     double *dst_up = d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up;
     static const bool thin_ok = getenv("PBX_NO_THIN_BOUNDARY") == nullptr;
     if (thin_ok && h->nz < 2 * BM) {
-        k_boundary_thin<<<(unsigned)((d->nlines + 127) / 128), 128, 0, h->stream>>>(
-            d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
+        const unsigned nb = (unsigned)((d->nlines + 127) / 128);
+        if (yrev == 0 && ordered)   // the y pass ended on the top planes: walk down from there
+            k_boundary_thin<true><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
+        else
+            k_boundary_thin<false><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
     } else {
         dim3 grid((unsigned)((d->nlines + 127) / 128), 2);
         k_boundary<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn,

@@ -63,7 +63,6 @@ struct YZT {
     int rev;                  // 1: walk the tiles from the last to the first (L2 reuse, see lapl_fast)
     SegGeom seg;              // long lines: tile = (segment, x tile, line group), segment fastest
     int ngt;                  // line groups (tiles in the remaining direction)
-    int dbg;                  // PBX_YZ_DBG=3: release the tile buffers without the proxy fence (timing only)
 };
 
 struct TileId {
@@ -236,7 +235,8 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         // still queued behind bank conflicts: round 2 saw exactly that with the segment tiles (one 64-row box of a
         // (tile, group) read as the NEXT tile's data in 3 of 40 applies, tools/seg_defect_probe2.py; 0 of 40 with the
         // fence, 0 of 40 with an arrival made data-dependent on every value read).
-        if (p.dbg != 3) fence_proxy_async();     // PBX_YZ_DBG=3: the unfenced release, for timing the fence only
+        // Cost at 512^3: 0.4 % of the apply (profiles/r2_fence_cost_and_seg_tma.log).
+        fence_proxy_async();
         mbar_arrive(&S.empty);   // this thread no longer needs the tile buffers
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             mbar_wait(&S.empty, (uint32_t)(it & 1));       // ... and neither does anybody else
@@ -293,7 +293,6 @@ struct XT {
     int ntiles;               // tiles of 256 chunks (ANYT: of `rows` chunks)
     int rev;                  // 1: walk the tiles from the last to the first
     int rows;                 // ANYT: chunks per tile = the whole lines that fit into 256
-    int dbg;                  // PBX_YZ_DBG=3: release the tile buffer without the proxy fence (timing only)
 };
 
 struct XShared {
@@ -407,7 +406,7 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
             ef[LC + 4] = r0.y;
             ef[LC + 5] = r1.x;
         }
-        if (p.dbg != 3) fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
+        fence_proxy_async();   // generic-proxy reads before the async-proxy refill, see yz_tma_kernel
         mbar_arrive(&S.empty);
         if (tid == 0 && tile0 + (int)gridDim.x < p.ntiles) {
             const int nxt = tile0 + (int)gridDim.x;
@@ -886,20 +885,14 @@ bool yz_geometry_tma(const Brick &g, int dir, YZT *p)
     if (n % LC || n < LC || (g.nx & 1)) return false;
     p->nx = g.nx;
     p->n = n;
-    p->dbg = env_int("PBX_YZ_DBG", 0);
     p->seg = seg_geometry(n / LC);
     p->T = p->seg.T;
-    // OPEN DEFECT (round 2, tools/determinism_check.py and tools/seg_defect_probe.py on the B200): with z lines of
-    // more than 512 points (segment tiles: eight wrapped 64-point boxes per field) the TMA z kernel WITH ITS FUSED DOT
-    // returns, in 10-30 % of the runs on bricks beyond the L2, a wrong field in one (tile, compute group): always the
-    // group of the TMA producer thread, starting at the segment's first interior chunk and decaying over ~10 chunks
-    // (a wrong incoming recursion state).  Without the dot (plain lapl) 0 of 53 runs fail; with the dot's loads of p
-    // removed 0 of 24; with the loads but without the reduction 3 of 24 -- i.e. the trigger is the timing the
-    // loads of p give the group's live warps, not the reduction.  The generic kernels (same arithmetic), the CPU
-    // harness running these very kernels, whole-line tiles (512^3: 0 of 29) and small bricks give the same bits every
-    // time.  Not root-caused, so segmented lines stay on the generic kernels (same results, 0.60 against 0.59-0.63
-    // of the roofline); PBX_TMA_SEG=1 re-enables the path for debugging.
-    if (p->seg.nseg > 1 && !env_switch("PBX_TMA_SEG", false)) return false;
+    // Lines of more than 512 points run as segment tiles (eight wrapped 64-point boxes per field).  Round 2 found these
+    // tiles returning a wrong (tile, group) in 10-30 % of the applies on large bricks; cause and fix are at the release
+    // of the tile buffers in yz_tma_kernel (proxy fence).  Since the fix: 0 of 250 applies differ from the generic
+    // kernels (profiles/r2_seg_defect_fix_confirm.log), and the TMA kernels are 12-17 % faster on such bricks
+    // (profiles/r2_fence_cost_and_seg_tma.log).  PBX_TMA_SEG=0 sends segmented lines to the generic kernels.
+    if (p->seg.nseg > 1 && !env_switch("PBX_TMA_SEG", true)) return false;
     // T divides 32 -- or the lines that fit leave some threads of the group without a chunk (any multiple
     // of 16 up to 512 points; 384^3: 51.6 instead of 37.4 GDoF/s on the generic kernels; PBX_TMA_ANY_T=0
     // turns it off)
@@ -978,7 +971,6 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     p.rows = anyT ? (NT / T) * T : NT;
     p.ntiles = (int)((nchunks + p.rows - 1) / p.rows);
     p.rev = rev;
-    p.dbg = env_int("PBX_YZ_DBG", 0);
     CUtensorMap mf, ma, mb;
     if (!make_map_x(&mf, f, nchunks, p.rows) || !make_map_x(&ma, A, nchunks, p.rows) ||
         !make_map_x(&mb, B, nchunks, p.rows))

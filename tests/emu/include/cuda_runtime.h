@@ -9,7 +9,7 @@
 #include "pbx_emu.h"
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600, cudaErrorNotSupported = 801 };
 typedef struct pbx_emu_stream *cudaStream_t;
 struct pbx_emu_event {
     std::chrono::steady_clock::time_point t;
@@ -82,6 +82,17 @@ static inline cudaError_t cudaMallocHost(T **p, size_t bytes)
 {
     return cudaMalloc(p, bytes);
 }
+enum { cudaHostAllocMapped = 2 };
+template <class T>
+static inline cudaError_t cudaHostAlloc(T **p, size_t bytes, unsigned)
+{
+    return cudaMalloc(p, bytes);
+}
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned)
+{
+    *d = h;   // one address space on the harness
+    return cudaSuccess;
+}
 static inline cudaError_t cudaFree(void *p)
 {
     pbx_emu::dev_free(p);
@@ -118,6 +129,7 @@ static inline cudaError_t cudaGetDevice(int *d)
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "pbx_emu error"; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)

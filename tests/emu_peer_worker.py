@@ -58,7 +58,8 @@ for name, fn, src, want in (("grad", h.grad, f, whole.grad(f)), ("div", h.div, v
     got = fn(np.asfortranarray(src[:, :, mine]))
     errs[name] = np.max(np.abs(got - want[:, :, mine])) / np.max(np.abs(want))
 # the fused z pass + dot + all-reduce
-_, dot = h.lapl_dot(np.asfortranarray(f[:, :, mine]))
+outd, dot = h.lapl_dot(np.asfortranarray(f[:, :, mine]))
+errs["lapl_of_dot"] = np.max(np.abs(outd - ref[:, :, mine])) / np.max(np.abs(ref))   # the in-CG tile order and sweep direction
 ref_dot = float(np.vdot(f, ref))
 errs["dot"] = abs(dot - ref_dot) / abs(ref_dot)
 # the stand-alone all-reduce: every rank must see the same bits

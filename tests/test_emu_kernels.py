@@ -53,7 +53,7 @@ def test_emu_lapl_fast_and_reference(shape, no_tma):
 def test_emu_tma_and_generic_bit_identical(shape, monkeypatch):
     """includes y / z lines of more than 512 points, which run as overlapping segments, and x lines
     of 1024 points (several warps per line in the TMA x kernel)"""
-    monkeypatch.setenv("PBX_TMA_SEG", "1")   # segmented TMA tiles: off by default on the GPU (open defect), logic kept under test
+    monkeypatch.setenv("PBX_TMA_SEG", "1")   # segmented TMA tiles (the default since the proxy-fence fix of round 2)
     dx = tuple(1.0 / n for n in shape)
     f = field(shape, 7)
     outs = []

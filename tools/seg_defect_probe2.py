@@ -1,9 +1,9 @@
-"""one GPU: the segmented TMA z tiles under PBX_YZ_DBG -- 3: the tile buffers released WITHOUT fence.proxy.async (the
-kernels as they were until round 2: generic-proxy loads still queued when the async-proxy refill lands), 0: as built.
-(The run that found the cause, profiles/r2_seg_defect_rootcause.log, had 0 = unfenced, 1 = a release made data-dependent
-on every value read, 2 = the fence.)  The output field is pre-filled with NaN (a store that never happened would show as
-NaN) and compared with the generic kernels' (same arithmetic, same bits expected); the first failing z line of every
-variant is printed."""
+"""one GPU: regression check of the segmented TMA z tiles -- the z pass with its fused dot, many applies, against the
+generic kernels (same arithmetic, same bits expected).  The output field is pre-filled with NaN, so a store that never
+happened would show as NaN.  History: until round 2 the tile buffers were released to the TMA refill without
+fence.proxy.async and 18 of 150 applies of (48, 512, 1088) returned one wrong 64-row box
+(profiles/r2_seg_defect_rootcause.log, profiles/r2_seg_defect_fix_confirm.log: PBX_YZ_DBG 3 = unfenced, 0 = fenced; the
+switch existed for those two runs only)."""
 import os
 import sys
 
@@ -13,10 +13,9 @@ import torch
 
 import poissbox_b200 as pbx
 
-os.environ["PBX_TMA_SEG"] = "1"
 shape = tuple(int(v) for v in sys.argv[1].split(",")) if len(sys.argv) > 1 else (48, 512, 1088)
 reps = int(os.environ.get("REPS", "40"))
-variants = [int(v) for v in os.environ.get("VARIANTS", "3,0").split(",")]
+variants = [0]
 nx, ny, nz = shape
 dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
 g = torch.Generator(device="cuda").manual_seed(7)
@@ -28,7 +27,6 @@ ref = hg.lapl(f)
 hg.close()
 out = torch.empty_like(ref)
 for v in variants:
-    os.environ["PBX_YZ_DBG"] = str(v)
     h = pbx.Handle(nx, ny, nz, dx)
     fails, dumped, t = 0, False, 0.0
     for rep in range(reps):
@@ -59,6 +57,6 @@ for v in variants:
                     print("   ref", lr[max(0, k - 4):k + 12])
                     d = np.abs(lo - lr)
                     print("   |diff| by chunk", np.array([d[c * 16:(c + 1) * 16].max() for c in range(nz // 16)]))
-    print(f"{shape} PBX_YZ_DBG={v}: {fails} of {reps} lapl_dot runs differ from the generic kernels; {t / reps:.3f} ms per apply",
+    print(f"{shape} {fails} of {reps} lapl_dot runs differ from the generic kernels; {t / reps:.3f} ms per apply",
           flush=True)
     h.close()
