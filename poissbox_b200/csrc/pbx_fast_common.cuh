@@ -362,6 +362,16 @@ __device__ __forceinline__ void slab_load_messages(const ZOpen &zo, bool first, 
     }
 }
 
+// ... as ONE array: a thread is chunk 0 or chunk T-1 of its line, never both (slabs hold at least four chunks), so
+// the message it does not need costs no registers
+__device__ __forceinline__ void slab_load_message(const ZOpen &zo, bool first, bool last, long long line,
+                                                  double (&m9)[DIST_MSG])
+{
+    const double *src = first ? zo.from_lo : zo.from_up;
+#pragma unroll
+    for (int a = 0; a < DIST_MSG; ++a) m9[a] = (first || last) ? __ldg(src + a * zo.nlines + line) : 0.0;
+}
+
 template <class Bar>
 __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
                                                 const ZOpen &zo, const Xchg &xc,

@@ -153,6 +153,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     Xchg xc{S.xchg[grp], lt, t, p.T, XW, (SLAB || segd) ? 1 : 0, dead ? 1 : 0};
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
+    double m9[DIST_MSG];   // slab: the message of the neighbour this thread's chunk touches (chunk 0: lower, T-1: upper)
     int it = 0;
     for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
         const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
@@ -169,9 +170,16 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         const bool live = (x < p.nx) && (g < p.ng) && sc.interior && !dead;
         const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
-        double lo9[DIST_MSG], up9[DIST_MSG];
-        if (SLAB)
-            slab_load_messages(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, lo9, up9);
+        // Slab: the neighbours' messages of THIS tile were loaded at the end of the previous iteration (below), when
+        // the chunk registers were free again: issued here they would cost a DRAM round trip per tile.
+        if (SLAB && it == 0)
+            slab_load_message(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, m9);
+        // Fused dot: p's rows of this tile on their way into the L2 while the tile is computed (one lane per 64-byte
+        // row segment); the loads themselves come after the last barrier, when there are registers for them.
+        if (ZPASS && pv != nullptr && live && tx == 0) {
+#pragma unroll
+            for (int k = 0; k < LC; ++k) prefetch_l2(pv + base + k * p.sl);
+        }
         mbar_wait(&S.full, (uint32_t)(it & 1));
         double a[LC], eb[LC + 6];
         if (ROT) {
@@ -252,11 +260,38 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                     out0[base + k * p.sl] = c[k];
                     out1[base + k * p.sl] = d[k];
                 }
+                if (zo.ymsg_dn != nullptr) {
+                    // slab: the raw planes of the neighbour messages leave from here (ZOpen, pbx_internal.h)
+                    const long long inpl = base - (long long)g * p.sg;
+                    if (g < 3) {
+                        double *m = zo.ymsg_dn + (4 + g) * zo.nlines + inpl;
+#pragma unroll
+                        for (int k = 0; k < LC; ++k) m[k * p.sl] = d[k];
+                    }
+                    if (g < 2) {
+                        double *m = zo.ymsg_dn + (7 + g) * zo.nlines + inpl;
+#pragma unroll
+                        for (int k = 0; k < LC; ++k) m[k * p.sl] = c[k];
+                    }
+                    if (g >= zo.ynz - 3) {
+                        double *m = zo.ymsg_up + (6 + (zo.ynz - 1 - g)) * zo.nlines + inpl;
+#pragma unroll
+                        for (int k = 0; k < LC; ++k) m[k * p.sl] = d[k];
+                    }
+                }
             }
         } else {
             double o[LC];
             if (SLAB) {
-                zpass_body_slab(p.M, p.D, zo, xc, lo9, up9, a, eb, o, bar);
+                zpass_body_slab(p.M, p.D, zo, xc, m9, m9, a, eb, o, bar);
+                // the next tile's messages (slab tiles are never segmented: TileId from the tile number)
+                const int nt0 = tile0 + (int)gridDim.x;
+                if (nt0 < p.ntiles) {
+                    const int ntile = p.rev ? p.ntiles - 1 - nt0 : nt0;
+                    const int nx_ = ((ntile % p.ntx) * NGRP + grp) * XW + tx, ng_ = (ntile / p.ntx) * p.G + tz;
+                    const bool nlive = (nx_ < p.nx) && (ng_ < p.ng) && !dead;
+                    slab_load_message(zo, t == 0, t == p.T - 1, nlive ? (long long)nx_ + (long long)p.nx * ng_ : 0, m9);
+                }
             } else {
                 zpass_body(p.M, p.D, xc, a, eb, o, bar);
             }
@@ -1012,6 +1047,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     if (zo.open && p.seg.nseg > 1) return PBX_ERR_UNSUPPORTED;   // the generic launcher reports it
     const bool anyT = NT % (XW * p.T) != 0;
     if (zo.open && anyT) return PBX_ERR_UNSUPPORTED;             // the slab look-back indexes directly
+    if (zo.open && p.T < 2) return PBX_ERR_UNSUPPORTED;          // a chunk is the first or the last of its line, not both
     p.rev = rev;
     p.M = fc.M;
     p.D = fc.D[dir];
@@ -1053,17 +1089,17 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
             yz_tma_kernel<true, false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, t);
         if (tail_used) *tail_used = true;
     } else if (anyT && dir == 1)
-        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
+        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (anyT)
         yz_tma_kernel<true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (rot && dir == 1)
-        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
+        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (rot)
         yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (dir == 1 && !segd)
-        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
+        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (dir == 1)
-        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, ZOpen(), m0, m1, out0, out1, nullptr, nullptr, RedTail());
+        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
     else if (zo.open)
         yz_tma_kernel<true, true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
     else if (!segd)

@@ -105,6 +105,12 @@ __device__ __forceinline__ void fence_mbar_init()
 }
 
 
+// bring the line holding p into the L2 (no register, no dependency: a later load finds it there)
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- system-scope flags in peer-mapped (NVLink) or local global memory -------------------------
 // A rank publishes data with plain stores followed by st_release_sys of a sequence number; the
 // owner of the memory spins on ld_acquire_sys of that word (its own L2 is the point of coherence

@@ -152,6 +152,8 @@ inline void fence_proxy_async() {}
 inline void fence_mbar_init() {}
 
 
+inline void prefetch_l2(const void *) {}
+
 // system-scope flags: the "peers" of the harness are other PROCESSES sharing the memory (mmap),
 // so these are real atomics; a spinning thread yields the CPU and gives up after two minutes
 inline void st_release_sys(unsigned long long *p, unsigned long long v)

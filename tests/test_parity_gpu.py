@@ -483,9 +483,40 @@ def test_tma_and_generic_kernels_bit_identical(shape):
         outs.append((w.clone(), dot.clone()))
         h.close()
     # (48, 640, 1088): a brick beyond the L2 with segmented y AND z lines -- the case in which the segmented TMA tiles
-    # returned wrong fields in round 2 (tools/determinism_check.py); such lines run on the generic kernels since
+    # returned wrong fields in round 2 until their buffers were released behind a proxy fence (test below)
     for o in outs[1:]:
         assert torch.equal(outs[0][0], o[0])
         # the per-CTA partial sums of p.Ap carry the same bits; the kernel that adds them up (the z pass's own
         # last CTA with 512 threads, or k_reduce with 256) associates them differently
         assert abs(outs[0][1].item() - o[1].item()) <= 1e-14 * abs(o[1].item())
+
+
+@pytest.mark.parametrize("shape", [(48, 512, 1088), (512, 512, 64)])
+def test_tma_tiles_repeatable(shape):
+    """Regression test of round 2's defect: tile buffers released to the TMA refill while shared-memory loads of them
+    were still queued returned, in 10-30 % of the applies of a large brick with segmented z lines, one 64-row box of the
+    NEXT tile (profiles/r2_seg_defect_rootcause.log).  Thirty applies of the z pass with its fused dot into a
+    NaN-filled field must all carry the generic kernels' bits."""
+    import torch
+
+    nx, ny, nz = shape
+    dx = (1.0 / nx, 1.0 / ny, 1.0 / nz)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f = torch.rand((nz, ny, nx), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    os.environ["PBX_NO_TMA"] = "1"
+    try:
+        hg = pbx.Handle(nx, ny, nz, dx)
+    finally:
+        os.environ.pop("PBX_NO_TMA", None)
+    ref = hg.lapl(f)
+    hg.close()
+    h = pbx.Handle(nx, ny, nz, dx)
+    out = torch.empty_like(ref)
+    bad = 0
+    for _ in range(30):
+        out.fill_(float("nan"))
+        h.lapl_dot(f, out)
+        torch.cuda.synchronize()
+        bad += int(not torch.equal(out, ref))
+    h.close()
+    assert bad == 0, f"{bad} of 30 applies differ from the generic kernels"
