@@ -149,7 +149,7 @@ __device__ __forceinline__ double sd_at(const CompositeCoef &D, const double *w,
 __global__ void __launch_bounds__(128)
 k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
            const __grid_constant__ CompositeCoef D, const double *__restrict__ C,
-           const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up, int raw)
+           const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up)
 {
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
@@ -178,13 +178,11 @@ k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
         msg_dn[1 * nlines + l] = Q;
         msg_dn[2 * nlines + l] = PD;
         msg_dn[3 * nlines + l] = QD;
-        if (raw) {   // else the y pass has sent the raw planes (ZOpen::ymsg_dn)
-            msg_dn[4 * nlines + l] = w[0];
-            msg_dn[5 * nlines + l] = w[1];
-            msg_dn[6 * nlines + l] = w[2];
-            msg_dn[7 * nlines + l] = c0;
-            msg_dn[8 * nlines + l] = c1;
-        }
+        msg_dn[4 * nlines + l] = w[0];
+        msg_dn[5 * nlines + l] = w[1];
+        msg_dn[6 * nlines + l] = w[2];
+        msg_dn[7 * nlines + l] = c0;
+        msg_dn[8 * nlines + l] = c1;
     } else {
         // ---- top planes: causal double recursion from zero state, BM (BD) planes below the top
         double y = 0.0, z = 0.0, z1 = 0.0, z2 = 0.0;
@@ -211,11 +209,9 @@ k_boundary(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
         msg_up[3 * nlines + l] = z2;
         msg_up[4 * nlines + l] = yD;
         msg_up[5 * nlines + l] = zD;
-        if (raw) {
-            msg_up[6 * nlines + l] = w[BD + 2];
-            msg_up[7 * nlines + l] = w[BD + 1];
-            msg_up[8 * nlines + l] = w[BD];
-        }
+        msg_up[6 * nlines + l] = w[BD + 2];
+        msg_up[7 * nlines + l] = w[BD + 1];
+        msg_up[8 * nlines + l] = w[BD];
     }
 }
 
@@ -234,7 +230,7 @@ template <bool DOWN>
 __global__ void __launch_bounds__(128)
 k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef M,
                 const __grid_constant__ CompositeCoef D, const double *__restrict__ C,
-                const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up, int raw)
+                const double *__restrict__ Dd, double *__restrict__ msg_dn, double *__restrict__ msg_up)
 {
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlines) return;
@@ -256,11 +252,9 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
         }
         msg_dn[2 * nlines + l] = PD;
         msg_dn[3 * nlines + l] = QD;
-        if (raw) {   // else the y pass has sent the raw planes (ZOpen::ymsg_dn)
-            msg_dn[4 * nlines + l] = w[0];
-            msg_dn[5 * nlines + l] = w[1];
-            msg_dn[6 * nlines + l] = w[2];
-        }
+        msg_dn[4 * nlines + l] = w[0];
+        msg_dn[5 * nlines + l] = w[1];
+        msg_dn[6 * nlines + l] = w[2];
     };
     auto d_top = [&]() {
         double w[BD + 3];
@@ -275,11 +269,9 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
         }
         msg_up[4 * nlines + l] = yD;
         msg_up[5 * nlines + l] = zD;
-        if (raw) {
-            msg_up[6 * nlines + l] = w[BD + 2];
-            msg_up[7 * nlines + l] = w[BD + 1];
-            msg_up[8 * nlines + l] = w[BD];
-        }
+        msg_up[6 * nlines + l] = w[BD + 2];
+        msg_up[7 * nlines + l] = w[BD + 1];
+        msg_up[8 * nlines + l] = w[BD];
     };
     if (DOWN) {
         d_top();
@@ -306,7 +298,7 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
                 const int jn = j0 + KB + u;
                 cn[u] = jn < nzl ? __ldg(C + (long long)jn * nlines + l) : 0.0;
             }
-            if (j0 == 0 && raw) {
+            if (j0 == 0) {
                 msg_dn[7 * nlines + l] = cb[0];
                 msg_dn[8 * nlines + l] = cb[1];
             }
@@ -369,8 +361,8 @@ k_boundary_thin(long long nlines, int nzl, const __grid_constant__ CompositeCoef
                         Q = M.r * (Q + P);
                         P = fma(M.r, P, c);
                     }
-                    if (j == 1 && raw) msg_dn[8 * nlines + l] = c;
-                    if (j == 0 && raw) msg_dn[7 * nlines + l] = c;
+                    if (j == 1) msg_dn[8 * nlines + l] = c;
+                    if (j == 0) msg_dn[7 * nlines + l] = c;
                 }
             }
             if (m0 == BM - KB) {
@@ -682,35 +674,21 @@ int dist_phase1(pbx_handle_s *h, const double *f, int in_cg)
     // with peer mappings the messages are stored straight into the neighbours' receive arrays
     double *dst_dn = d->peer_lo_recv_up[par] ? d->peer_lo_recv_up[par] : d->send_dn;
     double *dst_up = d->peer_up_recv_lo[par] ? d->peer_up_recv_lo[par] : d->send_up;
-    // The y pass sends the raw planes of the two messages itself (8 of the 18 numbers per line: they cross the link
-    // while the y pass runs, not in the sweep's burst); the generic y kernel does not, then the sweep does
-    // (PBX_SLAB_YMSG=0: always the sweep).
-    int raw = 1;
-    if (h->use_tma && h->use_tma_yz && env_switch("PBX_SLAB_YMSG", true)) {
-        ZOpen ym;
-        ym.ymsg_dn = dst_dn;
-        ym.ymsg_up = dst_up;
-        ym.nlines = d->nlines;
-        ym.ynz = h->nz;
-        const int rc = fast_yzpass_tma(h->stream, Brick{h->nx, h->ny, h->nz}, h->fc, 1, A, B, S[0], S[1], nullptr, nullptr,
-                                       ym, yrev, &h->launches, nullptr, nullptr);
-        if (rc == PBX_OK)
-            raw = 0;
-        else if (rc != PBX_ERR_UNSUPPORTED)
-            return rc;
-    }
-    if (raw) PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr, nullptr, yrev));
+    // (Sending the raw planes of the messages from the y pass instead -- 8 of the 18 numbers per line -- was built
+    // and measured on two B200: the y pass's stores over NVLink slowed it by more than the sweep gained, CG iteration
+    // 617 against 596 us; profiles/r2_slab_variants.md.)
+    PBX_TRY(fast_pass(h, 1, A, B, S[0], S[1], nullptr, nullptr, nullptr, yrev));
     static const bool thin_ok = getenv("PBX_NO_THIN_BOUNDARY") == nullptr;
     if (thin_ok && h->nz < 2 * BM) {
         const unsigned nb = (unsigned)((d->nlines + 127) / 128);
         if (yrev == 0 && ordered)   // the y pass ended on the top planes: walk down from there
-            k_boundary_thin<true><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up, raw);
+            k_boundary_thin<true><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
         else
-            k_boundary_thin<false><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up, raw);
+            k_boundary_thin<false><<<nb, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn, dst_up);
     } else {
         dim3 grid((unsigned)((d->nlines + 127) / 128), 2);
         k_boundary<<<grid, 128, 0, h->stream>>>(d->nlines, h->nz, h->fc.M, h->fc.D[2], S[0], S[1], dst_dn,
-                                                dst_up, raw);
+                                                dst_up);
     }
     ++h->launches;
     PBX_CUDA(cudaGetLastError());

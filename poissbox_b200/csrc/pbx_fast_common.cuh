@@ -286,10 +286,16 @@ __device__ __forceinline__ void ypass_body(const CompositeCoef &M, const Composi
 
 // z pass:  out = Mzz c + Dzz d.   slots: 8 (solve) + 6 (halo) = 14
 constexpr int Z_SLOTS = 14;
-template <class Bar>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `early` runs just before the last barrier: the caller's loads issued there (the rows of p for the fused dot) have
+// the barrier, the halo exchange and the last stencil to land, instead of a DRAM round trip after the last barrier
+template <class Bar, class Hook = NoHook>
 __device__ __forceinline__ void zpass_body(const CompositeCoef &M, const CompositeCoef &D,
                                            const Xchg &xc, const double (&c)[LC],
-                                           const double (&ed)[LC + 6], double (&out)[LC], Bar bar)
+                                           const double (&ed)[LC + 6], double (&out)[LC], Bar bar,
+                                           Hook early = Hook())
 {
     double v[2][LC];   // v0 = c, v1 = S_D d
     stencil<true>(D, ed, v[1]);
@@ -298,6 +304,7 @@ __device__ __forceinline__ void zpass_body(const CompositeCoef &M, const Composi
     const CompositeCoef *const cs[2] = {&M, &D};
     solve_chunks<2>(cs, xc, 0, v, bar);
     put_halo(xc, 8, v[0]);
+    early();
     bar();
     double e[LC + 6];
     get_halo(xc, 8, v[0], e);
@@ -372,13 +379,13 @@ __device__ __forceinline__ void slab_load_message(const ZOpen &zo, bool first, b
     for (int a = 0; a < DIST_MSG; ++a) m9[a] = (first || last) ? __ldg(src + a * zo.nlines + line) : 0.0;
 }
 
-template <class Bar>
+template <class Bar, class Hook = NoHook>
 __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const CompositeCoef &D,
                                                 const ZOpen &zo, const Xchg &xc,
                                                 const double (&lo9)[DIST_MSG],
                                                 const double (&up9)[DIST_MSG],
                                                 const double (&c)[LC], double (&ed)[LC + 6],
-                                                double (&out)[LC], Bar bar)
+                                                double (&out)[LC], Bar bar, Hook early = Hook())
 {
     const bool first = xc.t == 0, last = xc.t == xc.T - 1;
     // (i) true halos of the derivative input
@@ -493,6 +500,7 @@ __device__ __forceinline__ void zpass_body_slab(const CompositeCoef &M, const Co
         hh[1] = x1;
         hh[2] = x2;
     }
+    early();
     bar();
     double e[LC + 6];
     get_halo(xc, 8, v[0], e);

@@ -120,7 +120,8 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
 // FUSE (opt-in, PBX_FUSE_TAIL=1; z pass with the fused dot): the CTA that finishes last reduces the
 // partial sums of p.out, all-reduces them over the peer boards and runs the CG's scalar step
 // (cgdev::red_tail) -- compute and collective in ONE kernel, two launches fewer per iteration.
-template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT = false, bool FUSE = false>
+// DOT (z pass): the fused dot p . out -- a compile-time switch, so that the plain apply does not carry its registers.
+template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT = false, bool FUSE = false, bool DOT = false>
 __global__ void __launch_bounds__(NTHR_YZ, 1)
 yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
               const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
@@ -153,7 +154,6 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
     Xchg xc{S.xchg[grp], lt, t, p.T, XW, (SLAB || segd) ? 1 : 0, dead ? 1 : 0};
 
     const int soff = tz * p.sgm + grp * XW + tx;            // + i * se
-    double m9[DIST_MSG];   // slab: the message of the neighbour this thread's chunk touches (chunk 0: lower, T-1: upper)
     int it = 0;
     for (int tile0 = blockIdx.x; tile0 < p.ntiles; tile0 += gridDim.x, ++it) {
         const int tile = p.rev ? p.ntiles - 1 - tile0 : tile0;
@@ -170,16 +170,10 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
         const bool live = (x < p.nx) && (g < p.ng) && sc.interior && !dead;
         const long long base = (long long)x + (long long)(sc.chunk * LC) * p.sl + (long long)g * p.sg;
 
-        // Slab: the neighbours' messages of THIS tile were loaded at the end of the previous iteration (below), when
-        // the chunk registers were free again: issued here they would cost a DRAM round trip per tile.
-        if (SLAB && it == 0)
-            slab_load_message(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, m9);
-        // Fused dot: p's rows of this tile on their way into the L2 while the tile is computed (one lane per 64-byte
-        // row segment); the loads themselves come after the last barrier, when there are registers for them.
-        if (ZPASS && pv != nullptr && live && tx == 0) {
-#pragma unroll
-            for (int k = 0; k < LC; ++k) prefetch_l2(pv + base + k * p.sl);
-        }
+        // slab: the message of the neighbour this thread's chunk touches (chunk 0: lower, chunk T-1: upper), issued
+        // here so that the loads overlap the wait for the tile.  (Loading it one tile ahead was tried: no gain.)
+        double m9[DIST_MSG];
+        if (SLAB) slab_load_message(zo, t == 0, t == p.T - 1, live ? (long long)x + (long long)p.nx * g : 0, m9);
         mbar_wait(&S.full, (uint32_t)(it & 1));
         double a[LC], eb[LC + 6];
         if (ROT) {
@@ -260,47 +254,28 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                     out0[base + k * p.sl] = c[k];
                     out1[base + k * p.sl] = d[k];
                 }
-                if (zo.ymsg_dn != nullptr) {
-                    // slab: the raw planes of the neighbour messages leave from here (ZOpen, pbx_internal.h)
-                    const long long inpl = base - (long long)g * p.sg;
-                    if (g < 3) {
-                        double *m = zo.ymsg_dn + (4 + g) * zo.nlines + inpl;
-#pragma unroll
-                        for (int k = 0; k < LC; ++k) m[k * p.sl] = d[k];
-                    }
-                    if (g < 2) {
-                        double *m = zo.ymsg_dn + (7 + g) * zo.nlines + inpl;
-#pragma unroll
-                        for (int k = 0; k < LC; ++k) m[k * p.sl] = c[k];
-                    }
-                    if (g >= zo.ynz - 3) {
-                        double *m = zo.ymsg_up + (6 + (zo.ynz - 1 - g)) * zo.nlines + inpl;
-#pragma unroll
-                        for (int k = 0; k < LC; ++k) m[k * p.sl] = d[k];
-                    }
-                }
             }
         } else {
-            double o[LC];
-            if (SLAB) {
-                zpass_body_slab(p.M, p.D, zo, xc, m9, m9, a, eb, o, bar);
-                // the next tile's messages (slab tiles are never segmented: TileId from the tile number)
-                const int nt0 = tile0 + (int)gridDim.x;
-                if (nt0 < p.ntiles) {
-                    const int ntile = p.rev ? p.ntiles - 1 - nt0 : nt0;
-                    const int nx_ = ((ntile % p.ntx) * NGRP + grp) * XW + tx, ng_ = (ntile / p.ntx) * p.G + tz;
-                    const bool nlive = (nx_ < p.nx) && (ng_ < p.ng) && !dead;
-                    slab_load_message(zo, t == 0, t == p.T - 1, nlive ? (long long)nx_ + (long long)p.nx * ng_ : 0, m9);
+            double o[LC], pk[LC];
+            // fused dot: the rows of p are loaded just before the pass's last barrier (zpass_body's hook) -- after it
+            // they would cost a DRAM round trip per tile with every warp of the group waiting
+            auto load_p = [&]() {
+                if (DOT && live) {
+#pragma unroll
+                    for (int k = 0; k < LC; ++k) pk[k] = __ldg(pv + base + k * p.sl);
                 }
+            };
+            if (SLAB) {
+                zpass_body_slab(p.M, p.D, zo, xc, m9, m9, a, eb, o, bar, load_p);
             } else {
-                zpass_body(p.M, p.D, xc, a, eb, o, bar);
+                zpass_body(p.M, p.D, xc, a, eb, o, bar, load_p);
             }
             double dot = 0.0;
             if (live) {
-                if (pv != nullptr) {
+                if (DOT) {
 #pragma unroll
                     for (int k = 0; k < LC; ++k) {
-                        dot = fma(__ldg(pv + base + k * p.sl), o[k], dot);
+                        dot = fma(pk[k], o[k], dot);
                         out0[base + k * p.sl] = o[k];
                     }
                 } else {
@@ -308,7 +283,7 @@ yz_tma_kernel(const __grid_constant__ YZT p, const __grid_constant__ ZOpen zo,
                     for (int k = 0; k < LC; ++k) out0[base + k * p.sl] = o[k];
                 }
             }
-            if (pv != nullptr) {
+            if (DOT) {
                 // one partial per 8-wide sub-tile, numbered as the generic kernel numbers its CTAs;
                 // the warp sums go through the last exchange slot, which the z pass never uses
                 double tot = block_sum_warps(dot, S.xchg[grp] + (Y_SLOTS - 1) * NT, lt, NT, bar);
@@ -1036,6 +1011,24 @@ int fast_xpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, const do
     return PBX_OK;
 }
 
+// one instantiation of the y / z kernel: its shared-memory attribute (once per device) and its launch
+template <bool ZPASS, bool SLAB, bool SEG, bool ROT, bool ANYT, bool FUSE, bool DOT>
+static int launch_yz(cudaStream_t s, int grid, size_t smem, const YZT &p, const ZOpen &zo, const CUtensorMap &m0,
+                     const CUtensorMap &m1, double *out0, double *out1, const double *pv, double *partials,
+                     const RedTail &tail)
+{
+    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (!attr_set[dev_ & 63]) {
+        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<ZPASS, SLAB, SEG, ROT, ANYT, FUSE, DOT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev_ & 63] = true;
+    }
+    yz_tma_kernel<ZPASS, SLAB, SEG, ROT, ANYT, FUSE, DOT><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, pv, partials, tail);
+    return PBX_OK;
+}
+
 int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir, const double *in0,
                     const double *in1, double *out0, double *out1, const double *pvec,
                     double *partials, const ZOpen &zo, int rev, long long *launches, const RedTail *tail,
@@ -1057,55 +1050,43 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     CUtensorMap m0, m1;
     if (!make_map_yz(&m0, in0, g, p, rot) || !make_map_yz(&m1, in1, g, p, rot)) return PBX_ERR_UNSUPPORTED;
     const size_t smem = sizeof(YZShared);
-    static std::atomic<bool> attr_set[64];   // per device: the attribute belongs to the context
-    int dev_ = 0;
-    cudaGetDevice(&dev_);
-    if (!attr_set[dev_ & 63]) {
-        const int a = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, true, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, true, false>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<false, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, true, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        PBX_CUDA(cudaFuncSetAttribute(yz_tma_kernel<true, false, false, false, false, true>, (cudaFuncAttribute)a, (int)smem));
-        attr_set[dev_ & 63] = true;
-    }
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
-    const bool fuse = tail && tail->on && dir == 2 && pvec && partials && !segd && !anyT && !rot;
+    const bool dot = dir == 2 && pvec && partials;
+    const bool fuse = tail && tail->on && dot && !segd && !anyT && !rot;
+    RedTail t;
     if (fuse) {
-        RedTail t = *tail;
+        t = *tail;
         t.part = partials;
         t.cnt = t.stride = p.ntx8 * p.ngt;   // one partial sum per 8-wide sub-tile (fast_zpass_max_partials)
         t.narr = 1;
-        if (zo.open)
-            yz_tma_kernel<true, true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, t);
-        else
-            yz_tma_kernel<true, false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, t);
         if (tail_used) *tail_used = true;
-    } else if (anyT && dir == 1)
-        yz_tma_kernel<false, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
-    else if (anyT)
-        yz_tma_kernel<true, false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
-    else if (rot && dir == 1)
-        yz_tma_kernel<false, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
-    else if (rot)
-        yz_tma_kernel<true, false, false, true><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
-    else if (dir == 1 && !segd)
-        yz_tma_kernel<false, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
-    else if (dir == 1)
-        yz_tma_kernel<false, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, out1, nullptr, nullptr, RedTail());
-    else if (zo.open)
-        yz_tma_kernel<true, true, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
-    else if (!segd)
-        yz_tma_kernel<true, false, false, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
-    else
-        yz_tma_kernel<true, false, true, false><<<grid, NTHR_YZ, smem, s>>>(p, zo, m0, m1, out0, nullptr, pvec, partials, RedTail());
+    }
+#define PBX_YZ(Z, SL, SG, RO, AN, FU, DO) \
+    launch_yz<Z, SL, SG, RO, AN, FU, DO>(s, grid, smem, p, (Z) ? zo : ZOpen(), m0, m1, out0, (Z) ? nullptr : out1, (Z) ? pvec : nullptr, \
+                                         (Z) ? partials : nullptr, t)
+    int rc;
+    if (dir == 1) {
+        rc = anyT ? PBX_YZ(false, false, false, false, true, false, false)
+           : rot  ? PBX_YZ(false, false, false, true, false, false, false)
+           : segd ? PBX_YZ(false, false, true, false, false, false, false)
+                  : PBX_YZ(false, false, false, false, false, false, false);
+    } else if (dot) {
+        rc = fuse ? (zo.open ? PBX_YZ(true, true, false, false, false, true, true) : PBX_YZ(true, false, false, false, false, true, true))
+           : anyT ? PBX_YZ(true, false, false, false, true, false, true)
+           : rot  ? PBX_YZ(true, false, false, true, false, false, true)
+           : zo.open ? PBX_YZ(true, true, false, false, false, false, true)
+           : segd ? PBX_YZ(true, false, true, false, false, false, true)
+                  : PBX_YZ(true, false, false, false, false, false, true);
+    } else {
+        rc = anyT ? PBX_YZ(true, false, false, false, true, false, false)
+           : rot  ? PBX_YZ(true, false, false, true, false, false, false)
+           : zo.open ? PBX_YZ(true, true, false, false, false, false, false)
+           : segd ? PBX_YZ(true, false, true, false, false, false, false)
+                  : PBX_YZ(true, false, false, false, false, false, false);
+    }
+#undef PBX_YZ
+    PBX_TRY(rc);
     if (launches) ++*launches;
     PBX_CUDA(cudaGetLastError());
     return PBX_OK;

@@ -168,11 +168,6 @@ struct ZOpen {
     double gw[2] = {0, 0}, gx0[2] = {0, 0};
     double kwy[2] = {0, 0}, kwz[2] = {0, 0}, kxy[2] = {0, 0}, kxz[2] = {0, 0};
     double rinv = 0;                                // 1 / r of the interpolation recursion
-    // y pass of a slab (open == 0): where the raw planes of the two messages go -- planes 0..2 of D and 0..1 of C
-    // into rows 4..8 of the "down" message, planes nz-1..nz-3 of D into rows 6..8 of the "up" message -- so that they
-    // travel over NVLink while the y pass runs instead of in the boundary sweep's burst (nullptr: the sweep sends them)
-    double *ymsg_dn = nullptr, *ymsg_up = nullptr;
-    int ynz = 0;                                    // planes of the slab
 };
 
 // Peer boards (pbx_dist.cu): a small block of flags and records at the end of every rank's receive
