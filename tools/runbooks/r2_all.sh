@@ -1,6 +1,6 @@
 # Round 2, first GPU call (ONE B200, ~10 minutes): everything that was written after round 1's GPU budget
 # was spent, in order of importance, each step under its own timeout and in its own process.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/run_gpu_r2_all.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/runbooks/r2_all.sh'
 set -x
 mkdir -p gpurun_out
 # 1. the default path: GPU tests, smoke, the bench line (CG now 88 + 64 B/DoF per iteration)
@@ -20,7 +20,7 @@ cat gpurun_out/r2_bench_fuse.json
 # 4. tridsol batches, both layouts, generic against TMA tiles
 timeout 200 python tools/prof_ops.py 256 > gpurun_out/r2_prof_ops.log 2>&1; tail -8 gpurun_out/r2_prof_ops.log
 # 5. counters of the y / z passes (planes, bank conflicts, with and without PBX_YZ_ROT)
-bash tools/run_gpu_r2_zpass.sh
+bash tools/runbooks/r2_zpass.sh
 # 6. extents that are not 16 x a power of two: generic kernels against the TMA kernels (PBX_TMA_ANY_T=1)
 for anyt in 0 1; do
   PBX_TMA_ANY_T=$anyt timeout 120 python tools/prof_lapl.py --n 384 > gpurun_out/r2_anyt${anyt}_384.log 2>&1; tail -1 gpurun_out/r2_anyt${anyt}_384.log
