@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="global grid is n^3")
+    # `--grid`: the spelling to use under torchrun, whose own parser rejects `--n` as an ambiguous abbreviation
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=512, help="global grid is n^3")
     ap.add_argument("--no-cg", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -8,6 +8,6 @@ PBX_CHECK_CG_MAXIT=400 run 29555 tools/dist_check.py 512 > gpurun_out/r2o_dist_c
 run 29557 tools/dist_prof.py 512 > gpurun_out/r2o_dist_prof_w$W.log 2>&1; grep device gpurun_out/r2o_dist_prof_w$W.log
 run 29556 bench.py --gpus $W --no-cpu --quick > gpurun_out/r2o_bench_w$W.json 2> gpurun_out/r2o_bench_w$W.err
 grep '^{' gpurun_out/r2o_bench_w$W.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N', d['n_gpus'], 'GDoF/s', d['value'], 'ms', d['ms_per_step'], 'cg s', d['cg']['time_s'], 'its', d['cg']['its'], 'launches', d['cg']['gpu_launches'], 'parity', d['parity']['ok'], d['parity']['max_abs_err_over_max_ref'], 'e2e', d['e2e']['value'])"
-run 29558 bench.py --gpus $W --n 1024 --no-cpu --quick --cg-maxit 300 > gpurun_out/r2o_bench_1024_w$W.json 2> gpurun_out/r2o_bench_1024_w$W.err
+run 29558 bench.py --gpus $W --grid 1024 --no-cpu --quick --cg-maxit 300 > gpurun_out/r2o_bench_1024_w$W.json 2> gpurun_out/r2o_bench_1024_w$W.err
 grep '^{' gpurun_out/r2o_bench_1024_w$W.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('1024^3 N', d['n_gpus'], 'GDoF/s', d['value'], 'ms', d['ms_per_step'], 'cg s', d['cg']['time_s'], 'its', d['cg']['its'], 'ms/it', d['cg']['ms_per_it'], 'parity', d['parity']['ok'])"
 tail -n 3 gpurun_out/r2o_bench_1024_w$W.err
