@@ -670,7 +670,7 @@ def run_ours(args):
                        "parallelism": f"zslab{world}",
                        "rank_sync": ("n/a" if world == 1 else
                                      "peer boards (flag barrier + all-reduce in the CG's reduction kernel, no NCCL per iteration)"
-                                     if os.environ.get("PBX_PEER_SYNC") == "1" else
+                                     if pbx.LIB.pbx_peer_sync_active(h._h) == 1 else
                                      "peer stores of the boundary messages + ncclAllReduce (barrier, CG scalars)")},
             "parity": parity, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "cg": cg,

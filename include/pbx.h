@@ -153,6 +153,10 @@ int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *fro
 int pbx_slab_recv_bytes(pbx_handle h, size_t *bytes);
 int pbx_slab_recv_buffer(pbx_handle h, void **buf);
 int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n);
+/* 1 when the ranks of this handle synchronise and reduce over the peer boards (no NCCL call per apply / iteration),
+ * 0 when they go through NCCL (PBX_PEER_SYNC=0, PBX_NO_PEER=1, or peer mappings that could not be opened), negative
+ * error code for a handle without a decomposition.  Diagnostic: so that a host can report which path it timed. */
+int pbx_peer_sync_active(pbx_handle h);
 /* the exchange step alone (NCCL communicator or peer boards), and the CG's scalar all-reduce
  * (exposed for profiling the communication steps on their own) */
 int pbx_slab_exchange(pbx_handle h);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "pbx_slab_recv_bytes": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
     "pbx_slab_recv_buffer": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "pbx_slab_link_peers": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
+    "pbx_peer_sync_active": (c_int, [c_void_p]),
     "pbx_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int]),
     "pbx_dist_tables_host": (c_int, [c_int, c_double, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),
     "pbx_lapl_device": (c_int, [c_void_p, c_void_p, c_void_p]),

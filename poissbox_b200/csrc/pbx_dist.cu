@@ -978,6 +978,12 @@ int pbx_slab_recv_buffer(pbx_handle h, void **buf)
     return PBX_OK;
 }
 
+int pbx_peer_sync_active(pbx_handle h)
+{
+    if (!h || !h->dist) return -PBX_ERR_ARG;
+    return ((DistState *)h->dist)->peer_sync ? 1 : 0;
+}
+
 int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n)
 {
     if (!h || !h->dist || !bufs || n != h->nranks || n < 2) return PBX_ERR_ARG;
