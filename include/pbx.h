@@ -149,7 +149,7 @@ int pbx_slab_put_messages(pbx_handle h, const double *from_lo, const double *fro
  * its reduction kernels, and pbx_lapl_device / pbx_grad_device / ... / pbx_cg_solve_device work on
  * the handle as they do on one created with an NCCL communicator.  Each rank needs its own stream
  * and host thread: the kernels wait on the device for their peers.  (With a communicator,
- * PBX_PEER_SYNC=1 in the environment makes pbx_create set up the same thing over cudaIpc.) */
+ * pbx_create sets up the same thing over cudaIpc by default; PBX_PEER_SYNC=0 keeps the NCCL collectives.) */
 int pbx_slab_recv_bytes(pbx_handle h, size_t *bytes);
 int pbx_slab_recv_buffer(pbx_handle h, void **buf);
 int pbx_slab_link_peers(pbx_handle h, void *const *bufs, int n);

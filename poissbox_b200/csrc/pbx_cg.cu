@@ -418,7 +418,7 @@ __global__ void k_dot_generic(size_t N, const double *__restrict__ a, const doub
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
-// PBX_FUSE_TAIL=1: the reduction of the per-CTA partial sums, its all-reduce and the scalar step run in
+// Reduction tails (default; PBX_FUSE_TAIL=0 turns them off): the reduction of the per-CTA partial sums, its all-reduce and the scalar step run in
 // the tail of the kernel that wrote the partials (cgdev::red_tail) instead of in further launches.
 // Possible on one rank and with the peer boards (an NCCL all-reduce cannot be called from a kernel).
 bool make_tail(pbx_handle_s *h, double *dst, int guarded, int phase, RedTail *t)

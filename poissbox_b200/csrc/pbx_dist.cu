@@ -558,7 +558,7 @@ int dist_attach(pbx_handle_s *h)
         all_valid = all_valid && slots[q].valid == 1;
     }
     if (!all_valid) return PBX_OK;   // identical on every rank: the ncclSend/Recv path stays in place
-    // PBX_PEER_SYNC=1: map EVERY rank's buffer, so that the barrier of the exchange and the CG's
+    // Peer boards: map EVERY rank's buffer, so that the barrier of the exchange and the CG's
     // all-reduces run over the peer boards (no NCCL call inside an iteration); otherwise the two
     // neighbours only (messages by peer stores, a one-word ncclAllReduce as the barrier)
     // default since the 2- and 8-GPU runs of round 2 (8 GPUs, 512^3: exchange 19.2 -> 9.1 us, CG 0.775 -> 0.722 s);

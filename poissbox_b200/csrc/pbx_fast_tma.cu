@@ -117,7 +117,7 @@ __device__ __forceinline__ void yz_issue_tile(YZShared &S, const YZT &p, const C
 // ANYT (default for such lengths; PBX_TMA_ANY_T=0 falls back to the generic kernels): line lengths whose chunk count does not divide 32 -- the lines that
 // fit into a compute group leave threads without a chunk (`dead`); a compile-time switch, so that the
 // measured kernels do not carry the test.
-// FUSE (opt-in, PBX_FUSE_TAIL=1; z pass with the fused dot): the CTA that finishes last reduces the
+// FUSE (default, PBX_FUSE_TAIL=0 turns it off; z pass with the fused dot): the CTA that finishes last reduces the
 // partial sums of p.out, all-reduces them over the peer boards and runs the CG's scalar step
 // (cgdev::red_tail) -- compute and collective in ONE kernel, two launches fewer per iteration.
 // DOT (z pass): the fused dot p . out -- a compile-time switch, so that the plain apply does not carry its registers.
@@ -479,8 +479,8 @@ x_tma_kernel(const __grid_constant__ XT p, const __grid_constant__ CUtensorMap m
 // ONE compact line operator per launch (grad / div / interp of the FAST schedule, pbx_fast_lineop.cu)
 // with the data movement of the Laplacian passes.  A single input field leaves room for TWO tile
 // stages, so the tile after next is in flight while the current one is computed.  Arithmetic from
-// pbx_fast_lineop.cuh: same bits as the generic line-operator kernels.  Opt-in (PBX_LINEOP_TMA=1)
-// until measured.
+// pbx_fast_lineop.cuh: same bits as the generic line-operator kernels.  Default since round 2
+// (PBX_LINEOP_TMA=0: the generic kernels).
 // ---------------------------------------------------------------------------------------------
 struct LYZShared {
     double tile[2][YZ_TILE_DOUBLES];
@@ -1093,7 +1093,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
 }
 
 // one compact line operator along dir with the TMA-pipelined kernels; PBX_ERR_UNSUPPORTED: use the
-// generic kernel (not asked for with PBX_LINEOP_TMA=1, slab, unsupported shape).  out2 (y, z only):
+// generic kernel (PBX_LINEOP_TMA=0, slab, unsupported shape).  out2 (y, z only):
 // the other kind of operator (interpolation <-> derivative) on the same input goes there, in the same
 // launch.
 int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int stagger, double dx,
@@ -1162,7 +1162,7 @@ int fast_line_op_tma(cudaStream_t s, const Brick &g, int dir, OpKind kind, int s
     return PBX_OK;
 }
 
-// out = kindA(inA) + kindB(inB) along y or z in one launch (PBX_LINEOP_TMA=1); else PBX_ERR_UNSUPPORTED
+// out = kindA(inA) + kindB(inB) along y or z in one launch; PBX_ERR_UNSUPPORTED: the caller uses the generic kernels
 int fast_line_op_sum_tma(cudaStream_t s, const Brick &g, int dir, OpKind kindA, OpKind kindB, int stagger,
                          double dx, const double *inA, const double *inB, double *out, long long *launches)
 {
