@@ -1053,7 +1053,7 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
     int grid = sm_count();
     if (grid > p.ntiles) grid = p.ntiles;
     const bool dot = dir == 2 && pvec && partials;
-    const bool fuse = tail && tail->on && dot && !segd && !anyT && !rot;
+    const bool fuse = tail && tail->on && dot && !segd && !anyT;
     RedTail t;
     if (fuse) {
         t = *tail;
@@ -1072,7 +1072,9 @@ int fast_yzpass_tma(cudaStream_t s, const Brick &g, const FastCoefs &fc, int dir
            : segd ? PBX_YZ(false, false, true, false, false, false, false)
                   : PBX_YZ(false, false, false, false, false, false, false);
     } else if (dot) {
-        rc = fuse ? (zo.open ? PBX_YZ(true, true, false, false, false, true, true) : PBX_YZ(true, false, false, false, false, true, true))
+        rc = fuse ? (zo.open ? PBX_YZ(true, true, false, false, false, true, true)
+                     : rot   ? PBX_YZ(true, false, false, true, false, true, true)
+                             : PBX_YZ(true, false, false, false, false, true, true))
            : anyT ? PBX_YZ(true, false, false, false, true, false, true)
            : rot  ? PBX_YZ(true, false, false, true, false, false, true)
            : zo.open ? PBX_YZ(true, true, false, false, false, false, true)

@@ -522,3 +522,32 @@ def test_emu_fused_reduction_tails(monkeypatch):
     assert np.array_equal(out1, out0) and abs(dot1 - dot0) <= 1e-13 * abs(dot0)
     h.close()
 
+
+
+def test_emu_fused_tail_on_rotated_z_kernel(monkeypatch):
+    """512-point z lines run on the rotated-tile z kernel; with the reduction tail fused into it (default) the CG takes
+    the same iterations to the same x as with the reductions in launches of their own, in five launches per iteration
+    instead of nine"""
+    shape = (16, 16, 512)
+    dx = tuple(2 * np.pi / s for s in shape)
+    b = orc.lapl(field(shape, 8), dx)
+    h = handle(shape, dx)
+    lib = h.lib
+    lib.pbx_launch_count.restype = ctypes.c_longlong
+
+    def run(maxit):
+        l0 = lib.pbx_launch_count(h._h)
+        res = h.cg_solve(b, rtol=1e-30, maxit=maxit)
+        return res, lib.pbx_launch_count(h._h) - l0
+
+    out = {}
+    for ft in ("0", "1"):
+        monkeypatch.setenv("PBX_FUSE_TAIL", ft)
+        (_, _, _, _, _), n3 = run(3)
+        res, n6 = run(6)
+        out[ft] = (res, (n6 - n3) / 3)
+    (x0, it0, _, why0, hist0), per0 = out["0"]
+    (x1, it1, _, why1, hist1), per1 = out["1"]
+    assert (it1, why1) == (it0, why0) and (per0, per1) == (9, 5)
+    assert np.allclose(hist1, hist0, rtol=1e-12) and np.max(np.abs(x1 - x0)) <= 1e-12 * np.max(np.abs(x0))
+    h.close()
