@@ -689,6 +689,9 @@ int cg_solve(pbx_handle_s *h, const double *b, double *x, double rtol, double ab
             unsigned long long wv;
             long long spins = 0;
             while (((wv = *hword) >> 16) < want) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();   // the word arrives within an iteration (0.6-4 ms): be a polite spinner
+#endif
                 if ((++spins & 0xfff) == 0) {
                     const cudaError_t q = cudaStreamQuery(s);
                     if (q != cudaErrorNotReady && ((*hword) >> 16) < want) {

@@ -27,14 +27,6 @@ inline bool env_switch(const char *name, bool dflt)
     return e[0] != '0';
 }
 
-// integer-valued switch (bit masks of measurement variants)
-inline int env_int(const char *name, int dflt)
-{
-    const char *e = getenv(name);
-    if (!e || !e[0]) return dflt;
-    return atoi(e);
-}
-
 void set_last_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
