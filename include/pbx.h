@@ -245,6 +245,10 @@ int pbx_bwd_sweep_batch_device(int n, long long nlines, long long elem_stride,
  * x0 = 0, z = r - mean(r), preconditioned norm ||z||_2, converged when
  * ||z|| <= max(rtol*||z_0||, abstol), diverged at 1e4*||z_0|| or max_it.
  *   hist  may be NULL; else receives ||z|| for iterations 0..its (at most nhist values).
+ * The call returns when the solve has finished.  While it runs the host thread stays one iteration ahead of the
+ * device: every kernel that changes solver state checks the device status word, and the host learns the status from a
+ * single word the device posts into pinned, mapped host memory each iteration (no copy or event in the stream); the
+ * wait for that word is bounded by the stream's own state, so a failed kernel surfaces as PBX_ERR_CUDA, not as a hang.
  * ------------------------------------------------------------------------------------------- */
 int pbx_cg_solve_device(pbx_handle h, const double *b, double *x, double rtol, double abstol,
                         int maxit, int *its, double *rnorm, int *reason, double *hist, int nhist);
