@@ -165,8 +165,9 @@ def run_reference(args):
     rate64, _ = cpu_lapl_rate(64, cores, 1)
     budget = 120.0 / max(1, args.steps + args.warmup)
     n = 64
+    cap = int(os.environ.get("PBX_BENCH_REF_N", "0"))   # tests: cap the sample brick (tests/test_bench_contract.py)
     for cand in (96, 128, 192, 256, 384, 512):
-        if cand**3 / (rate64 * 1e9) <= budget and cand <= args.n:
+        if cand**3 / (rate64 * 1e9) <= budget and cand <= args.n and (cap <= 0 or cand <= cap):
             n = cand
     for _ in range(args.warmup):
         cpu_lapl_rate(n, cores, 1)
